@@ -1,0 +1,121 @@
+/*
+ * va_b200.h -- C-ABI of libva_b200.so: the B200-native (sm_100a) two-stream action-recognition forward path.
+ *
+ * The reference (arindamrc/video_analytics, Sheet03) is pure Python on stock PyTorch and exposes no FFI; the
+ * drop-in boundary is therefore its Python class API (see video_analytics_b200/{spatialModel,temporalModel,
+ * combinedModel}.py) and THIS header is what that Python layer binds with ctypes.  Every entry point names the
+ * reference lines whose work it replaces.  Conventions:
+ *   - plain pointers and sizes only; every data pointer is a BORROWED DEVICE pointer unless it says "host";
+ *   - every call is asynchronous on the caller's CUDA stream (va_stream_t == cudaStream_t, 0 = default stream);
+ *   - return value 0 = ok, non-zero = error; va_last_error() returns the message of the calling thread's last
+ *     failure.  There is no CPU fallback: without a CUDA device / the sm_100a image every call fails loudly;
+ *   - one va_handle per process+GPU+stream kind; a handle is not thread-safe.
+ */
+#ifndef VA_B200_H_
+#define VA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct va_handle va_handle;
+typedef void* va_stream_t; /* cudaStream_t */
+typedef int va_status;     /* 0 == VA_OK */
+
+enum { VA_OK = 0, VA_ERR_INVALID = 1, VA_ERR_CUDA = 2, VA_ERR_UNSUPPORTED = 3 };
+enum { VA_STREAM_SPATIAL = 0, VA_STREAM_TEMPORAL = 1 };
+
+const char* va_last_error(void);
+/* library/ABI version, bumped on any signature change */
+int va_abi_version(void);
+/* SM count of the current device (grid sizing in callers / bench) */
+va_status va_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Network handle.  Replaces SpatialNetwork.__init__ / TemporalNetwork.__init__ model construction
+ * (reference Sheet03/spatialModel.py:110-113,136-152; temporalModel.py:122-126,149-181): VGG16-D features
+ * (13x conv3x3+bias+ReLU, 5x maxpool2x2) + classifier 25088-4096-4096-desc_dim-n_classes.
+ *   in_channels: 3 (spatial) or 2*L = 20 (temporal).  max_batch: snippets per internal chunk (workspace size).
+ * --------------------------------------------------------------------------------------------------------- */
+va_status va_create(va_handle** out, int stream_kind, int in_channels, int n_classes, int desc_dim, int max_batch);
+va_status va_destroy(va_handle* h);
+
+/* channels the NHWC bf16 network input must be padded to for this handle (16 for 3, 32 for 20) */
+int va_input_channels_padded(const va_handle* h);
+
+/* Load the reference state_dict.  `tensors` is a HOST array of 34 DEVICE pointers to fp32 tensors in the
+ * reference's state_dict order (features.{0,2,5,7,10,12,14,17,19,21,24,26,28}.{weight,bias} as OIHW / [O],
+ * classifier.{0,3,6,9}.{weight,bias} as [out,in] / [out]); cf. spatialModel.py:256-261 (checkpoint "model").
+ * Packs conv weights to [tap][Cout][Cin_pad] bf16, FC1..3 to bf16 (FC1 columns permuted from the reference's
+ * NCHW flatten order c*49+h*7+w, spatialModel.py:172, to NHWC), FC4 kept fp32. */
+va_status va_load_weights(va_handle* h, const void* const* tensors, int n_tensors, va_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1 fused snippet preprocess.  Replaces the per-item CPU pipeline RandomCrop(224) + RandomHorizontalFlip +
+ * ToTensor + Normalize (reference utils.py:137-151) applied in SpatialDataset.__getitem__
+ * (spatialModel.py:64-81) and, once per flow image, in TemporalDataset.__getitem__ (temporalModel.py:67-92),
+ * including the x/y interleaved stacking of 2L flow images (temporalModel.py:80-90).
+ *   images:      u8 image store; image `id` starts at images + id*image_bytes, layout [img_h][img_w][img_c]
+ *   index_table: int32 [n][planes][4] = {image id, crop_i (top), crop_j (left), flip}; planes = 1 (RGB image
+ *                with img_c = 3) or 2L (one 1-channel image per output channel)
+ *   mean/std:    HOST float arrays [planes*img_c], applied as ((u8/255) - mean) / std in IEEE fp32
+ *   out_mode 0:  bf16 NHWC [n][crop][crop][c_pad] (padding channels zero) -- the network input
+ *   out_mode 1:  fp32 NCHW [n][planes*img_c][crop][crop]                  -- the reference tensor, bit-exact
+ * --------------------------------------------------------------------------------------------------------- */
+va_status va_preprocess(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                        const int32_t* index_table, int n, int planes, int crop, const float* mean,
+                        const float* std, int c_pad, int out_mode, void* out, va_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Network forward (eval mode).  Replaces the inlined forward of validate()
+ * (spatialModel.py:212-221, temporalModel.py:241-250): features -> flatten -> classifier[:9] -> featureVectors
+ * -> classifier[9] -> logits -> argmax; plus softmax class scores (notes.txt:113-116).
+ *   in_nhwc: bf16 [n][224][224][c_pad] from va_preprocess.  Any output pointer may be NULL.
+ *   descriptors fp32 [n][desc_dim]; logits fp32 [n][n_classes]; probs fp32 [n][n_classes]; pred int32 [n]
+ *   (0-based index of the first maximum, torch semantics).
+ * --------------------------------------------------------------------------------------------------------- */
+va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptors, float* logits, float* probs,
+                     int32_t* pred, va_stream_t stream);
+
+/* Layer primitives behind va_forward, exported for per-layer parity tests and profiling.
+ * conv: x bf16 NHWC [n][H][W][cin_pad]; w fp32 OIHW [cout][cin][ks][ks]; y bf16 NHWC [n][H(/2)][W(/2)][cout].
+ *       ks in {1,3}, stride 1, zero pad (ks-1)/2; optional fused ReLU and 2x2/2 max-pool.
+ *       force_bn in {0 (auto),64,128,256}; force_r in {0 (auto),1,3} select kernel variants.
+ * linear: x bf16 [n][in]; w fp32 [out][in]; y bf16 [n][out] and/or y_f32 fp32 [n][out] (exactly one). */
+va_status va_conv2d_nhwc(const void* x, int n, int H, int W, int cin, int cin_pad, const float* w,
+                         const float* bias, int cout, int ks, int relu, int pool, void* y, int force_bn,
+                         int force_r, va_stream_t stream);
+va_status va_linear(const void* x, int n, int in_features, const float* w, const float* bias, int out_features,
+                    int relu, void* y_bf16, float* y_f32, int force_bn, va_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K4 per-video consensus + late fusion.  Replaces the AverageMeter loop (spatialModel.py:223-228,
+ * utils.py:154-171: sequential fp32 sum in snippet order, then / count), combineDescriptors
+ * (combinedModel.py:9-26: [spatial 256 | temporal 256]) and LinearSVC.predict (combinedModel.py:38:
+ * argmax_c X.W[c] + b[c] in fp64), plus the score-averaging protocol of notes.txt:113-116,121-124,225-230.
+ *   desc_s/desc_t  fp32 [N][D]; score_s/score_t fp32 [N][C] (softmax); snippets of video v are rows
+ *   video_offsets[v] .. video_offsets[v+1]-1 (int32 [V+1]) of all four arrays.
+ *   svm_w fp64 [C][2D], svm_b fp64 [C] (NULL = skip SVM scoring).
+ *   out: video_desc fp32 [V][2D]; video_scores fp32 [V][C] = (w_s*mean_s + w_t*mean_t)/(w_s+w_t);
+ *        score_pred int32 [V]; svm_scores fp64 [V][C]; svm_pred int32 [V].  Any output may be NULL.
+ * --------------------------------------------------------------------------------------------------------- */
+va_status va_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
+                  const int32_t* video_offsets, int V, int D, int C, const double* svm_w, const double* svm_b,
+                  float w_s, float w_t, float* video_desc, float* video_scores, int32_t* score_pred,
+                  double* svm_scores, int32_t* svm_pred, va_stream_t stream);
+
+/* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
+ * fills n_images images of image_bytes each, image id = first_id + i. */
+va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,
+                        uint32_t seed, uint32_t first_id, va_stream_t stream);
+
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+uint64_t va_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VA_B200_H_ */

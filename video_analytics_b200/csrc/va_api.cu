@@ -1,0 +1,279 @@
+// C-ABI of libva_b200.so (see include/va_b200.h).  Owns the network handle: packed weights, activation
+// workspace, and the layer schedule of the VGG16-D two-stream networks.
+#include "../../include/va_b200.h"
+#include "va_internal.h"
+
+#include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+namespace va {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace va
+
+namespace {
+
+thread_local char g_last_error[768] = "";
+
+va_status fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define VA_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(VA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));      \
+  } while (0)
+
+// VGG16 configuration "D" (torchvision models.vgg16; reference spatialModel.py:110): output channels per conv,
+// `true` = followed by MaxPool2d(2,2).
+struct ConvSpec { int cout; bool pool; };
+const ConvSpec kVgg16[13] = {{64, false}, {64, true},  {128, false}, {128, true}, {256, false}, {256, false}, {256, true},
+                             {512, false}, {512, false}, {512, true}, {512, false}, {512, false}, {512, true}};
+constexpr int kCrop = 224;       // parameters.py:10 CROP_SIZE_TF
+constexpr int kFc1In = 512 * 7 * 7;
+constexpr int kFcHidden = 4096;
+
+}  // namespace
+
+struct va_handle {
+  int stream_kind, cin, cin_pad, n_classes, desc_dim, max_batch;
+  bool loaded;
+  void* wconv[13];
+  float* bconv[13];
+  void* wfc[3];     // FC1, FC2, FC3 packed bf16
+  float* bfc[3];
+  float* w4t;       // FC4 fp32, transposed [desc_dim][n_classes]
+  float* b4;
+  void* act[2];     // ping-pong activation workspace
+  size_t act_bytes;
+  float* desc_ws;   // [max_batch][desc_dim] when the caller does not want descriptors
+};
+
+extern "C" {
+
+const char* va_last_error(void) { return g_last_error; }
+int va_abi_version(void) { return 1; }
+uint64_t va_launch_count(void) { return va::g_launches.load(); }
+
+va_status va_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  VA_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  VA_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return VA_OK;
+}
+
+static va_status require_sm100() {
+  int dev = 0;
+  VA_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  VA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(VA_ERR_UNSUPPORTED, "libva_b200 is built for sm_100a only; device has cc %d.x", major);
+  return VA_OK;
+}
+
+va_status va_create(va_handle** out, int stream_kind, int in_channels, int n_classes, int desc_dim, int max_batch) {
+  if (!out) return fail(VA_ERR_INVALID, "va_create: out is NULL");
+  *out = nullptr;
+  if (va_status s = require_sm100()) return s;
+  if (in_channels < 1 || in_channels > 32) return fail(VA_ERR_INVALID, "in_channels %d not in [1,32]", in_channels);
+  if (desc_dim % 64 != 0 || desc_dim <= 0) return fail(VA_ERR_INVALID, "desc_dim %d must be a multiple of 64", desc_dim);
+  if (n_classes < 1 || n_classes > 1024) return fail(VA_ERR_INVALID, "n_classes %d", n_classes);
+  if (max_batch < 1) return fail(VA_ERR_INVALID, "max_batch %d", max_batch);
+  va_handle* h = new (std::nothrow) va_handle();
+  if (!h) return fail(VA_ERR_INVALID, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->stream_kind = stream_kind; h->cin = in_channels; h->cin_pad = in_channels <= 16 ? 16 : 32;
+  h->n_classes = n_classes; h->desc_dim = desc_dim; h->max_batch = max_batch;
+  int cin = h->cin_pad;
+  for (int i = 0; i < 13; ++i) {
+    const size_t wbytes = (size_t)9 * kVgg16[i].cout * cin * 2;
+    if (cudaMalloc(&h->wconv[i], wbytes) != cudaSuccess || cudaMalloc(&h->bconv[i], kVgg16[i].cout * 4) != cudaSuccess) {
+      va_destroy(h);
+      return fail(VA_ERR_CUDA, "cudaMalloc conv weights failed");
+    }
+    cin = kVgg16[i].cout;
+  }
+  const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
+  const int fout[3] = {kFcHidden, kFcHidden, desc_dim};
+  for (int i = 0; i < 3; ++i) {
+    if (cudaMalloc(&h->wfc[i], (size_t)fin[i] * fout[i] * 2) != cudaSuccess ||
+        cudaMalloc(&h->bfc[i], fout[i] * 4) != cudaSuccess) {
+      va_destroy(h);
+      return fail(VA_ERR_CUDA, "cudaMalloc fc weights failed");
+    }
+  }
+  h->act_bytes = (size_t)max_batch * kCrop * kCrop * 64 * 2;
+  if (cudaMalloc(&h->w4t, (size_t)desc_dim * n_classes * 4) != cudaSuccess ||
+      cudaMalloc(&h->b4, n_classes * 4) != cudaSuccess || cudaMalloc(&h->act[0], h->act_bytes) != cudaSuccess ||
+      cudaMalloc(&h->act[1], h->act_bytes) != cudaSuccess ||
+      cudaMalloc(&h->desc_ws, (size_t)max_batch * desc_dim * 4) != cudaSuccess) {
+    va_destroy(h);
+    return fail(VA_ERR_CUDA, "cudaMalloc workspace failed (max_batch %d needs 2 x %zu bytes)", max_batch, h->act_bytes);
+  }
+  *out = h;
+  return VA_OK;
+}
+
+va_status va_destroy(va_handle* h) {
+  if (!h) return VA_OK;
+  for (int i = 0; i < 13; ++i) { cudaFree(h->wconv[i]); cudaFree(h->bconv[i]); }
+  for (int i = 0; i < 3; ++i) { cudaFree(h->wfc[i]); cudaFree(h->bfc[i]); }
+  cudaFree(h->w4t); cudaFree(h->b4); cudaFree(h->act[0]); cudaFree(h->act[1]); cudaFree(h->desc_ws);
+  delete h;
+  return VA_OK;
+}
+
+int va_input_channels_padded(const va_handle* h) { return h ? h->cin_pad : 0; }
+
+va_status va_load_weights(va_handle* h, const void* const* tensors, int n_tensors, va_stream_t stream) {
+  if (!h || !tensors) return fail(VA_ERR_INVALID, "va_load_weights: NULL argument");
+  if (n_tensors != 34) return fail(VA_ERR_INVALID, "va_load_weights: expected 34 state_dict tensors, got %d", n_tensors);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cin = h->cin, cin_pad = h->cin_pad;
+  for (int i = 0; i < 13; ++i) {
+    const int cout = kVgg16[i].cout;
+    VA_CUDA(va::launch_pack_conv_w(static_cast<const float*>(tensors[2 * i]), h->wconv[i], cout, cin, cin_pad, 3, st));
+    VA_CUDA(cudaMemcpyAsync(h->bconv[i], tensors[2 * i + 1], cout * 4, cudaMemcpyDeviceToDevice, st));
+    cin = cout; cin_pad = cout;
+  }
+  const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
+  const int fout[3] = {kFcHidden, kFcHidden, h->desc_dim};
+  for (int i = 0; i < 3; ++i) {
+    // FC1 consumes our NHWC flatten of the [7][7][512] feature map
+    VA_CUDA(va::launch_pack_fc_w(static_cast<const float*>(tensors[26 + 2 * i]), h->wfc[i], fout[i], fin[i],
+                                 i == 0 ? 512 : 0, 49, st));
+    VA_CUDA(cudaMemcpyAsync(h->bfc[i], tensors[26 + 2 * i + 1], fout[i] * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  VA_CUDA(va::launch_transpose_f32(static_cast<const float*>(tensors[32]), h->w4t, h->n_classes, h->desc_dim, st));
+  VA_CUDA(cudaMemcpyAsync(h->b4, tensors[33], h->n_classes * 4, cudaMemcpyDeviceToDevice, st));
+  h->loaded = true;
+  return VA_OK;
+}
+
+va_status va_preprocess(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                        const int32_t* index_table, int n, int planes, int crop, const float* mean, const float* std,
+                        int c_pad, int out_mode, void* out, va_stream_t stream) {
+  if (!images || !index_table || !mean || !std || !out) return fail(VA_ERR_INVALID, "va_preprocess: NULL argument");
+  if (n < 0 || planes < 1 || img_c < 1 || planes * img_c > 32) return fail(VA_ERR_INVALID, "va_preprocess: bad shape");
+  if (crop > img_h || crop > img_w || crop < 1) return fail(VA_ERR_INVALID, "va_preprocess: crop %d vs image %dx%d", crop, img_h, img_w);
+  if (out_mode == 0 && !(c_pad == 16 || c_pad == 32 || c_pad == 64)) return fail(VA_ERR_INVALID, "va_preprocess: c_pad %d", c_pad);
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_preprocess(images, image_bytes, img_h, img_w, img_c, index_table, n, planes, crop, mean, std, c_pad,
+                                out_mode, out, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptors, float* logits, float* probs,
+                     int32_t* pred, va_stream_t stream) {
+  if (!h || !in_nhwc) return fail(VA_ERR_INVALID, "va_forward: NULL argument");
+  if (!h->loaded) return fail(VA_ERR_INVALID, "va_forward: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_stride = (size_t)kCrop * kCrop * h->cin_pad * 2;
+  for (int off = 0; off < n; off += h->max_batch) {
+    const int nb = (n - off) < h->max_batch ? (n - off) : h->max_batch;
+    const void* x = static_cast<const uint8_t*>(in_nhwc) + (size_t)off * in_stride;
+    int H = kCrop, cin_pad = h->cin_pad, cur = 0;
+    for (int i = 0; i < 13; ++i) {
+      va::ConvLayerDesc d;
+      d.x = x; d.n = nb; d.H = H; d.W = H; d.cin_pad = cin_pad;
+      d.w_packed = h->wconv[i]; d.bias = h->bconv[i]; d.Cout = kVgg16[i].cout; d.ks = 3;
+      d.relu = 1; d.pool = kVgg16[i].pool ? 1 : 0; d.y = h->act[cur]; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0;
+      if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "conv layer %d: %s", i, e);
+      x = h->act[cur]; cur ^= 1;
+      cin_pad = d.Cout;
+      if (d.pool) H >>= 1;
+    }
+    float* desc_out = descriptors ? descriptors + (size_t)off * h->desc_dim : h->desc_ws;
+    const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
+    const int fout[3] = {kFcHidden, kFcHidden, h->desc_dim};
+    for (int i = 0; i < 3; ++i) {
+      va::ConvLayerDesc d;
+      d.x = x; d.n = nb; d.H = 1; d.W = 1; d.cin_pad = fin[i];
+      d.w_packed = h->wfc[i]; d.bias = h->bfc[i]; d.Cout = fout[i]; d.ks = 1;
+      d.relu = 1; d.pool = 0; d.force_bn = 0; d.force_r = 0;
+      d.y = (i < 2) ? h->act[cur] : nullptr;
+      d.y_f32 = (i < 2) ? nullptr : desc_out;
+      if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "fc layer %d: %s", i + 1, e);
+      x = h->act[cur]; cur ^= 1;
+    }
+    VA_CUDA(va::launch_head(desc_out, h->w4t, h->b4, nb, h->desc_dim, h->n_classes,
+                            logits ? logits + (size_t)off * h->n_classes : nullptr,
+                            probs ? probs + (size_t)off * h->n_classes : nullptr, pred ? pred + off : nullptr, st));
+  }
+  return VA_OK;
+}
+
+va_status va_conv2d_nhwc(const void* x, int n, int H, int W, int cin, int cin_pad, const float* w, const float* bias,
+                         int cout, int ks, int relu, int pool, void* y, int force_bn, int force_r, va_stream_t stream) {
+  if (!x || !w || !bias || !y) return fail(VA_ERR_INVALID, "va_conv2d_nhwc: NULL argument");
+  if (cin > cin_pad) return fail(VA_ERR_INVALID, "va_conv2d_nhwc: cin %d > cin_pad %d", cin, cin_pad);
+  if (va_status s = require_sm100()) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* wp = nullptr;
+  VA_CUDA(cudaMallocAsync(&wp, (size_t)ks * ks * cout * cin_pad * 2, st));
+  VA_CUDA(va::launch_pack_conv_w(w, wp, cout, cin, cin_pad, ks, st));
+  va::ConvLayerDesc d;
+  d.x = x; d.n = n; d.H = H; d.W = W; d.cin_pad = cin_pad; d.w_packed = wp; d.bias = bias; d.Cout = cout; d.ks = ks;
+  d.relu = relu; d.pool = pool; d.y = y; d.y_f32 = nullptr; d.force_bn = force_bn; d.force_r = force_r;
+  const char* e = va::conv_layer_run(d, st);
+  cudaFreeAsync(wp, st);
+  if (e) return fail(VA_ERR_CUDA, "va_conv2d_nhwc: %s", e);
+  return VA_OK;
+}
+
+va_status va_linear(const void* x, int n, int in_features, const float* w, const float* bias, int out_features,
+                    int relu, void* y_bf16, float* y_f32, int force_bn, va_stream_t stream) {
+  if (!x || !w || !bias) return fail(VA_ERR_INVALID, "va_linear: NULL argument");
+  if ((y_bf16 == nullptr) == (y_f32 == nullptr)) return fail(VA_ERR_INVALID, "va_linear: exactly one of y_bf16 / y_f32");
+  if (in_features % 64 != 0) return fail(VA_ERR_INVALID, "va_linear: in_features %d must be a multiple of 64", in_features);
+  if (va_status s = require_sm100()) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* wp = nullptr;
+  VA_CUDA(cudaMallocAsync(&wp, (size_t)out_features * in_features * 2, st));
+  VA_CUDA(va::launch_pack_fc_w(w, wp, out_features, in_features, 0, 0, st));
+  va::ConvLayerDesc d;
+  d.x = x; d.n = n; d.H = 1; d.W = 1; d.cin_pad = in_features; d.w_packed = wp; d.bias = bias; d.Cout = out_features;
+  d.ks = 1; d.relu = relu; d.pool = 0; d.y = y_bf16; d.y_f32 = y_f32; d.force_bn = force_bn; d.force_r = 0;
+  const char* e = va::conv_layer_run(d, st);
+  cudaFreeAsync(wp, st);
+  if (e) return fail(VA_ERR_CUDA, "va_linear: %s", e);
+  return VA_OK;
+}
+
+va_status va_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
+                  const int32_t* video_offsets, int V, int D, int C, const double* svm_w, const double* svm_b, float w_s,
+                  float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
+                  int32_t* svm_pred, va_stream_t stream) {
+  if (!video_offsets) return fail(VA_ERR_INVALID, "va_fuse: video_offsets is NULL");
+  if (V < 0 || D < 1 || C < 1) return fail(VA_ERR_INVALID, "va_fuse: bad sizes V=%d D=%d C=%d", V, D, C);
+  if ((svm_w == nullptr) != (svm_b == nullptr)) return fail(VA_ERR_INVALID, "va_fuse: svm_w and svm_b go together");
+  if (svm_w && !(desc_s && desc_t)) return fail(VA_ERR_INVALID, "va_fuse: SVM scoring needs both descriptor arrays");
+  if (w_s + w_t == 0.f) return fail(VA_ERR_INVALID, "va_fuse: w_s + w_t == 0");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_fuse(desc_s, desc_t, score_s, score_t, video_offsets, V, D, C, svm_w, svm_b, w_s, w_t, video_desc,
+                          video_scores, score_pred, svm_scores, svm_pred, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c, uint32_t seed,
+                        uint32_t first_id, va_stream_t stream) {
+  if (!images) return fail(VA_ERR_INVALID, "va_synth_fill: NULL");
+  if (image_bytes < (size_t)img_h * img_w * img_c) return fail(VA_ERR_INVALID, "va_synth_fill: image_bytes too small");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_synth_fill(images, image_bytes, n_images, img_h, img_w, img_c, seed, first_id,
+                                static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+}  // extern "C"

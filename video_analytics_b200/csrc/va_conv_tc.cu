@@ -1,0 +1,198 @@
+// Host-side planner/launcher for the tcgen05 implicit-GEMM layer kernel (va_conv_tc.cuh).
+#include "va_internal.h"
+#include "va_conv_tc.cuh"
+
+#include <mutex>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace va {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+thread_local char g_err[512];
+
+const char* errf(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return g_err;
+}
+
+// bf16 tensor map of rank `rank`; dims[0] is the contiguous (channel) dimension.
+const char* encode_bf16(CUtensorMap* m, const void* addr, int rank, const uint64_t* dims, const uint32_t* box,
+                        int inner_bytes, CUtensorMapL2promotion promo) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return "cuTensorMapEncodeTiled not available (no CUDA driver?)";
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : inner_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                   : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(addr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return errf("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] inner %dB",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, inner_bytes);
+  return nullptr;
+}
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int CK, int R>
+const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const CUtensorMap& tO,
+                           const ConvKernelParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kfn = conv_tc_kernel<BN, CK, R>;
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return errf("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  count_launch();
+  kfn<<<grid, kConvThreads, smem, st>>>(tA, tW, tO, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return errf("conv_tc_kernel<%d,%d,%d> launch: %s", BN, CK, R, cudaGetErrorString(e));
+  return nullptr;
+}
+
+}  // namespace
+
+const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
+  if (d.n <= 0) return nullptr;
+  if (d.ks != 1 && d.ks != 3) return "ks must be 1 or 3";
+  const int CK = (d.cin_pad % 64 == 0) ? 64 : d.cin_pad;
+  if (CK != 64 && CK != 32 && CK != 16) return errf("cin_pad %d unsupported (16, 32 or multiple of 64)", d.cin_pad);
+  if (d.Cout % 64 != 0) return errf("Cout %d must be a multiple of 64", d.Cout);
+  if (d.pool && ((d.H | d.W) & 1)) return "fused 2x2 pool needs even H and W";
+  if (d.y_f32 && (d.H != 1 || d.W != 1 || d.pool)) return "fp32 output only for fully-connected (H=W=1) layers";
+
+  ConvKernelParams p;
+  p.n_img = d.n; p.H = d.H; p.W = d.W;
+  if (d.H == 1 && d.W == 1) { p.h_t = 1; p.w_t = 1; p.n_t = 128; }
+  else if (d.W % 16 == 0 && d.H % 8 == 0) { p.h_t = 8; p.w_t = 16; p.n_t = 1; }
+  else if (d.W % 8 == 0 && d.H % 8 == 0) { p.h_t = 8; p.w_t = 8; p.n_t = 2; }
+  else if (d.W % 4 == 0 && d.H % 4 == 0) { p.h_t = 4; p.w_t = 4; p.n_t = 8; }
+  else if (d.W % 2 == 0 && d.H % 2 == 0) { p.h_t = 2; p.w_t = 2; p.n_t = 32; }
+  else return errf("unsupported spatial size %dx%d", d.H, d.W);
+  if (d.pool && (p.h_t < 2 || p.w_t < 2)) return "pool needs a spatial tile";
+  p.log2_w_t = ilog2(p.w_t); p.log2_h_t = ilog2(p.h_t);
+  p.tiles_w = d.W / p.w_t; p.tiles_h = d.H / p.h_t; p.tiles_n = (d.n + p.n_t - 1) / p.n_t;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+
+  int R = 1;
+  if (d.force_r == 3) {
+    if (!(d.ks == 3 && p.n_t == 1 && p.w_t % 8 == 0)) return "force_r=3 needs ks=3 and a single-image tile with w_t%8==0";
+    R = 3;
+  }
+  const int sms = sm_count();
+  int BN = d.force_bn;
+  if (BN == 0) {
+    double best = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int bn = cands[i];
+      if (d.Cout % bn) continue;
+      if (CK != 64 && bn != 64) continue;
+      if (R == 3 && bn == 256) continue;
+      const long long tiles = (long long)tiles_m * (d.Cout / bn);
+      const long long waves = (tiles + sms - 1) / sms;
+      const double eff = bn == 256 ? 1.0 : (bn == 128 ? 1.08 : 1.45);
+      const double cost = (double)waves * bn * eff;
+      if (cost < best) { best = cost; BN = bn; }
+    }
+  }
+  if (BN != 64 && BN != 128 && BN != 256) return errf("bad BN %d", BN);
+  if (d.Cout % BN) return errf("Cout %d not divisible by BN %d", d.Cout, BN);
+  if (CK != 64 && BN != 64) return "CK<64 variants are built for BN=64 only";
+  if (R == 3 && BN == 256) return "R=3 not built for BN=256";
+
+  p.n_tiles_cout = d.Cout / BN;
+  p.total_tiles = tiles_m * p.n_tiles_cout;
+  p.ks = d.ks; p.pad = (d.ks - 1) / 2;
+  p.cin_chunks = d.cin_pad / CK;
+  p.pool = d.pool; p.relu = d.relu; p.out_f32 = d.y_f32 ? 1 : 0;
+  p.Cout = d.Cout;
+  p.bias = d.bias; p.out_f32_ptr = d.y_f32;
+  const int rowb = CK * 2;
+  const int a_rows = p.n_t * (p.h_t + (R - 1)) * p.w_t;
+  p.a_tx_bytes = (uint32_t)a_rows * rowb;
+  p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.a_stage_bytes + conv_b_stage_bytes(BN, CK, R);
+  const size_t smem_cap = 227 * 1024;
+  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, p.a_stage_bytes, 0)) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return errf("not enough shared memory for 2 stages (stage %u B)", stage_bytes);
+  p.num_stages = stages;
+  const size_t smem = conv_smem_bytes(BN, CK, R, p.a_stage_bytes, stages);
+
+  CUtensorMap tA, tW, tO;
+  {
+    const uint64_t dims[4] = {(uint64_t)d.cin_pad, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.n};
+    const uint32_t box[4] = {(uint32_t)CK, (uint32_t)p.w_t, (uint32_t)(p.h_t + R - 1), (uint32_t)p.n_t};
+    if (const char* e = encode_bf16(&tA, d.x, 4, dims, box, rowb, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)d.cin_pad, (uint64_t)d.Cout, (uint64_t)(d.ks * d.ks)};
+    const uint32_t box[3] = {(uint32_t)CK, (uint32_t)BN, (uint32_t)R};
+    if (const char* e = encode_bf16(&tW, d.w_packed, 3, dims, box, rowb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
+  }
+  if (!d.y_f32) {
+    const int sh = d.pool ? 1 : 0;
+    const uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)(d.W >> sh), (uint64_t)(d.H >> sh), (uint64_t)d.n};
+    const uint32_t box[4] = {64u, (uint32_t)(p.w_t >> sh), (uint32_t)(p.h_t >> sh), (uint32_t)p.n_t};
+    if (const char* e = encode_bf16(&tO, d.y, 4, dims, box, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
+  } else {
+    tO = tA;   // unused by the fp32 epilogue; must still be a valid descriptor
+  }
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+
+#define VA_CASE(bn, ck, r) \
+  if (BN == bn && CK == ck && R == r) return launch_variant<bn, ck, r>(tA, tW, tO, p, grid, smem, st);
+  VA_CASE(64, 16, 1) VA_CASE(64, 32, 1) VA_CASE(64, 64, 1) VA_CASE(128, 64, 1) VA_CASE(256, 64, 1)
+  VA_CASE(64, 64, 3) VA_CASE(128, 64, 3)
+#undef VA_CASE
+  return errf("no kernel variant for BN=%d CK=%d R=%d", BN, CK, R);
+}
+
+}  // namespace va

@@ -1,0 +1,300 @@
+// K2/K3: implicit-GEMM 3x3 (and 1x1 / fully-connected) convolution on the 5th-gen tensor cores.
+//
+// Replaces the reference's `self.features(ip)` + classifier Linear layers, i.e. torchvision VGG16
+// Conv2d(3x3,s1,p1)+bias+ReLU(+MaxPool2d(2,2)) and nn.Linear+ReLU
+// (reference Sheet03/spatialModel.py:171-177, temporalModel.py:200-206; model surgery :136-152).
+//
+// GEMM view: D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[tap, cout, cin].
+//   * activations: NHWC bf16, channels padded to a multiple of CK
+//   * weights:     [tap' = s*ks + r][Cout][Cin_pad] bf16 (K-major "B" operand)
+//   * an M tile is a 128-pixel patch n_t x h_t x w_t of the output; for tap (r,s) the A operand is the
+//     same patch of the input shifted by (r-pad, s-pad), fetched by ONE 4-D tiled TMA box whose
+//     out-of-bounds part (the zero halo, and partial batches) is zero-filled by the TMA unit.
+//   * R==3 ("vertical reuse"): one TMA box of h_t+2 rows serves the three taps r=0..2 of a filter
+//     column s; the three MMAs address it at row offsets r*w_t (whole 8-row swizzle atoms).
+//   * accumulators live in TMEM (2 stages x BN fp32 columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1; epilogue = tcgen05.ld -> +bias -> ReLU -> bf16 -> (2x2 max-pool by warp
+//     shuffles) -> 128B-swizzled smem staging -> TMA store (clips partial tiles).
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer
+// (+TMEM alloc), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#pragma once
+#include <cuda.h>
+#include "va_ptx.cuh"
+
+namespace va {
+
+struct ConvKernelParams {
+  int n_img, H, W;                 // input (== pre-pool output) spatial size
+  int h_t, w_t, n_t;               // output-pixel tile; h_t*w_t*n_t == 128, all powers of two
+  int log2_w_t, log2_h_t;
+  int tiles_w, tiles_h, tiles_n;   // ceil-div tile counts
+  int n_tiles_cout;                // Cout / BN
+  int total_tiles;
+  int ks, pad;                     // 3/1 or 1/0
+  int cin_chunks;                  // Cin_pad / CK
+  int pool, relu, out_f32;
+  int Cout;
+  int num_stages;
+  uint32_t a_stage_bytes;          // smem bytes reserved per stage for A (multiple of 1024)
+  uint32_t a_tx_bytes;             // bytes one A TMA box delivers
+  const float* bias;               // [Cout]
+  float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kStagingBytes = 16384;   // one 128-row x 64-channel bf16 chunk
+
+__host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R) { return R * BN * CK * 2; }
+
+inline size_t conv_smem_bytes(int BN, int CK, int R, uint32_t a_stage_bytes, int stages) {
+  return 1024 /*align slack*/ + (size_t)stages * (a_stage_bytes + conv_b_stage_bytes(BN, CK, R)) +
+         2 * kStagingBytes + 256 * sizeof(float) + 256;
+}
+
+__device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 m = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+
+template <int BN, int CK, int R>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  static_assert(CK == 16 || CK == 32 || CK == 64, "CK");
+  static_assert(R == 1 || R == 3, "R");
+  constexpr int ROWB = CK * 2;
+  constexpr uint32_t B_STAGE = conv_b_stage_bytes(BN, CK, R);
+  constexpr uint32_t TMEM_COLS = 2 * BN;   // 128 / 256 / 512: powers of two >= 32
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = p.a_stage_bytes + B_STAGE;
+  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 256);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int groups = (p.ks * p.ks) / R;          // R=1: one group per tap; R=3: one per filter column
+  const int num_kb = groups * p.cin_chunks;      // pipeline stages consumed per tile
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nt = tile % p.n_tiles_cout;
+        int mt = tile / p.n_tiles_cout;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tn = mt / p.tiles_h;
+        const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
+        for (int g = 0; g < groups; ++g) {
+          const int s = (R == 1) ? (g / p.ks) : g;
+          const int r = (R == 1) ? (g % p.ks) : 0;
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+            uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+            uint8_t* b_dst = a_dst + p.a_stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + B_STAGE);
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * CK, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_3d(b_dst, &tmW, &full_bar[stage], cc * CK, c0, g * R);
+            if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      const uint32_t a_r_stride = (uint32_t)p.w_t * ROWB;   // bytes per input row of the A box (R==3, n_t==1)
+      uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint64_t da = make_smem_desc<ROWB>(a_addr + r * a_r_stride + k * 32);
+              const uint64_t db = make_smem_desc<ROWB>(b_addr + r * (BN * ROWB) + k * 32);
+              umma_bf16(d_tmem, da, db, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);         // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) as_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================================================== epilogue (4 warps, 128 threads)
+    const int q = warp & 3;               // TMEM lane quarter accessible to this warp
+    const int m = q * 32 + lane;          // accumulator row == pixel index inside the tile
+    const int et = threadIdx.x - 64;      // 0..127
+    const int w_i = m & (p.w_t - 1);
+    const int h_i = (m >> p.log2_w_t) & (p.h_t - 1);
+    const int n_i = m >> (p.log2_w_t + p.log2_h_t);
+    uint32_t as = 0, as_phase = 0;
+    int sbuf = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt = tile % p.n_tiles_cout;
+      int mt = tile / p.n_tiles_cout;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tn = mt / p.tiles_h;
+      const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
+
+      named_bar_sync(1, 128);             // everyone is done reading the previous tile's bias
+      for (int i = et; i < BN; i += 128) bias_s[i] = __ldg(p.bias + c0 + i);
+      named_bar_sync(1, 128);
+
+      mbar_wait(&tfull_bar[as], as_phase, 400 + as);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 64; ++chunk) {
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + chunk * 64;
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (chunk == BN / 64 - 1) {        // accumulator stage fully drained into registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        const float* bs = bias_s + chunk * 64;
+        if (p.out_f32) {
+          // fully-connected tail (H=W=1, tile = 128 images): fp32 rows straight to global.
+          const int img = n0 + m;
+          if (img < p.n_img) {
+            float* dst = p.out_f32_ptr + (size_t)img * p.Cout + c0 + chunk * 64;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o;
+              o.x = __uint_as_float(v0[i]) + bs[i];
+              o.y = __uint_as_float(v0[i + 1]) + bs[i + 1];
+              o.z = __uint_as_float(v0[i + 2]) + bs[i + 2];
+              o.w = __uint_as_float(v0[i + 3]) + bs[i + 3];
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(dst + i) = o;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o;
+              o.x = __uint_as_float(v1[i]) + bs[32 + i];
+              o.y = __uint_as_float(v1[i + 1]) + bs[32 + i + 1];
+              o.z = __uint_as_float(v1[i + 2]) + bs[32 + i + 2];
+              o.w = __uint_as_float(v1[i + 3]) + bs[32 + i + 3];
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(dst + 32 + i) = o;
+            }
+          }
+          continue;
+        }
+        // bias + ReLU + round to bf16 (pairs of channels packed low|high)
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = __uint_as_float(v0[2 * i]) + bs[2 * i];
+          float b = __uint_as_float(v0[2 * i + 1]) + bs[2 * i + 1];
+          float c = __uint_as_float(v1[2 * i]) + bs[32 + 2 * i];
+          float d = __uint_as_float(v1[2 * i + 1]) + bs[32 + 2 * i + 1];
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f); d = fmaxf(d, 0.f); }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+          pk[i] = *reinterpret_cast<uint32_t*>(&lo);
+          pk[16 + i] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        bool writer = true;
+        int row = m;
+        if (p.pool) {
+          // 2x2/2 max-pool: partners are the neighbouring pixel (lane^1) and the next tile row (lane^w_t).
+          // max commutes with the (monotonic) bf16 rounding and ReLU, so pooling the rounded values is exact.
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            uint32_t u = pk[i];
+            u = bf162_max(u, __shfl_xor_sync(0xffffffffu, u, 1));
+            u = bf162_max(u, __shfl_xor_sync(0xffffffffu, u, p.w_t));
+            pk[i] = u;
+          }
+          writer = ((w_i | h_i) & 1) == 0;
+          row = ((n_i * (p.h_t >> 1)) + (h_i >> 1)) * (p.w_t >> 1) + (w_i >> 1);
+        }
+        // staging buffer `sbuf` was last read by the TMA store issued two chunks ago
+        if (et == 0) tma_store_wait_read<1>();
+        named_bar_sync(2, 128);
+        if (writer) {
+          uint8_t* rowp = staging + sbuf * kStagingBytes + row * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 val = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = val;   // 128B swizzle, as the TMA store expects
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          const int sh = p.pool ? 1 : 0;
+          tma_store_4d(&tmO, staging + sbuf * kStagingBytes, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      as ^= 1;
+      if (as == 0) as_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace va

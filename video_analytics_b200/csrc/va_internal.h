@@ -1,0 +1,45 @@
+// Internal (non-ABI) declarations shared by the translation units of libva_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <algorithm>
+
+namespace va {
+
+void count_launch();   // bumps the library-wide launch counter (va_launch_count)
+
+cudaError_t launch_preprocess(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                              const int32_t* table, int n, int planes, int crop, const float* mean,
+                              const float* stdv, int c_pad, int out_mode, void* out, cudaStream_t st);
+cudaError_t launch_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int H, int W, int C, uint32_t seed,
+                              uint32_t first_id, cudaStream_t st);
+cudaError_t launch_pack_conv_w(const float* w, void* out, int Cout, int Cin, int cin_pad, int ks, cudaStream_t st);
+cudaError_t launch_pack_fc_w(const float* w, void* out, int n_out, int n_in, int chan, int hw, cudaStream_t st);
+cudaError_t launch_transpose_f32(const float* w, float* out, int rows, int cols, cudaStream_t st);
+cudaError_t launch_head(const float* desc, const float* w4t, const float* b4, int n, int D, int C, float* logits,
+                        float* probs, int32_t* pred, cudaStream_t st);
+cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
+                        const int32_t* offs, int V, int D, int C, const double* svm_w, const double* svm_b, float w_s,
+                        float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
+                        int32_t* svm_pred, cudaStream_t st);
+
+// ---- tensor-core conv / linear layer (va_conv_tc.cu)
+struct ConvLayerDesc {
+  const void* x;        // bf16 NHWC [n][H][W][cin_pad]
+  int n, H, W, cin_pad;
+  const void* w_packed; // bf16 [ks*ks][Cout][cin_pad]
+  const float* bias;    // fp32 [Cout]
+  int Cout, ks;
+  int relu, pool;
+  void* y;              // bf16 NHWC [n][H>>pool][W>>pool][Cout] (unless y_f32)
+  float* y_f32;         // fp32 [n][Cout] (H=W=1 only)
+  int force_bn, force_r;
+};
+// Plans (tile shape, kernel variant, tensor maps) and launches one layer.  Returns nullptr on success or a
+// static/thread-local error string.
+const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st);
+
+}  // namespace va

@@ -1,0 +1,366 @@
+// HBM-bound kernels of the two-stream path: K1 snippet preprocess, weight packing, the fp32 logit/softmax/argmax
+// head, K4 consensus + late fusion, and the synthetic image-store generator.  All integer/byte work stays
+// integer; all fp32 arithmetic that must match the reference bit-for-bit uses explicit IEEE intrinsics.
+#include "va_internal.h"
+
+namespace va {
+
+// ------------------------------------------------------------------------------------------------ synth
+// Counter-based pixel hash; MUST stay identical to oracle/synth.py::synth_image (pure uint32 arithmetic).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+__global__ void synth_fill_kernel(uint8_t* images, size_t image_bytes, int n_images, int H, int W, int C,
+                                  uint32_t seed, uint32_t first_id) {
+  const size_t per = (size_t)H * W * C;
+  const size_t total = per * n_images;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t img = (uint32_t)(g / per);
+    const uint32_t idx = (uint32_t)(g % per);
+    const uint32_t id = first_id + img;
+    const uint32_t c = idx % C, x = (idx / C) % W, y = idx / (C * W);
+    const uint32_t h = mix32(seed ^ mix32(id * 0x9E3779B1u + 0x85EBCA6Bu) ^ (idx * 0xC2B2AE35u));
+    const uint32_t smooth = (x * 3u + y * 5u + c * 41u + id * 29u) >> 1;
+    images[(size_t)img * image_bytes + idx] = (uint8_t)((smooth + (h & 63u)) & 255u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+struct PreprocessParams {
+  const uint8_t* images;
+  size_t image_bytes;
+  int img_h, img_w, img_c;
+  const int32_t* table;   // [n][planes][4]
+  int n, planes, crop;
+  float mean[32], stdv[32];
+  void* out;
+};
+
+// One thread per output pixel; channels (planes*img_c <= C_PAD) gathered into registers, written as 16-byte
+// vectors (bf16 NHWC) or as coalesced fp32 planes (NCHW).  ((u8/255) - mean)/std in IEEE fp32, exactly
+// torchvision ToTensor + Normalize (reference utils.py:148-150).  PLANES/IMG_C are compile-time for the two
+// shapes of the path (1x3 RGB, 20x1 flow) so the channel loop unrolls into registers; PLANES==0 is the
+// generic (runtime-shaped, slower) instance.
+template <int C_PAD, int MODE, int PLANES, int IMG_C>
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams p) {
+  const int pix_per = p.crop * p.crop;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)p.n * pix_per) return;
+  const int snip = (int)(g / pix_per);
+  const int pix = (int)(g % pix_per);
+  const int y = pix / p.crop, x = pix % p.crop;
+  const int planes = PLANES > 0 ? PLANES : p.planes;
+  const int img_c = PLANES > 0 ? IMG_C : p.img_c;
+  const int nch = planes * img_c;
+  float vals[C_PAD];
+#pragma unroll
+  for (int c = 0; c < C_PAD; ++c) vals[c] = 0.f;
+  const int4* t = reinterpret_cast<const int4*>(p.table) + (size_t)snip * planes;
+  if (PLANES > 0) {
+#pragma unroll
+    for (int pl = 0; pl < PLANES; ++pl) {
+      const int4 e = __ldg(t + pl);   // {image id, crop_i, crop_j, flip}
+      const int xs = e.w ? (p.crop - 1 - x) : x;   // hflip of the crop == reversed columns
+      const uint8_t* src =
+          p.images + (size_t)e.x * p.image_bytes + ((size_t)(e.y + y) * p.img_w + (e.z + xs)) * IMG_C;
+#pragma unroll
+      for (int k = 0; k < IMG_C; ++k) {
+        const float u = (float)__ldg(src + k);
+        vals[pl * IMG_C + k] = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), p.mean[pl * IMG_C + k]), p.stdv[pl * IMG_C + k]);
+      }
+    }
+  } else {
+    int ch = 0;
+    for (int pl = 0; pl < planes; ++pl) {
+      const int4 e = __ldg(t + pl);
+      const int xs = e.w ? (p.crop - 1 - x) : x;
+      const uint8_t* src =
+          p.images + (size_t)e.x * p.image_bytes + ((size_t)(e.y + y) * p.img_w + (e.z + xs)) * img_c;
+      for (int k = 0; k < img_c; ++k, ++ch) {
+        const float u = (float)__ldg(src + k);
+        const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), p.mean[ch]), p.stdv[ch]);
+#pragma unroll
+        for (int c = 0; c < C_PAD; ++c)
+          if (c == ch) vals[c] = v;   // keeps vals[] in registers
+      }
+    }
+  }
+  if (MODE == 0) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)g * C_PAD);
+#pragma unroll
+    for (int c = 0; c < C_PAD; c += 8) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(vals[c], vals[c + 1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(vals[c + 2], vals[c + 3]);
+      __nv_bfloat162 cc = __floats2bfloat162_rn(vals[c + 4], vals[c + 5]);
+      __nv_bfloat162 d = __floats2bfloat162_rn(vals[c + 6], vals[c + 7]);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+      o.z = *reinterpret_cast<uint32_t*>(&cc); o.w = *reinterpret_cast<uint32_t*>(&d);
+      dst[c / 8] = o;
+    }
+  } else {
+    float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+    for (int c = 0; c < C_PAD; ++c)
+      if (c < nch) out[((size_t)snip * nch + c) * pix_per + pix] = vals[c];
+  }
+}
+
+cudaError_t launch_preprocess(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                              const int32_t* table, int n, int planes, int crop, const float* mean,
+                              const float* stdv, int c_pad, int out_mode, void* out, cudaStream_t st) {
+  PreprocessParams p;
+  p.images = images; p.image_bytes = image_bytes; p.img_h = img_h; p.img_w = img_w; p.img_c = img_c;
+  p.table = table; p.n = n; p.planes = planes; p.crop = crop; p.out = out;
+  const int nch = planes * img_c;
+  if (nch > 32 || (out_mode == 0 && nch > c_pad)) return cudaErrorInvalidValue;
+  for (int i = 0; i < 32; ++i) { p.mean[i] = i < nch ? mean[i] : 0.f; p.stdv[i] = i < nch ? stdv[i] : 1.f; }
+  const long long total = (long long)n * crop * crop;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks == 0) return cudaSuccess;
+  count_launch();
+  const bool rgb = (planes == 1 && img_c == 3), flow = (planes == 20 && img_c == 1);
+  if (out_mode == 0) {
+    if (c_pad == 16 && rgb) preprocess_kernel<16, 0, 1, 3><<<blocks, 256, 0, st>>>(p);
+    else if (c_pad == 32 && flow) preprocess_kernel<32, 0, 20, 1><<<blocks, 256, 0, st>>>(p);
+    else if (c_pad == 64 && rgb) preprocess_kernel<64, 0, 1, 3><<<blocks, 256, 0, st>>>(p);
+    else if (c_pad == 64 && flow) preprocess_kernel<64, 0, 20, 1><<<blocks, 256, 0, st>>>(p);
+    else if (c_pad == 16) preprocess_kernel<16, 0, 0, 0><<<blocks, 256, 0, st>>>(p);
+    else if (c_pad == 32) preprocess_kernel<32, 0, 0, 0><<<blocks, 256, 0, st>>>(p);
+    else if (c_pad == 64) preprocess_kernel<64, 0, 0, 0><<<blocks, 256, 0, st>>>(p);
+    else return cudaErrorInvalidValue;
+  } else if (out_mode == 1) {
+    if (rgb) preprocess_kernel<8, 1, 1, 3><<<blocks, 256, 0, st>>>(p);
+    else if (flow) preprocess_kernel<24, 1, 20, 1><<<blocks, 256, 0, st>>>(p);
+    else preprocess_kernel<32, 1, 0, 0><<<blocks, 256, 0, st>>>(p);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int H, int W, int C, uint32_t seed,
+                              uint32_t first_id, cudaStream_t st) {
+  const size_t total = (size_t)H * W * C * n_images;
+  if (total == 0) return cudaSuccess;
+  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
+  count_launch();
+  synth_fill_kernel<<<blocks, 256, 0, st>>>(images, image_bytes, n_images, H, W, C, seed, first_id);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// OIHW fp32 -> [tap' = s*ks + r][Cout][cin_pad] bf16, zero padded input channels.
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                   int cin_pad, int ks) {
+  const size_t total = (size_t)ks * ks * Cout * cin_pad;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(g % cin_pad);
+    const int o = (int)((g / cin_pad) % Cout);
+    const int tap = (int)(g / ((size_t)cin_pad * Cout));
+    const int s = tap / ks, r = tap % ks;
+    const float v = c < Cin ? w[(((size_t)o * Cin + c) * ks + r) * ks + s] : 0.f;
+    out[g] = __float2bfloat16_rn(v);
+  }
+}
+// [out][in] fp32 -> bf16; with chan>0 the input index is re-ordered from the reference's NCHW flatten
+// (c*hw + p, spatialModel.py:172) to our NHWC flatten (p*chan + c).
+__global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int n_out, int n_in,
+                                 int chan, int hw) {
+  const size_t total = (size_t)n_out * n_in;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(g % n_in);
+    const size_t o = g / n_in;
+    int src = j;
+    if (chan > 0) { const int c = j % chan, pp = j / chan; src = c * hw + pp; }
+    out[g] = __float2bfloat16_rn(w[o * n_in + src]);
+  }
+}
+__global__ void transpose_f32_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int cols) {
+  const int total = rows * cols;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int r = g / cols, c = g % cols;
+    out[(size_t)c * rows + r] = w[g];
+  }
+}
+
+cudaError_t launch_pack_conv_w(const float* w, void* out, int Cout, int Cin, int cin_pad, int ks, cudaStream_t st) {
+  const size_t total = (size_t)ks * ks * Cout * cin_pad;
+  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  count_launch();
+  pack_conv_w_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cout, Cin, cin_pad, ks);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_fc_w(const float* w, void* out, int n_out, int n_in, int chan, int hw, cudaStream_t st) {
+  const size_t total = (size_t)n_out * n_in;
+  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  count_launch();
+  pack_fc_w_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), n_out, n_in, chan, hw);
+  return cudaGetLastError();
+}
+cudaError_t launch_transpose_f32(const float* w, float* out, int rows, int cols, cudaStream_t st) {
+  unsigned blocks = (unsigned)((rows * cols + 255) / 256);
+  count_launch();
+  transpose_f32_kernel<<<blocks, 256, 0, st>>>(w, out, rows, cols);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ head
+// logits = desc . W4^T + b4 (fp32), softmax, argmax (first maximum).  One CTA (128 threads) per snippet.
+// Replaces classifierList[9] + op.max(1) (reference spatialModel.py:176-177,220).
+__global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ desc, const float* __restrict__ w4t,
+                                                   const float* __restrict__ b4, int D, int C,
+                                                   float* __restrict__ logits, float* __restrict__ probs,
+                                                   int32_t* __restrict__ pred) {
+  extern __shared__ float sm[];   // D desc + C logits
+  float* sd = sm;
+  float* sl = sm + D;
+  __shared__ float red_v[4];
+  __shared__ int red_i[4];
+  __shared__ float red_s[4];
+  const int n = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) sd[d] = desc[(size_t)n * D + d];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = b4[c];
+    for (int d = 0; d < D; ++d) acc = fmaf(sd[d], w4t[(size_t)d * C + c], acc);
+    sl[c] = acc;
+    if (logits) logits[(size_t)n * C + c] = acc;
+  }
+  __syncthreads();
+  // argmax with first-index tie break
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = sl[c];
+    if (v > bv || (v == bv && c < bi)) { bv = v; bi = c; }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+  __syncthreads();
+  bv = red_v[0]; bi = red_i[0];
+  for (int w = 1; w < 4; ++w)
+    if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+  if (threadIdx.x == 0 && pred) pred[n] = bi;
+  // softmax
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float e = expf(sl[c] - bv);
+    sl[c] = e;
+    s += e;
+  }
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) red_s[warp] = s;
+  __syncthreads();
+  s = red_s[0] + red_s[1] + red_s[2] + red_s[3];
+  if (probs)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) probs[(size_t)n * C + c] = __fdiv_rn(sl[c], s);
+}
+
+cudaError_t launch_head(const float* desc, const float* w4t, const float* b4, int n, int D, int C, float* logits,
+                        float* probs, int32_t* pred, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  count_launch();
+  head_kernel<<<n, 128, (D + C) * sizeof(float), st>>>(desc, w4t, b4, D, C, logits, probs, pred);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// One CTA per video.  Means are SEQUENTIAL fp32 sums in snippet order followed by one division, i.e. exactly
+// AverageMeter.update (reference utils.py:167-171) -- bit-identical to the reference given identical inputs.
+__global__ void __launch_bounds__(512) fuse_kernel(const float* __restrict__ desc_s, const float* __restrict__ desc_t,
+                                                   const float* __restrict__ score_s,
+                                                   const float* __restrict__ score_t,
+                                                   const int32_t* __restrict__ offs, int D, int C,
+                                                   const double* __restrict__ svm_w, const double* __restrict__ svm_b,
+                                                   float w_s, float w_t, float* __restrict__ video_desc,
+                                                   float* __restrict__ video_scores, int32_t* __restrict__ score_pred,
+                                                   double* __restrict__ svm_scores, int32_t* __restrict__ svm_pred) {
+  extern __shared__ unsigned char fsm_raw[];
+  double* ssvm = reinterpret_cast<double*>(fsm_raw);          // C
+  float* sx = reinterpret_cast<float*>(ssvm + C);             // 2D fused descriptor
+  float* ssc = sx + 2 * D;                                    // C fused scores
+  const int v = blockIdx.x;
+  const int b = offs[v], e = offs[v + 1];
+  const float cnt = (float)(e - b);
+  const bool has_desc = desc_s != nullptr && desc_t != nullptr;
+  const bool has_sc = score_s != nullptr && score_t != nullptr;
+  // descriptors: thread j < 2D owns one output dimension
+  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
+    const float* src = (j < D) ? (desc_s + j) : (desc_t + (j - D));
+    float sum = 0.f;
+    if (has_desc) {
+      int i = b;
+      for (; i + 4 <= e; i += 4) {   // 4 independent loads in flight, adds stay in order
+        const float a0 = __ldg(src + (size_t)i * D), a1 = __ldg(src + (size_t)(i + 1) * D),
+                    a2 = __ldg(src + (size_t)(i + 2) * D), a3 = __ldg(src + (size_t)(i + 3) * D);
+        sum = __fadd_rn(sum, a0); sum = __fadd_rn(sum, a1); sum = __fadd_rn(sum, a2); sum = __fadd_rn(sum, a3);
+      }
+      for (; i < e; ++i) sum = __fadd_rn(sum, __ldg(src + (size_t)i * D));
+    }
+    const float avg = (e > b) ? __fdiv_rn(sum, cnt) : 0.f;
+    sx[j] = avg;
+    if (video_desc) video_desc[(size_t)v * 2 * D + j] = avg;
+  }
+  // class scores: threads 0..C-1 spatial, C..2C-1 temporal (if blockDim allows), else strided
+  if (has_sc) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int i = b; i < e; ++i) {
+        s0 = __fadd_rn(s0, __ldg(score_s + (size_t)i * C + c));
+        s1 = __fadd_rn(s1, __ldg(score_t + (size_t)i * C + c));
+      }
+      const float m0 = (e > b) ? __fdiv_rn(s0, cnt) : 0.f;
+      const float m1 = (e > b) ? __fdiv_rn(s1, cnt) : 0.f;
+      const float f = __fdiv_rn(__fadd_rn(__fmul_rn(w_s, m0), __fmul_rn(w_t, m1)), __fadd_rn(w_s, w_t));
+      ssc[c] = f;
+      if (video_scores) video_scores[(size_t)v * C + c] = f;
+    }
+  }
+  __syncthreads();
+  if (has_sc && score_pred != nullptr && threadIdx.x == 0) {
+    float bv = ssc[0]; int bi = 0;
+    for (int c = 1; c < C; ++c) if (ssc[c] > bv) { bv = ssc[c]; bi = c; }
+    score_pred[v] = bi;
+  }
+  if (svm_w != nullptr) {
+    // decision_function in fp64 like sklearn: one warp per class, lanes stride the 2D-long dot product.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int c = warp; c < C; c += nwarps) {
+      double acc = 0.0;
+      for (int j = lane; j < 2 * D; j += 32) acc += (double)sx[j] * svm_w[(size_t)c * 2 * D + j];
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) {
+        acc += svm_b[c];
+        ssvm[c] = acc;
+        if (svm_scores) svm_scores[(size_t)v * C + c] = acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && svm_pred) {
+      double bv = ssvm[0]; int bi = 0;
+      for (int c = 1; c < C; ++c) if (ssvm[c] > bv) { bv = ssvm[c]; bi = c; }
+      svm_pred[v] = bi;
+    }
+  }
+}
+
+cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
+                        const int32_t* offs, int V, int D, int C, const double* svm_w, const double* svm_b, float w_s,
+                        float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
+                        int32_t* svm_pred, cudaStream_t st) {
+  if (V == 0) return cudaSuccess;
+  const size_t smem = C * sizeof(double) + (2 * D + C) * sizeof(float);
+  count_launch();
+  fuse_kernel<<<V, 512, smem, st>>>(desc_s, desc_t, score_s, score_t, offs, D, C, svm_w, svm_b, w_s, w_t, video_desc,
+                                    video_scores, score_pred, svm_scores, svm_pred);
+  return cudaGetLastError();
+}
+
+}  // namespace va

@@ -1,0 +1,181 @@
+"""Python call layer over the C-ABI (include/va_b200.h).  torch is used only to own device memory and streams.
+
+Every function launches hand-written sm_100a kernels from libva_b200.so on the current CUDA stream and raises
+`VAError` on failure -- nothing here computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import VAError, check, ptr, stream_ptr
+
+STREAM_SPATIAL, STREAM_TEMPORAL = 0, 1
+CROP = 224
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VAError("libva_b200 operates on CUDA tensors only (no CPU fallback)")
+        if t is not None and not t.is_contiguous():
+            raise VAError("libva_b200 needs contiguous tensors")
+
+
+def device_info():
+    lib = _lib.load()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib.va_device_info(C.byref(a), C.byref(b), C.byref(c)), "va_device_info")
+    return {"sm_count": a.value, "cc": (b.value, c.value)}
+
+
+def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, relu=True, pool=False, force_bn=0,
+                force_r=0) -> torch.Tensor:
+    """x bf16 [n,H,W,cin_pad]; w fp32 OIHW [cout,cin,ks,ks]; -> bf16 [n,H',W',cout] (H'=H/2 when pool)."""
+    _need_cuda(x, w, bias)
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.float32 and bias.dtype == torch.float32
+    n, H, W, cin_pad = x.shape
+    cout, cin, ks, _ = w.shape
+    sh = 1 if pool else 0
+    y = torch.empty((n, H >> sh, W >> sh, cout), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().va_conv2d_nhwc(ptr(x), n, H, W, cin, cin_pad, ptr(w), ptr(bias), cout, ks, int(relu), int(pool),
+                                     ptr(y), force_bn, force_r, stream_ptr()), "va_conv2d_nhwc")
+    return y
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, relu=True, out_f32=False, force_bn=0) -> torch.Tensor:
+    """x bf16 [n,in]; w fp32 [out,in] -> bf16 (or fp32) [n,out]."""
+    _need_cuda(x, w, bias)
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.float32
+    n, fin = x.shape
+    fout = w.shape[0]
+    y = torch.empty((n, fout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    check(_lib.load().va_linear(ptr(x), n, fin, ptr(w), ptr(bias), fout, int(relu), ptr(None if out_f32 else y),
+                                ptr(y if out_f32 else None), force_bn, stream_ptr()), "va_linear")
+    return y
+
+
+def preprocess(images: torch.Tensor, image_shape: Sequence[int], index_table: torch.Tensor, mean: Sequence[float],
+               std: Sequence[float], *, c_pad: int = 16, reference_layout: bool = False, crop: int = CROP,
+               image_bytes: Optional[int] = None) -> torch.Tensor:
+    """K1.  images: u8 store (flat); image_shape (h, w, c); index_table int32 [n, planes, 4]
+    = (image id, crop top, crop left, flip).  Returns bf16 NHWC [n,crop,crop,c_pad], or with
+    reference_layout=True the reference's fp32 NCHW tensor [n, planes*c, crop, crop] (bit-exact)."""
+    _need_cuda(images, index_table)
+    assert images.dtype == torch.uint8 and index_table.dtype == torch.int32 and index_table.dim() == 3
+    h, w, c = image_shape
+    n, planes, four = index_table.shape
+    assert four == 4
+    nch = planes * c
+    assert len(mean) == nch and len(std) == nch, "one mean/std per stacked channel"
+    if image_bytes is None:
+        image_bytes = h * w * c
+    if reference_layout:
+        out = torch.empty((n, nch, crop, crop), dtype=torch.float32, device=images.device)
+    else:
+        out = torch.empty((n, crop, crop, c_pad), dtype=torch.bfloat16, device=images.device)
+    fm = (C.c_float * nch)(*mean)
+    fs = (C.c_float * nch)(*std)
+    check(_lib.load().va_preprocess(ptr(images), image_bytes, h, w, c, ptr(index_table), n, planes, crop, fm, fs, c_pad,
+                                    1 if reference_layout else 0, ptr(out), stream_ptr()), "va_preprocess")
+    return out
+
+
+def fuse(desc_s, desc_t, score_s, score_t, video_offsets: torch.Tensor, *, svm_w=None, svm_b=None, w_s=1.0, w_t=1.0,
+         out: Optional[dict] = None) -> dict:
+    """K4.  Per-video consensus (sequential-sum means) + late fusion.  Returns dict with video_desc [V,2D],
+    video_scores [V,C], score_pred [V], svm_scores [V,C] f64, svm_pred [V] (those that apply)."""
+    _need_cuda(desc_s, desc_t, score_s, score_t, video_offsets, svm_w, svm_b)
+    assert video_offsets.dtype == torch.int32
+    V = video_offsets.numel() - 1
+    ref = desc_s if desc_s is not None else score_s
+    dev = ref.device
+    D = desc_s.shape[1] if desc_s is not None else 1
+    Cn = score_s.shape[1] if score_s is not None else (svm_w.shape[0] if svm_w is not None else 1)
+    res = out if out is not None else {}
+    if desc_s is not None and "video_desc" not in res:
+        res["video_desc"] = torch.empty((V, 2 * D), dtype=torch.float32, device=dev)
+    if score_s is not None and "video_scores" not in res:
+        res["video_scores"] = torch.empty((V, Cn), dtype=torch.float32, device=dev)
+        res["score_pred"] = torch.empty((V,), dtype=torch.int32, device=dev)
+    if svm_w is not None and "svm_scores" not in res:
+        assert svm_w.dtype == torch.float64 and svm_b.dtype == torch.float64
+        res["svm_scores"] = torch.empty((V, Cn), dtype=torch.float64, device=dev)
+        res["svm_pred"] = torch.empty((V,), dtype=torch.int32, device=dev)
+    check(_lib.load().va_fuse(ptr(desc_s), ptr(desc_t), ptr(score_s), ptr(score_t), ptr(video_offsets), V, D, Cn,
+                              ptr(svm_w), ptr(svm_b), float(w_s), float(w_t), ptr(res.get("video_desc")),
+                              ptr(res.get("video_scores")), ptr(res.get("score_pred")), ptr(res.get("svm_scores")),
+                              ptr(res.get("svm_pred")), stream_ptr()), "va_fuse")
+    return res
+
+
+def synth_fill(images: torch.Tensor, image_shape: Sequence[int], n_images: int, *, seed: int, first_id: int = 0,
+               image_bytes: Optional[int] = None) -> torch.Tensor:
+    _need_cuda(images)
+    h, w, c = image_shape
+    if image_bytes is None:
+        image_bytes = h * w * c
+    assert images.numel() >= n_images * image_bytes
+    check(_lib.load().va_synth_fill(ptr(images), image_bytes, n_images, h, w, c, seed & 0xFFFFFFFF,
+                                    first_id & 0xFFFFFFFF, stream_ptr()), "va_synth_fill")
+    return images
+
+
+# reference state_dict order (torchvision vgg16 features + the swapped classifier, spatialModel.py:141-152)
+STATE_DICT_KEYS = [f"features.{i}.{p}" for i in (0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28) for p in ("weight", "bias")] + \
+                  [f"classifier.{i}.{p}" for i in (0, 3, 6, 9) for p in ("weight", "bias")]
+
+
+class StreamNet:
+    """One VGG16-D stream (spatial: 3 input channels, temporal: 2L=20) resident on the current CUDA device."""
+
+    def __init__(self, stream_kind: int, in_channels: int, n_classes: int = 101, desc_dim: int = 256, max_batch: int = 64):
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.va_create(C.byref(h), stream_kind, in_channels, n_classes, desc_dim, max_batch), "va_create")
+        self._h = h
+        self.stream_kind, self.in_channels = stream_kind, in_channels
+        self.n_classes, self.desc_dim, self.max_batch = n_classes, desc_dim, max_batch
+        self.c_pad = lib.va_input_channels_padded(h)
+        self._keep = None
+
+    def load_state_dict(self, state_dict) -> None:
+        """Accepts the reference checkpoint's "model" dict (keys may carry the DataParallel "module." prefix,
+        spatialModel.py:133,256-261)."""
+        sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in state_dict.items()}
+        missing = [k for k in STATE_DICT_KEYS if k not in sd]
+        if missing:
+            raise VAError(f"state_dict is missing {missing[:3]}...")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        tensors = [sd[k].detach().to(device=dev, dtype=torch.float32).contiguous() for k in STATE_DICT_KEYS]
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        check(_lib.load().va_load_weights(self._h, arr, len(tensors), stream_ptr()), "va_load_weights")
+        torch.cuda.current_stream().synchronize()   # packing done; fp32 staging copies may be freed
+
+    def forward(self, x_nhwc: torch.Tensor, *, want_logits=True, want_probs=True, want_pred=True):
+        """x bf16 [n,224,224,c_pad] -> (descriptors [n,D] f32, logits [n,C] f32, probs [n,C] f32, pred [n] i32)."""
+        _need_cuda(x_nhwc)
+        assert x_nhwc.dtype == torch.bfloat16 and tuple(x_nhwc.shape[1:]) == (CROP, CROP, self.c_pad), x_nhwc.shape
+        n = x_nhwc.shape[0]
+        dev = x_nhwc.device
+        desc = torch.empty((n, self.desc_dim), dtype=torch.float32, device=dev)
+        logits = torch.empty((n, self.n_classes), dtype=torch.float32, device=dev) if want_logits else None
+        probs = torch.empty((n, self.n_classes), dtype=torch.float32, device=dev) if want_probs else None
+        pred = torch.empty((n,), dtype=torch.int32, device=dev) if want_pred else None
+        check(_lib.load().va_forward(self._h, ptr(x_nhwc), n, ptr(desc), ptr(logits), ptr(probs), ptr(pred),
+                                     stream_ptr()), "va_forward")
+        return desc, logits, probs, pred
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().va_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,110 @@
+"""Synthetic UCF101-shaped video store resident in HBM (bench / test data; there is no network for datasets).
+
+Replaces the on-disk frame folders the reference reads with os.listdir + PIL.Image.open
+(Sheet03/spatialModel.py:72-77, temporalModel.py:76-86): per video, `n_frames` RGB frames named 0.jpg..n-1.jpg
+(every 10th video frame, utils.py:65) and `n_flows` x/y flow images flow_x_0001.. / flow_y_0001..
+(parameters.py:38-39).  Decoded images live in two flat u8 device buffers addressed by a global image id --
+the id is what the preprocess kernel's index table carries.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
+
+RGB_SHAPE = (240, 320, 3)     # UCF101 native; the reference never resizes (utils.py:116-120)
+FLOW_SHAPE = (256, 340, 1)    # TSN tvl1 tool convention for parameters.py:27's directory -- an assumption, a parameter
+STORE_SEED = 1234
+
+
+def _mix32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+@dataclass
+class VideoMeta:
+    """Where one video's images live in the flat stores (ids are global image indices)."""
+    name: str
+    category: str
+    label: int          # 1-based, as in demoTrain.txt
+    n_frames: int
+    rgb_first: int      # image id of frame "0.jpg" in the RGB store
+    n_flows: int
+    flowx_first: int    # image id of flow_x_0001 in the flow store
+    flowy_first: int    # image id of flow_y_0001
+
+
+@dataclass
+class StoreLayout:
+    """Pool of P distinct synthetic videos; video v of a larger job maps to pool entry v % P."""
+    videos: List[VideoMeta] = field(default_factory=list)
+    n_rgb_images: int = 0
+    n_flow_images: int = 0
+    rgb_shape: tuple = RGB_SHAPE
+    flow_shape: tuple = FLOW_SHAPE
+    seed: int = STORE_SEED
+
+    def video(self, v: int) -> VideoMeta:
+        return self.videos[v % len(self.videos)]
+
+    def list_line(self, v: int, mode: str = "train") -> str:
+        """A line in the format of demoTrain.txt / demoTest.txt (parsed by utils.videoInfo)."""
+        m = self.video(v)
+        base = f"{m.category}/{m.name}.avi"
+        return f"{base} {m.label}\n" if mode == "train" else base + "\n"
+
+
+def make_layout(pool: int, *, seed: int = STORE_SEED, min_frames: int = 12, frame_span: int = 19, n_classes: int = 25,
+                rgb_shape=RGB_SHAPE, flow_shape=FLOW_SHAPE) -> StoreLayout:
+    """n_frames_v = min_frames + hash(seed, v) % frame_span stored frames; n_flows_v = 2 * n_frames_v + 10."""
+    lay = StoreLayout(seed=seed, rgb_shape=tuple(rgb_shape), flow_shape=tuple(flow_shape))
+    rgb = flow = 0
+    for v in range(pool):
+        hv = _mix32(seed * 0x9E3779B1 + v * 0x85EBCA6B + 0x27D4EB2F)
+        nf = min_frames + hv % frame_span
+        nfl = 2 * nf + 10
+        label = 1 + v % n_classes
+        cat = f"Class{label:03d}"
+        name = f"v_{cat}_g{1 + (v // n_classes) % 25:02d}_c{1 + v % 7:02d}"
+        lay.videos.append(VideoMeta(name, cat, label, nf, rgb, nfl, flow, flow + nfl))
+        rgb += nf
+        flow += 2 * nfl
+    lay.n_rgb_images, lay.n_flow_images = rgb, flow
+    return lay
+
+
+class DeviceStore:
+    """The two flat u8 image buffers in HBM, generated on the device by va_synth_fill
+    (same integer hash as oracle/synth.py, so the CPU oracle can rebuild identical bytes)."""
+
+    def __init__(self, layout: StoreLayout, device=None):
+        import torch
+        from . import ops
+
+        self.layout = layout
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        h, w, c = layout.rgb_shape
+        hf, wf, cf = layout.flow_shape
+        self.rgb = torch.empty(max(1, layout.n_rgb_images) * h * w * c, dtype=torch.uint8, device=dev)
+        self.flow = torch.empty(max(1, layout.n_flow_images) * hf * wf * cf, dtype=torch.uint8, device=dev)
+        if layout.n_rgb_images:
+            ops.synth_fill(self.rgb, layout.rgb_shape, layout.n_rgb_images, seed=layout.seed)
+        if layout.n_flow_images:
+            ops.synth_fill(self.flow, layout.flow_shape, layout.n_flow_images, seed=layout.seed + 1)
+
+    @classmethod
+    def from_host(cls, layout: StoreLayout, rgb_u8, flow_u8, device=None):
+        """Upload host-decoded frames (numpy u8) instead of generating them."""
+        import torch
+
+        self = cls.__new__(cls)
+        self.layout = layout
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.rgb = torch.from_numpy(rgb_u8).reshape(-1).to(dev)
+        self.flow = torch.from_numpy(flow_u8).reshape(-1).to(dev)
+        return self
