@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: two-stream snippets/sec of the Sheet03 evaluation hot path on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+Workload (BASELINE.json configs[2], "Combined two-stream late fusion, 25 snippets x 10 crops per video, 101
+classes, synthetic UCF101-shaped clips"; configs[3] at N > 1): one STEP = `--videos-per-step` whole videos through
+preprocess (both streams) -> VGG16 spatial + temporal forward -> per-video consensus + late fusion; one "two-stream
+snippet" = one spatial forward + one temporal forward + its share of fusion.  Videos shard across ranks (weak
+scaling: per-GPU work fixed) and the per-video scores are all-gathered over NCCL inside the timed region.
+
+`value`   : device-timed (CUDA events, max over ranks) with the frame store already resident in HBM.
+`e2e`     : same metric through the public Python API with HOST (pinned) frames: every step copies its videos'
+            u8 frames and index tables host->device and reads the fused scores back, inside the timed region.
+`roofline`: the tensor-core layer kernel (conv_tc_kernel), ALGORITHMIC FLOPs / its live event-timed duration,
+            against MEASURED_PEAKS.json's sustained bf16 figure (the kernel is timed inside a long step).
+`cpu_baseline` / `--impl reference`: the reference's CPU path = oracle/two_stream.py on stock PyTorch fp32 (the
+            reference's scripts are Python-2 only and cannot run; kind "port"), bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SPATIAL_FLOPS = 30_934_485_504     # per snippet, SURVEY.md 8d / BASELINE.md section 3
+TEMPORAL_FLOPS = 31_917_132_288
+METRIC = "two-stream snippets/sec"
+UNIT = "snippets/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "hbm": float(d.get("hbm_gbs", 6650.0)),
+                "src": "MEASURED_PEAKS.json bf16_tflops_sustained"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained, 6.65 TB/s)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        # under-load samples: the upper half of the SM clock readings (idle gaps between steps excluded)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_pass(n_spatial, n_temporal, batch=10, threads=None):
+    """The reference's CPU path for the same workload, bounded: preprocess + forward + consensus + fusion of the
+    first n snippets of one synthetic video per stream, via the oracle port on stock PyTorch fp32."""
+    import numpy as np
+    import torch
+    from oracle import synth, two_stream as ts
+    from video_analytics_b200.store import make_layout
+    torch.set_num_threads(threads or os.cpu_count())
+    state = cpu_reference_pass.__dict__.setdefault("state", {})
+    if not state:
+        lay = make_layout(1)
+        rgb, flow = synth.build_store_numpy(lay)
+        state.update(store=ts.OracleStore(lay, rgb, flow), name=lay.videos[0].name, ms=ts.build_spatial_model(seed=0),
+                     mt=ts.build_temporal_model(seed=0))
+    st, name = state["store"], state["name"]
+    t0 = time.perf_counter()
+    # spatial: first n of the 250 protocol snippets
+    img_recs = [(f, c) for f in ts.test_frame_indices(st.n_frame_files(name)) for c in ts.ten_crop_params(*synth.RGB_SHAPE[:2])]
+    xs = torch.stack([ts.apply_transform(st.frame(name, f), i, j, fl, ts.NORM_MEANS_TF, ts.NORM_STDS_TF)
+                      for (f, (i, j, fl)) in img_recs[:n_spatial]])
+    ds, ss, _, _ = ts.video_consensus(state["ms"], xs, batch=batch)
+    mean, std = ts.flow_norm_constants(1)
+    stk = [(s, c) for s in ts.test_flow_starts(st.n_flow_files(name) // 2) for c in ts.ten_crop_params(*synth.FLOW_SHAPE[:2])]
+    xt = []
+    for (s, (i, j, fl)) in stk[:n_temporal]:
+        planes = []
+        for idx in range(s, s + ts.VIDEO_INPUT_FLOW_COUNT):
+            planes.append(ts.apply_transform(st.flow_x(name, idx), i, j, fl, mean, std))
+            planes.append(ts.apply_transform(st.flow_y(name, idx), i, j, fl, mean, std))
+        xt.append(torch.cat(planes, 0))
+    dt_, st_, _, _ = ts.video_consensus(state["mt"], torch.stack(xt), batch=batch)
+    fused = ts.fuse_scores(ss, st_)
+    _ = torch.cat([ds, dt_]), int(fused.argmax())
+    return time.perf_counter() - t0, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.ref_snippets
+    for _ in range(args.warmup):
+        cpu_reference_pass(n, n)
+    t = 0.0
+    cores = 0
+    for _ in range(args.steps):
+        dt, cores = cpu_reference_pass(n, n)
+        t += dt
+    value = args.steps * n / t
+    sample = f"{n} spatial + {n} temporal protocol snippets of one synthetic video per step (batch 10), preprocess+forward+consensus+fusion"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "two-stream 25x10 evaluation, 101 classes (BASELINE configs[2]); CPU reference arm: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--videos-per-step", type=int, default=2)
+    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic videos in the HBM store")
+    ap.add_argument("--max-batch", type=int, default=125, help="snippets per internal network chunk")
+    ap.add_argument("--ref-snippets", type=int, default=10, help="snippets per stream per CPU-reference step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from video_analytics_b200 import _lib, ops
+    from video_analytics_b200.combinedModel import CombinedModel
+    from video_analytics_b200.distributed import gather_video_rows, init_from_env, shard_bounds
+    from video_analytics_b200.evaluate import SNIPPETS_PER_VIDEO, TwoStreamEvaluator, spatial_table, temporal_table
+    from video_analytics_b200.spatialModel import build_spatial_torch_model
+    from video_analytics_b200.store import DeviceStore, VideoMeta, make_layout
+    from video_analytics_b200.temporalModel import build_temporal_torch_model
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback for the product path)")
+    rank, world, local = init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K, W, vps = args.steps, max(args.warmup, 0), args.videos_per_step
+    C, D = 101, 256
+
+    # ---- model + data (random-init weights of the reference architecture, synthetic frames; no network here)
+    spatial = ops.StreamNet(ops.STREAM_SPATIAL, 3, C, D, max_batch=args.max_batch)
+    temporal = ops.StreamNet(ops.STREAM_TEMPORAL, 20, C, D, max_batch=args.max_batch)
+    spatial.load_state_dict(build_spatial_torch_model(C, D, seed=0).state_dict())
+    temporal.load_state_dict(build_temporal_torch_model(C, 10, D, seed=0).state_dict())
+    layout = make_layout(args.pool)
+    store = DeviceStore(layout, dev)
+    combined = CombinedModel()
+    g = torch.Generator().manual_seed(3)
+    combined.set_svm(torch.randn(C, 2 * D, generator=g, dtype=torch.float64).numpy() * 0.05,
+                     torch.randn(C, generator=g, dtype=torch.float64).numpy() * 0.01)
+    ev = TwoStreamEvaluator(spatial, temporal, store, combined)
+
+    # videos of this job: world * (W + K) * vps, contiguous block per rank
+    n_videos = world * (W + K) * vps
+    lo, hi, per = shard_bounds(n_videos, rank, world)
+    out = ev.alloc_outputs(world * per, D, C, with_svm=True)
+    my = list(range(lo, hi))
+
+    def step(i):
+        vids = my[i * vps:(i + 1) * vps]
+        ev.run_videos(vids, out=out, out_row=rank * per + i * vps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib = _lib.load()
+    lib.va_profile_enable(1)
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        step(i)
+    gather_video_rows(out, rank, world, per)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    import ctypes as Ct
+    t_ms, t_l, t_f = Ct.c_double(), Ct.c_uint64(), Ct.c_double()
+    lib.va_profile_read(Ct.byref(t_ms), Ct.byref(t_l), Ct.byref(t_f))
+    lib.va_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    snippets = world * K * vps * SNIPPETS_PER_VIDEO
+    value = snippets / (total_ms * 1e-3)
+
+    # ---- end to end: host (pinned) frames -> H2D -> path -> D2H scores, every step, through the public API
+    rgb_host = store.rgb.cpu().pin_memory()
+    flow_host = store.flow.cpu().pin_memory()
+    rgb_img = layout.rgb_shape[0] * layout.rgb_shape[1] * layout.rgb_shape[2]
+    flow_img = layout.flow_shape[0] * layout.flow_shape[1] * layout.flow_shape[2]
+    max_fr = max(m.n_frames for m in layout.videos)
+    max_fl = max(m.n_flows for m in layout.videos)
+    stage = DeviceStore.__new__(DeviceStore)
+    stage.layout = layout
+    stage.rgb = torch.empty(vps * max_fr * rgb_img, dtype=torch.uint8, device=dev)
+    stage.flow = torch.empty(vps * 2 * max_fl * flow_img, dtype=torch.uint8, device=dev)
+    host_tables = {}
+
+    def staged_tables(k, slot):
+        if (k, slot) not in host_tables:
+            m = layout.videos[k]
+            sm = VideoMeta(m.name, m.category, m.label, m.n_frames, slot * max_fr, m.n_flows, slot * 2 * max_fl,
+                           slot * 2 * max_fl + m.n_flows)
+            host_tables[(k, slot)] = (torch.from_numpy(spatial_table(sm, layout.rgb_shape)).pin_memory(),
+                                      torch.from_numpy(temporal_table(sm, layout.flow_shape)).pin_memory())
+        return host_tables[(k, slot)]
+
+    res_host = {"video_scores": torch.empty((vps, C), dtype=torch.float32).pin_memory(),
+                "score_pred": torch.empty((vps,), dtype=torch.int32).pin_memory(),
+                "svm_pred": torch.empty((vps,), dtype=torch.int32).pin_memory()}
+    h2d = d2h = 0
+
+    def e2e_step(i, count=False):
+        nonlocal h2d, d2h
+        vids = my[i * vps:(i + 1) * vps]
+        tabs_s, tabs_t, nb = [], [], 0
+        for slot, v in enumerate(vids):
+            k = v % len(layout.videos)
+            m = layout.videos[k]
+            a, b = m.rgb_first * rgb_img, (m.rgb_first + m.n_frames) * rgb_img
+            stage.rgb[slot * max_fr * rgb_img: slot * max_fr * rgb_img + (b - a)].copy_(rgb_host[a:b], non_blocking=True)
+            a, b = m.flowx_first * flow_img, (m.flowx_first + 2 * m.n_flows) * flow_img
+            stage.flow[slot * 2 * max_fl * flow_img: slot * 2 * max_fl * flow_img + (b - a)].copy_(flow_host[a:b], non_blocking=True)
+            nb += m.n_frames * rgb_img + 2 * m.n_flows * flow_img
+            hs, ht = staged_tables(k, slot)
+            tabs_s.append(hs.to(dev, non_blocking=True)); tabs_t.append(ht.to(dev, non_blocking=True))
+            nb += hs.numel() * 4 + ht.numel() * 4
+        r = ev.run_tables(torch.cat(tabs_s), torch.cat(tabs_t), len(vids), store=stage)
+        nd = 0
+        for kname, hbuf in res_host.items():
+            hbuf[:len(vids)].copy_(r[kname], non_blocking=True)
+            nd += r[kname].numel() * r[kname].element_size()
+        torch.cuda.current_stream().synchronize()      # the step's result is on the host
+        if count:
+            h2d, d2h = nb, nd
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        e2e_step(i, count=(i == W))
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = snippets / float(e2e_s.item())
+
+    if rank == 0:
+        peaks = read_peaks()
+        achieved = (t_f.value / 1e12) / (t_ms.value * 1e-3) if t_ms.value > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "two-stream 25 snippets x 10 crops per video evaluation, 101 classes, VGG16 spatial(3ch)+temporal(20ch), "
+                                   "late fusion (BASELINE configs[2]; configs[3] sharding at N>1)",
+                       "videos_per_step_per_gpu": vps, "snippets_per_video_per_stream": SNIPPETS_PER_VIDEO,
+                       "global_videos_timed": world * K * vps, "parallelism": f"video-shard x{world} + all-gather of fused scores",
+                       "l2_policy": "inputs larger than L2: each step streams ~1.2 GB of preprocessed snippets and >800 MB activations per chunk",
+                       "weights": "random init (seed 0) of the reference architecture", "max_batch": args.max_batch},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": achieved,
+                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                         "peak_source": peaks["src"], "launches": int(t_l.value), "avg_launch_ms": t_ms.value / max(1, t_l.value),
+                         "flops_per_launch": t_f.value / max(1, t_l.value),
+                         "share_of_step": t_ms.value / total_ms if total_ms > 0 else None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n = args.ref_snippets
+            cpu_reference_pass(n, n)                                   # warm-up
+            t, reps, cores = 0.0, 0, 0
+            while t < 12.0 and reps < 6:
+                dt, cores = cpu_reference_pass(n, n)
+                t += dt
+                reps += 1
+            line["cpu_baseline"] = {"value": reps * n / t, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{reps} x ({n} spatial + {n} temporal protocol snippets, batch 10) of one synthetic video: "
+                                              "CPU preprocess + VGG16 fp32 forward + consensus + fusion (oracle/two_stream.py)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

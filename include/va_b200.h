@@ -107,10 +107,30 @@ va_status va_fuse(const float* desc_s, const float* desc_t, const float* score_s
                   float w_s, float w_t, float* video_desc, float* video_scores, int32_t* score_pred,
                   double* svm_scores, int32_t* svm_pred, va_stream_t stream);
 
+/* Running per-video descriptor sums: the device form of the reference's per-sample AverageMeter loop in
+ * train()/validate() (spatialModel.py:183-188, 223-228).  For b = 0..B-1 in order: sum[video_ids[b]][:] +=
+ * descriptors[b][:] (fp32, sequential -> the reference's summation order), count[video_ids[b]] += 1.
+ * sum fp32 [V][D], count int32 [V], video_ids int32 [B], descriptors fp32 [B][D]. */
+va_status va_consensus_update(float* sum, int32_t* count, const int32_t* video_ids, const float* descriptors, int B,
+                              int D, va_stream_t stream);
+
+/* Reference-layout network input (fp32 NCHW [n][channels][height][width], the tensor SpatialDataset/
+ * TemporalDataset.__getitem__ return and train()/validate() feed as `ip`, spatialModel.py:166-171) -> bf16 NHWC
+ * [n][height][width][c_pad] for va_forward. */
+va_status va_pack_input_nchw(const float* x_nchw, int n, int channels, int height, int width, int c_pad,
+                             void* out_nhwc, va_stream_t stream);
+
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,
                         uint32_t seed, uint32_t first_id, va_stream_t stream);
+
+/* Live profile of the tensor-core layer kernel (the dominant kernel): while enabled, every va_forward chunk records
+ * a CUDA event pair on its stream around its 16 conv/FC launches (the fp32 head launch is outside the pair).
+ * va_profile_read synchronises those events and returns, then clears, the accumulated device time (ms), the number
+ * of layer-kernel launches and their ALGORITHMIC FLOPs (2*MAC over real, unpadded channels). */
+va_status va_profile_enable(int on);
+va_status va_profile_read(double* tensor_ms, uint64_t* tensor_launches, double* tensor_flops);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 uint64_t va_launch_count(void);

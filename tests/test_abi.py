@@ -1,0 +1,61 @@
+"""The C-ABI library loads and exports exactly what include/va_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "va_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(va_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_path():
+    fns = header_functions()
+    for must in ("va_create", "va_load_weights", "va_preprocess", "va_forward", "va_fuse", "va_last_error"):
+        assert must in fns
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(str(built_lib))
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} declared in va_b200.h but not exported"
+
+
+def test_python_binding_covers_header(built_lib):
+    from video_analytics_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == header_functions()
+    handle = _lib.load()
+    assert handle.va_abi_version() == 1
+    assert handle.va_launch_count() == 0 or handle.va_launch_count() > 0   # callable without a GPU
+
+
+def test_no_cpu_fallback(built_lib):
+    """Product ops refuse CPU tensors instead of silently computing with torch."""
+    import torch
+    from video_analytics_b200 import ops
+    from video_analytics_b200._lib import VAError
+    x = torch.zeros(1, 8, 16, 64, dtype=torch.bfloat16)
+    w = torch.zeros(64, 64, 3, 3)
+    with pytest.raises(VAError):
+        ops.conv2d_nhwc(x, w, torch.zeros(64))
+    if not torch.cuda.is_available():
+        with pytest.raises(VAError):
+            ops.StreamNet(0, 3)   # va_create needs an sm_100 device
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """tcgen05 / TMA / TMEM instructions are present in the shipped cubin (UTCHMMA, UTMALDG, UTMASTG, LDTM)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(built_lib)], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass     # no legacy mma.sync path

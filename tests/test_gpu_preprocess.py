@@ -1,0 +1,100 @@
+"""K1 (fused snippet preprocess) and the synthetic store on the GPU vs the CPU oracle: bytes and fp32 pixels
+bit-exact, bf16 output == round-to-nearest of the oracle's fp32."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(t):
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def world():
+    from oracle import synth, two_stream as ts
+    from video_analytics_b200.store import DeviceStore, make_layout
+    lay = make_layout(3)
+    store = DeviceStore(lay)
+    rgb, flow = synth.build_store_numpy(lay)
+    return lay, store, rgb, flow, ts.OracleStore(lay, rgb, flow)
+
+
+def test_device_store_equals_oracle_store(world):
+    lay, store, rgb, flow, _ = world
+    assert np.array_equal(store.rgb.cpu().numpy()[:rgb.size].reshape(rgb.shape), rgb)
+    assert np.array_equal(store.flow.cpu().numpy()[:flow.size].reshape(flow.shape), flow)
+
+
+def test_golden_transform_cases_bit_exact(golden):
+    """The kernel reproduces the sha256 the REFERENCE's getTransforms() output had (tests/golden/transform_cases.json)."""
+    from oracle import synth
+    from video_analytics_b200 import ops
+    for c in golden("transform_cases.json"):
+        shape = tuple(c["shape"])
+        img = synth.synth_image(c["store_seed"], c["image_id"], shape)
+        dev_img = torch.from_numpy(img).reshape(-1).cuda()
+        table = torch.tensor([[[0, c["i"], c["j"], c["flip"]]]], dtype=torch.int32, device="cuda")
+        mean, std = ([0.485], [0.229]) if c["flow"] else ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+        out = ops.preprocess(dev_img, shape, table, mean, std, reference_layout=True)
+        assert out.shape == (1, shape[2], 224, 224)
+        assert sha(out[0]) == c["sha256"], c
+
+
+def test_protocol_snippets_bit_exact_and_bf16_rounding(world):
+    from oracle import two_stream as ts
+    from video_analytics_b200 import ops
+    from video_analytics_b200.evaluate import spatial_table, temporal_table
+    lay, store, _, _, ost = world
+    m = lay.videos[1]
+    sel = [0, 9, 10, 55, 128, 249]
+    snips_s, _ = ts.video_snippets_spatial(ost, m.name)
+    snips_t, _ = ts.video_snippets_temporal(ost, m.name)
+    tab_s = torch.from_numpy(spatial_table(m, lay.rgb_shape)[sel]).cuda()
+    tab_t = torch.from_numpy(temporal_table(m, lay.flow_shape)[sel]).cuda()
+    ref_s = ops.preprocess(store.rgb, lay.rgb_shape, tab_s, ts.NORM_MEANS_TF, ts.NORM_STDS_TF, reference_layout=True)
+    assert torch.equal(ref_s.cpu(), snips_s[sel])
+    ref_t = ops.preprocess(store.flow, lay.flow_shape, tab_t, [0.485] * 20, [0.229] * 20, reference_layout=True)
+    assert torch.equal(ref_t.cpu(), snips_t[sel])
+    # network layout: bf16 NHWC, zero padded channels
+    x_s = ops.preprocess(store.rgb, lay.rgb_shape, tab_s, ts.NORM_MEANS_TF, ts.NORM_STDS_TF, c_pad=16).cpu()
+    assert torch.equal(x_s[..., :3], snips_s[sel].permute(0, 2, 3, 1).bfloat16())
+    assert float(x_s[..., 3:].abs().max()) == 0.0
+    x_t = ops.preprocess(store.flow, lay.flow_shape, tab_t, [0.485] * 20, [0.229] * 20, c_pad=32).cpu()
+    assert torch.equal(x_t[..., :20], snips_t[sel].permute(0, 2, 3, 1).bfloat16())
+    assert float(x_t[..., 20:].abs().max()) == 0.0
+
+
+def test_per_image_crop_quirk_and_generic_shapes(world):
+    """20 independent crops/flips per stack (reference temporalModel.py:86) and a non-standard plane count."""
+    from oracle import two_stream as ts
+    from video_analytics_b200 import ops
+    lay, store, _, flow, _ = world
+    g = torch.Generator().manual_seed(3)
+    for planes in (20, 6):
+        n = 3
+        ids = torch.randint(0, lay.n_flow_images, (n, planes), generator=g)
+        ci = torch.randint(0, 256 - 224 + 1, (n, planes), generator=g)
+        cj = torch.randint(0, 340 - 224 + 1, (n, planes), generator=g)
+        fl = torch.randint(0, 2, (n, planes), generator=g)
+        table = torch.stack([ids, ci, cj, fl], dim=-1).to(torch.int32).cuda()
+        out = ops.preprocess(store.flow, lay.flow_shape, table, [0.485] * planes, [0.229] * planes, reference_layout=True).cpu()
+        for a in range(n):
+            for p in range(planes):
+                ref = ts.apply_transform(flow[int(ids[a, p])], int(ci[a, p]), int(cj[a, p]), int(fl[a, p]), [0.485], [0.229])
+                assert torch.equal(out[a, p], ref[0])
+
+
+def test_empty_and_invalid(world):
+    from video_analytics_b200 import ops
+    from video_analytics_b200._lib import VAError
+    lay, store, _, _, _ = world
+    empty = torch.zeros((0, 1, 4), dtype=torch.int32, device="cuda")
+    out = ops.preprocess(store.rgb, lay.rgb_shape, empty, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225], c_pad=16)
+    assert out.shape == (0, 224, 224, 16)
+    with pytest.raises(VAError):
+        ops.preprocess(store.rgb, (100, 320, 3), torch.zeros((1, 1, 4), dtype=torch.int32, device="cuda"),
+                       [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])          # crop larger than the image

@@ -1,0 +1,193 @@
+"""Host-side logic of the product package (no GPU): list parsing, RNG draw order, index tables, CSV wire format,
+sharding.  The oracle (restated reference) is the checker."""
+import io
+import random
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import two_stream as ts
+from video_analytics_b200 import utils as U
+from video_analytics_b200.distributed import shard_bounds
+from video_analytics_b200.evaluate import spatial_table, temporal_table
+from video_analytics_b200.store import make_layout
+
+
+def test_videoinfo_matches_reference(golden):
+    g = golden("videoinfo_samples.json")
+    for mode in ("train", "test"):
+        for s in g["samples"][mode]:
+            assert list(U.videoInfo(s["line"], mode)) == s["expect"]
+    with pytest.raises(ValueError):
+        U.videoInfo("NoSlashHere.avi 3", "train")            # the reference raises on malformed lines too
+
+
+def test_transform_draw_order_matches_oracle():
+    tr = U.getTransforms()
+    for seed, (h, w) in enumerate([(240, 320), (256, 340), (224, 224), (224, 300)]):
+        torch.manual_seed(seed)
+        a = [tr.draw(h, w) for _ in range(5)]
+        after_a = torch.rand(1)
+        torch.manual_seed(seed)
+        b = [ts.draw_transform_params(h, w) for _ in range(5)]
+        after_b = torch.rand(1)
+        assert a == b and torch.equal(after_a, after_b)       # same draws AND same RNG state afterwards
+    with pytest.raises(ValueError):
+        tr.draw(200, 320)
+    with pytest.raises(NotImplementedError):
+        U.getTransforms(jitter=[0.1, 0, 0, 0])
+
+
+def test_norm_constants():
+    tr = U.getTransforms()
+    assert tr.norm_constants(3, 3) == ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    m, s = tr.norm_constants(20, 1)
+    assert m == [0.485] * 20 and s == [0.229] * 20           # 2018 zip semantics for 1-channel flow images
+
+
+class _StubStore:
+    def __init__(self, layout):
+        self.layout = layout
+
+
+def _datasets(tmp_path, lay, mode="train"):
+    from video_analytics_b200.spatialModel import SpatialDataset
+    from video_analytics_b200.temporalModel import TemporalDataset
+    lst, cls = tmp_path / "list.txt", tmp_path / "classInd.txt"
+    lst.write_text("".join(lay.list_line(v, mode) for v in range(len(lay.videos))))
+    cls.write_text("".join(f"{m.label} {m.category}\n" for m in lay.videos))
+    tr = U.getTransforms()
+    sd = SpatialDataset(str(lst), None, tr, mode=mode, actionLabelLoc=str(cls), store=_StubStore(lay))
+    td = TemporalDataset(str(lst), None, tr, mode=mode, actionLabelLoc=str(cls), store=_StubStore(lay))
+    return sd, td, lst.read_text().splitlines(keepends=True), {m.category: m.label for m in lay.videos}
+
+
+@pytest.mark.parametrize("mode", ["train", "test"])
+def test_dataset_indices_bit_exact_vs_oracle(tmp_path, mode):
+    """Snippet, crop and flip indices are bit-exact with the restated reference datasets under the same seeds."""
+    lay = make_layout(5)
+    sd, td, lines, labels = _datasets(tmp_path, lay, mode)
+    ost = ts.OracleStore(lay, np.zeros((lay.n_rgb_images,) + tuple(lay.rgb_shape), np.uint8),
+                         np.zeros((lay.n_flow_images,) + tuple(lay.flow_shape), np.uint8))
+    osd = ts.SpatialDataset(lines, ost, mode=mode, actionLabelDict=labels)
+    otd = ts.TemporalDataset(lines, ost, mode=mode, actionLabelDict=labels)
+    for seed in range(6):
+        for idx in range(5):
+            random.seed(seed * 7 + idx); torch.manual_seed(seed * 7 + idx)
+            rows, label, name = sd.sample_indices(idx)
+            random.seed(seed * 7 + idx); torch.manual_seed(seed * 7 + idx)
+            _, olabel, oname = osd[idx]
+            assert (label, name) == (olabel, oname)
+            assert sd.last_indices == osd.last_indices
+            m = lay.videos[idx]
+            assert rows.tolist() == [[m.rgb_first + osd.last_indices["frame"], *osd.last_indices["crops"][0]]]
+            random.seed(seed * 7 + idx); torch.manual_seed(seed * 7 + idx)
+            rows, label, name = td.sample_indices(idx)
+            random.seed(seed * 7 + idx); torch.manual_seed(seed * 7 + idx)
+            _, olabel, oname = otd[idx]
+            assert (label, name) == (olabel, oname) and td.last_indices == otd.last_indices
+            s = otd.last_indices["start"]
+            assert 1 <= s <= m.n_flows - 10
+            assert rows.shape == (20, 4)
+            assert rows[0::2, 0].tolist() == [m.flowx_first + s - 1 + l for l in range(10)]     # x_t, then
+            assert rows[1::2, 0].tolist() == [m.flowy_first + s - 1 + l for l in range(10)]     # y_t interleaved
+            assert len(set(map(tuple, rows[:, 1:].tolist()))) > 1                                # per-image crops (quirk)
+
+
+def test_dataset_errors(tmp_path):
+    from video_analytics_b200.spatialModel import SpatialDataset
+    lay = make_layout(1)
+    lst = tmp_path / "l.txt"
+    lst.write_text(lay.list_line(0))
+    with pytest.raises(ValueError, match="Action label dictionary required!"):
+        SpatialDataset(str(lst), None, U.getTransforms(), store=_StubStore(lay))
+
+
+def test_protocol_tables_match_oracle_records():
+    lay = make_layout(3)
+    ost = ts.OracleStore(lay, np.zeros((lay.n_rgb_images, 1, 1, 3), np.uint8), np.zeros((lay.n_flow_images, 1, 1, 1), np.uint8))
+    for m in lay.videos:
+        st = spatial_table(m, lay.rgb_shape)
+        assert st.shape == (250, 1, 4) and st.dtype == np.int32
+        frames = ts.test_frame_indices(m.n_frames)
+        crops = ts.ten_crop_params(*lay.rgb_shape[:2])
+        expect = [[m.rgb_first + f, *c] for f in frames for c in crops]
+        assert st.reshape(250, 4).tolist() == expect
+        tt = temporal_table(m, lay.flow_shape)
+        assert tt.shape == (250, 20, 4)
+        starts = ts.test_flow_starts(m.n_flows)
+        fcrops = ts.ten_crop_params(*lay.flow_shape[:2])
+        k = 0
+        for s in starts:
+            for c in fcrops:
+                assert tt[k, 0::2, 0].tolist() == [m.flowx_first + s - 1 + l for l in range(10)]
+                assert tt[k, 1::2, 0].tolist() == [m.flowy_first + s - 1 + l for l in range(10)]
+                assert all(r == list(c) for r in tt[k, :, 1:].tolist())
+                k += 1
+        assert tt[:, :, 0].max() < lay.n_flow_images and st[:, :, 0].max() < lay.n_rgb_images
+
+
+def test_ten_crop_and_indices_equal_oracle():
+    for (h, w) in ((240, 320), (256, 340), (225, 231)):
+        assert U.ten_crop_params(h, w) == ts.ten_crop_params(h, w)
+    for n in (12, 17, 30):
+        assert U.test_frame_indices(n) == ts.test_frame_indices(n)
+        assert U.test_flow_starts(2 * n + 10) == ts.test_flow_starts(2 * n + 10)
+
+
+def test_average_meter_and_csv_wire_format(golden, tmp_path):
+    g = golden("combine_descriptors.json")
+    # rebuild the dict the golden CSV was written from (same seed, same draw order as make_golden.py)
+    torch.manual_seed(g["seed"])
+    d = {}
+    for v in range(5):
+        m = U.AverageMeter()
+        for _ in range(3):
+            m.update(torch.rand(256))
+        d[f"v_Class{v:03d}_g01_c01"] = (m, torch.tensor(1 + v))
+    out = tmp_path / "s.csv"
+    U.saveVideoDescriptors(d, str(out))
+    assert out.read_bytes().replace(b"\r\n", b"\n") == g["csv_spatial"].encode().replace(b"\r\n", b"\n")
+    # and the product join equals the reference's on the golden files
+    from video_analytics_b200.combinedModel import combineDescriptors
+    pt = tmp_path / "t.csv"
+    pt.write_text(g["csv_temporal"], newline="")
+    X, y = combineDescriptors(str(out), str(pt))
+    Xo, yo = ts.combineDescriptors(str(out), str(pt))
+    assert np.array_equal(X, Xo) and np.array_equal(y, yo) and X.shape == (5, 512)
+
+
+def test_save_performance_and_dirs(tmp_path):
+    p = tmp_path / "perf.csv"
+    U.savePerformance(0.5, 1.25, str(p))
+    U.savePerformance(0.75, 0.5, str(p))
+    assert p.read_text() == "0.5,1.25\n0.75,0.5\n"
+    a, b = tmp_path / "x" / "y", tmp_path / "z"
+    assert U.checkAndMakeDirectories(str(a), str(b)) == [False, False]
+    assert U.checkAndMakeDirectories(str(a), str(b)) == [True, True]
+    assert float(U.getOneHot(3, 25)[0, 2]) == 1.0
+
+
+def test_shard_bounds():
+    assert shard_bounds(3783, 0, 8) == (0, 473, 473)
+    assert shard_bounds(3783, 7, 8) == (3311, 3783, 473)       # last rank: 472 videos + 1 padding row
+    covered = []
+    for V, R in ((3783, 8), (10, 4), (3, 8), (16, 2), (1, 1)):
+        rows = []
+        for r in range(R):
+            lo, hi, per = shard_bounds(V, r, R)
+            assert 0 <= lo <= hi <= V and hi - lo <= per
+            rows += list(range(lo, hi))
+        assert rows == list(range(V))
+
+
+def test_layout_is_deterministic_and_valid():
+    a, b = make_layout(8), make_layout(8)
+    assert a.videos == b.videos
+    for m in a.videos:
+        assert m.n_frames >= 12 and m.n_flows >= 10 + 1 and 1 <= m.label <= 25
+        assert m.flowy_first == m.flowx_first + m.n_flows
+    line = a.list_line(3, "train")
+    assert U.videoInfo(line, "train")[1] == a.videos[3].name

@@ -1,0 +1,104 @@
+"""Late fusion of the two streams -- API-compatible with the reference's `Sheet03/combinedModel.py`
+(`combineDescriptors` :9-26, `main` :29-43) plus the explicit `CombinedModel` class named by the north star.
+
+`combineDescriptors` keeps the CSV wire format (it is a one-off host-side join); per-video consensus, the 512-d
+concatenation, LinearSVC scoring (argmax_c X.W_c + b_c) and the class-score average run in the CUDA fusion kernel
+(`va_fuse`).  Fitting the SVM stays in scikit-learn on the host (out of scope).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .parameters import *  # noqa: F401,F403
+
+
+def combineDescriptors(spatialCsv, temporalCsv):
+    """reference combinedModel.py:9-26 -- inner-join the two descriptor CSVs on the video name and return
+    (descriptors [V, 2*VIDEO_DESCRIPTOR_DIM] float64 = [spatial | temporal], labels [V] from the spatial file)."""
+    import pandas as pd
+    columns = ["vidname", "label"] + ["dim" + str(d) for d in range(VIDEO_DESCRIPTOR_DIM)]
+    spatial = pd.read_csv(spatialCsv, names=columns)
+    temporal = pd.read_csv(temporalCsv, names=columns)
+    merged = pd.merge(spatial, temporal, on="vidname", how="inner", suffixes=("_s", "_t"))
+    wanted = [c + "_s" for c in columns[2:]] + [c + "_t" for c in columns[2:]]
+    return merged[wanted].values, merged["label_s"].values
+
+
+class CombinedModel:
+    """Two-stream late fusion on the GPU.
+
+    * `fit(X, y)`: scikit-learn LinearSVC on the host (reference :34-35), coefficients uploaded once.
+    * `predict(X)`: reference :38 -- `classes_[argmax(X @ coef.T + intercept)]`, scored by `va_fuse` in fp64.
+    * `fuse(...)`: the whole K4 step for a batch of videos straight from per-snippet network outputs.
+    """
+
+    def __init__(self, w_spatial: float = STREAM_WEIGHT_SPATIAL, w_temporal: float = STREAM_WEIGHT_TEMPORAL):
+        self.w_s, self.w_t = float(w_spatial), float(w_temporal)
+        self.classes_: Optional[np.ndarray] = None
+        self.coef_ = self.intercept_ = None
+        self._w_dev = self._b_dev = None
+
+    # ---- SVM
+    def fit(self, descriptors: np.ndarray, labels: np.ndarray):
+        from sklearn import svm
+        clf = svm.LinearSVC()
+        clf.fit(descriptors, labels)
+        return self.set_svm(clf.coef_, clf.intercept_, clf.classes_)
+
+    def set_svm(self, coef, intercept, classes=None):
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        intercept = np.ascontiguousarray(intercept, dtype=np.float64)
+        if coef.shape[0] == 1:
+            # sklearn stores a single hyperplane for two classes: score > 0 -> classes_[1].  Expand to one-vs-rest
+            # rows so that argmax reproduces predict().
+            coef = np.concatenate([-coef, coef], axis=0)
+            intercept = np.concatenate([-intercept, intercept], axis=0)
+        self.coef_, self.intercept_ = coef, intercept
+        self.classes_ = np.arange(coef.shape[0]) if classes is None else np.asarray(classes)
+        self._w_dev = torch.from_numpy(coef).cuda()
+        self._b_dev = torch.from_numpy(intercept).cuda()
+        return self
+
+    def decision_function(self, descriptors) -> torch.Tensor:
+        """[V, C] fp64 scores on the device for already-fused descriptors [V, 2D] (numpy or tensor)."""
+        X = torch.as_tensor(np.asarray(descriptors) if not isinstance(descriptors, torch.Tensor) else descriptors)
+        X = X.to(device="cuda", dtype=torch.float32).contiguous()
+        V, twoD = X.shape
+        D = twoD // 2
+        # each video is its own 1-snippet segment; the kernel's mean over one element is the identity
+        offs = torch.arange(V + 1, dtype=torch.int32, device="cuda")
+        ds, dt = X[:, :D].contiguous(), X[:, D:].contiguous()
+        res = ops.fuse(ds, dt, None, None, offs, svm_w=self._w_dev, svm_b=self._b_dev)
+        self._last = res
+        return res["svm_scores"]
+
+    def predict(self, descriptors) -> np.ndarray:
+        self.decision_function(descriptors)
+        idx = self._last["svm_pred"].cpu().numpy()
+        return self.classes_[idx]
+
+    # ---- full K4 step
+    def fuse(self, desc_s, desc_t, score_s, score_t, video_offsets, out=None):
+        """Per-video consensus over each video's snippets + late fusion; see ops.fuse."""
+        return ops.fuse(desc_s, desc_t, score_s, score_t, video_offsets, svm_w=self._w_dev, svm_b=self._b_dev,
+                        w_s=self.w_s, w_t=self.w_t, out=out)
+
+
+def main():
+    """reference combinedModel.py:29-43 with the GPU scorer."""
+    import joblib
+    trainX, trainY = combineDescriptors(SPATIAL_TRAIN_CSV_LOC, TEMPORAL_TRAIN_CSV_LOC)
+    testX, testY = combineDescriptors(SPATIAL_TEST_CSV_LOC, TEMPORAL_TEST_CSV_LOC)
+    model = CombinedModel().fit(trainX, trainY)
+    joblib.dump({"coef": model.coef_, "intercept": model.intercept_, "classes": model.classes_}, SVM_FILE)
+    preds = model.predict(testX)
+    acc = sum(int(p == a) for p, a in zip(preds, testY))
+    print("accuracy = %f percent" % ((acc * 100.0) / len(testY)))
+
+
+if __name__ == "__main__":
+    main()

@@ -9,10 +9,22 @@
 #include <string.h>
 #include <new>
 
+#include <vector>
+
 namespace va {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace va
+
+// Optional live profile of the tensor-core layer kernel: event pairs bracket the conv/FC launches of every
+// va_forward chunk on the launching stream; bench.py reads them after the timed region (roofline.achieved).
+namespace {
+struct ProfSpan { cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfSpan> g_prof_spans;
+uint64_t g_prof_launches = 0;
+double g_prof_flops = 0.0;
+}  // namespace
 
 namespace {
 
@@ -184,6 +196,13 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
     const int nb = (n - off) < h->max_batch ? (n - off) : h->max_batch;
     const void* x = static_cast<const uint8_t*>(in_nhwc) + (size_t)off * in_stride;
     int H = kCrop, cin_pad = h->cin_pad, cur = 0;
+    ProfSpan span{nullptr, nullptr};
+    if (g_prof_on) {
+      VA_CUDA(cudaEventCreate(&span.a));
+      VA_CUDA(cudaEventCreate(&span.b));
+      VA_CUDA(cudaEventRecord(span.a, st));
+    }
+    int cin_real = h->cin;
     for (int i = 0; i < 13; ++i) {
       va::ConvLayerDesc d;
       d.x = x; d.n = nb; d.H = H; d.W = H; d.cin_pad = cin_pad;
@@ -191,7 +210,8 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
       d.relu = 1; d.pool = kVgg16[i].pool ? 1 : 0; d.y = h->act[cur]; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0;
       if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "conv layer %d: %s", i, e);
       x = h->act[cur]; cur ^= 1;
-      cin_pad = d.Cout;
+      if (g_prof_on) { g_prof_flops += 2.0 * nb * H * H * (double)d.Cout * 9.0 * cin_real; ++g_prof_launches; }
+      cin_pad = d.Cout; cin_real = d.Cout;
       if (d.pool) H >>= 1;
     }
     float* desc_out = descriptors ? descriptors + (size_t)off * h->desc_dim : h->desc_ws;
@@ -206,6 +226,11 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
       d.y_f32 = (i < 2) ? nullptr : desc_out;
       if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "fc layer %d: %s", i + 1, e);
       x = h->act[cur]; cur ^= 1;
+      if (g_prof_on) { g_prof_flops += 2.0 * nb * (double)fin[i] * fout[i]; ++g_prof_launches; }
+    }
+    if (g_prof_on) {
+      VA_CUDA(cudaEventRecord(span.b, st));
+      g_prof_spans.push_back(span);
     }
     VA_CUDA(va::launch_head(desc_out, h->w4t, h->b4, nb, h->desc_dim, h->n_classes,
                             logits ? logits + (size_t)off * h->n_classes : nullptr,
@@ -263,6 +288,49 @@ va_status va_fuse(const float* desc_s, const float* desc_t, const float* score_s
   if (va_status s = require_sm100()) return s;
   VA_CUDA(va::launch_fuse(desc_s, desc_t, score_s, score_t, video_offsets, V, D, C, svm_w, svm_b, w_s, w_t, video_desc,
                           video_scores, score_pred, svm_scores, svm_pred, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+va_status va_consensus_update(float* sum, int32_t* count, const int32_t* video_ids, const float* descriptors, int B, int D,
+                              va_stream_t stream) {
+  if (!sum || !count || !video_ids || !descriptors) return fail(VA_ERR_INVALID, "va_consensus_update: NULL argument");
+  if (B < 0 || D < 1) return fail(VA_ERR_INVALID, "va_consensus_update: bad sizes");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_consensus_update(sum, count, video_ids, descriptors, B, D, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+va_status va_pack_input_nchw(const float* x_nchw, int n, int channels, int height, int width, int c_pad, void* out_nhwc,
+                             va_stream_t stream) {
+  if (!x_nchw || !out_nhwc) return fail(VA_ERR_INVALID, "va_pack_input_nchw: NULL argument");
+  if (channels > c_pad || !(c_pad == 16 || c_pad == 32 || c_pad == 64))
+    return fail(VA_ERR_INVALID, "va_pack_input_nchw: channels %d / c_pad %d", channels, c_pad);
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_nchw_to_nhwc(x_nchw, n, channels, height * width, c_pad, out_nhwc, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+va_status va_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return VA_OK;
+}
+
+va_status va_profile_read(double* tensor_ms, uint64_t* tensor_launches, double* tensor_flops) {
+  double ms = 0.0;
+  for (ProfSpan& sp : g_prof_spans) {
+    VA_CUDA(cudaEventSynchronize(sp.b));
+    float t = 0.f;
+    VA_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms += t;
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  g_prof_spans.clear();
+  if (tensor_ms) *tensor_ms = ms;
+  if (tensor_launches) *tensor_launches = g_prof_launches;
+  if (tensor_flops) *tensor_flops = g_prof_flops;
+  g_prof_launches = 0;
+  g_prof_flops = 0.0;
   return VA_OK;
 }
 

@@ -137,7 +137,9 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
       if (R == 3 && bn == 256) continue;
       const long long tiles = (long long)tiles_m * (d.Cout / bn);
       const long long waves = (tiles + sms - 1) / sms;
-      const double eff = bn == 256 ? 1.0 : (bn == 128 ? 1.08 : 1.45);
+      // relative cost per output column, measured on B200 (profiles/r01_diag_forward_call1.log): narrower N tiles
+      // re-read the A patch from L2 more often and are L2->SM bandwidth bound.
+      const double eff = bn == 256 ? 1.0 : (bn == 128 ? 1.5 : 2.6);
       const double cost = (double)waves * bn * eff;
       if (cost < best) { best = cost; BN = bn; }
     }

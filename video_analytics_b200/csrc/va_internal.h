@@ -26,6 +26,11 @@ cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* s
                         float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
                         int32_t* svm_pred, cudaStream_t st);
 
+cudaError_t launch_consensus_update(float* sum, int32_t* count, const int32_t* video_ids, const float* fv, int B, int D,
+                                    cudaStream_t st);
+
+cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad, void* out, cudaStream_t st);
+
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
 struct ConvLayerDesc {
   const void* x;        // bf16 NHWC [n][H][W][cin_pad]

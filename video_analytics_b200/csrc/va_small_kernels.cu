@@ -363,4 +363,66 @@ cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* s
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ C1 (epoch mode)
+// Running per-video descriptor sums, the device form of the reference's per-sample AverageMeter loop
+// (spatialModel.py:223-228): for b in batch order: sum[video[b]] += fv[b]; count[video[b]] += 1.
+// One thread per descriptor dimension walks the batch sequentially, so the fp32 sum order is the reference's
+// even when a video appears twice in a batch.
+__global__ void consensus_update_kernel(float* __restrict__ sum, int32_t* __restrict__ count,
+                                        const int32_t* __restrict__ video_ids, const float* __restrict__ fv, int B,
+                                        int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  for (int b = 0; b < B; ++b) {
+    const int v = video_ids[b];
+    float* dst = sum + (size_t)v * D + d;
+    *dst = __fadd_rn(*dst, fv[(size_t)b * D + d]);
+    if (d == 0) count[v] += 1;
+  }
+}
+cudaError_t launch_consensus_update(float* sum, int32_t* count, const int32_t* video_ids, const float* fv, int B, int D,
+                                    cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  count_launch();
+  consensus_update_kernel<<<(D + 127) / 128, 128, 0, st>>>(sum, count, video_ids, fv, B, D);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ layout import
+// Reference-layout snippets (fp32 NCHW, what SpatialDataset.__getitem__ returns) -> network input (bf16 NHWC,
+// channels zero-padded to c_pad).  One thread per pixel; each channel plane is read coalesced.
+template <int C_PAD>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int hw,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n * hw) return;
+  const int img = (int)(g / hw), pix = (int)(g % hw);
+  const float* src = x + (size_t)img * c * hw + pix;
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)g * C_PAD);
+#pragma unroll
+  for (int c0 = 0; c0 < C_PAD; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (c0 + k < c) ? __ldg(src + (size_t)(c0 + k) * hw) : 0.f;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 cc = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.z = *reinterpret_cast<uint32_t*>(&cc); o.w = *reinterpret_cast<uint32_t*>(&d);
+    dst[c0 / 8] = o;
+  }
+}
+cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad, void* out, cudaStream_t st) {
+  const long long total = (long long)n * hw;
+  if (total == 0) return cudaSuccess;
+  if (c > c_pad) return cudaErrorInvalidValue;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  count_launch();
+  if (c_pad == 16) nchw_to_nhwc_kernel<16><<<blocks, 256, 0, st>>>(x, n, c, hw, reinterpret_cast<__nv_bfloat16*>(out));
+  else if (c_pad == 32) nchw_to_nhwc_kernel<32><<<blocks, 256, 0, st>>>(x, n, c, hw, reinterpret_cast<__nv_bfloat16*>(out));
+  else if (c_pad == 64) nchw_to_nhwc_kernel<64><<<blocks, 256, 0, st>>>(x, n, c, hw, reinterpret_cast<__nv_bfloat16*>(out));
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 }  // namespace va
