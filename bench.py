@@ -67,6 +67,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken before this call (warm-up) are excluded from the summary."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -77,7 +81,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -157,7 +161,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--videos-per-step", type=int, default=2)
@@ -218,12 +222,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()               # nvidia-smi needs ~1 s to produce its first line: start it before the warm-up
     for i in range(W):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     lib = _lib.load()
     lib.va_profile_enable(1)
     launches0 = _lib.launch_count()

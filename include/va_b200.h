@@ -83,7 +83,8 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
 /* Layer primitives behind va_forward, exported for per-layer parity tests and profiling.
  * conv: x bf16 NHWC [n][H][W][cin_pad]; w fp32 OIHW [cout][cin][ks][ks]; y bf16 NHWC [n][H(/2)][W(/2)][cout].
  *       ks in {1,3}, stride 1, zero pad (ks-1)/2; optional fused ReLU and 2x2/2 max-pool.
- *       force_bn in {0 (auto),64,128,256}; force_r in {0 (auto),1,3} select kernel variants.
+ *       force_bn in {0 (auto),64,128,256}; force_r in {0 (auto), 1 (one tap per stage), 3 (vertical tap reuse),
+ *       9 (whole 3x3 filter per stage, Cin_pad 16/32 only)} select kernel variants.
  * linear: x bf16 [n][in]; w fp32 [out][in]; y bf16 [n][out] and/or y_f32 fp32 [n][out] (exactly one). */
 va_status va_conv2d_nhwc(const void* x, int n, int H, int W, int cin, int cin_pad, const float* w,
                          const float* bias, int cout, int ks, int relu, int pool, void* y, int force_bn,

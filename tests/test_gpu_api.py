@@ -147,8 +147,9 @@ def test_temporal_network_and_fusion_pipeline(setup):
     oracle_model = ts.build_temporal_model(seed=5)
     net.model.module.load_state_dict(oracle_model.state_dict())
     net.sync_weights()
+    it = iter(loader)                      # creating the iterator draws the loader's base seed from the torch RNG
     random.seed(3); torch.manual_seed(3)
-    batch, labels, names = next(iter(loader))
+    batch, labels, names = next(it)        # items (and their RNG draws) are produced here
     fv, logits = net.forward(batch)
     random.seed(3); torch.manual_seed(3)
     otd = ts.TemporalDataset(s["lines"], s["ost"], actionLabelDict=s["labels"])

@@ -46,6 +46,13 @@ CONV_CASES = [
     (33, 14, 512, 512, 512, 1, 0, 1),              # 2x2x32
     (2, 32, 3, 16, 64, 0, 64, 1),                  # conv1_1 spatial: 16-channel k-blocks, 32B swizzle
     (2, 32, 20, 32, 64, 0, 64, 1),                 # conv1_1 temporal: 32-channel k-blocks, 64B swizzle
+    (2, 32, 3, 16, 64, 0, 64, 3),                  # first-layer variants: vertical reuse only ...
+    (2, 32, 20, 32, 64, 0, 64, 3),
+    (2, 32, 3, 16, 64, 0, 64, 9),                  # ... and whole-filter stages (S=3)
+    (3, 32, 20, 32, 64, 1, 64, 9),
+    (2, 224, 3, 16, 64, 0, 0, 0),                  # full-size conv1_1, auto variant (S=3)
+    (2, 224, 20, 32, 64, 0, 0, 0),
+    (2, 32, 64, 64, 64, 1, 64, 1),                 # forced one-tap-per-stage on an R=3-capable shape
     (2, 32, 64, 64, 64, 1, 64, 3),                 # vertical tap reuse
     (2, 32, 128, 128, 128, 0, 128, 3),
     (2, 224, 64, 64, 64, 1, 64, 0),                # full-size conv1_2, auto variant

@@ -50,8 +50,9 @@ def check_stream(cin, n=3):
 
 
 def time_layers(batch):
-    cfg = [(224, 16, 3, 64, 0), (224, 64, 64, 64, 1), (112, 64, 64, 128, 0), (112, 128, 128, 128, 1), (56, 128, 128, 256, 0),
-           (56, 256, 256, 256, 0), (56, 256, 256, 256, 1), (28, 256, 256, 512, 0), (28, 512, 512, 512, 0),
+    """Per-layer device time of the layer kernel at one chunk size, default (auto) variant first."""
+    cfg = [(224, 16, 3, 64, 0), (224, 32, 20, 64, 0), (224, 64, 64, 64, 1), (112, 64, 64, 128, 0), (112, 128, 128, 128, 1),
+           (56, 128, 128, 256, 0), (56, 256, 256, 256, 0), (56, 256, 256, 256, 1), (28, 256, 256, 512, 0), (28, 512, 512, 512, 0),
            (28, 512, 512, 512, 1), (14, 512, 512, 512, 0), (14, 512, 512, 512, 1)]
     tot = 0.0
     for (H, cin_pad, cin, cout, pool) in cfg:
@@ -59,25 +60,39 @@ def time_layers(batch):
         w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
         b = torch.zeros(cout, device="cuda")
         variants = [(0, 0)]
-        if H >= 112 and cin_pad == 64 or (H == 112 and cin_pad == 128):
-            variants.append((0, 3))
+        if H >= 112:
+            variants += [(0, 1), (0, 3)] if cin_pad < 64 else [(0, 1)]
         if cout >= 256:
-            variants += [(128, 0), (256, 0)]
+            variants += [(128, 0)] if H > 14 else [(128, 0)]
         for (bn, r) in variants:
             for _ in range(2):
                 ops.conv2d_nhwc(x, w, b, pool=bool(pool), force_bn=bn, force_r=r)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(5):
+            for _ in range(4):
                 ops.conv2d_nhwc(x, w, b, pool=bool(pool), force_bn=bn, force_r=r)
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 5
+            ms = e0.elapsed_time(e1) / 4
             fl = 2.0 * batch * H * H * cout * 9 * cin
             print(f"  conv H={H} {cin}->{cout} pool={pool} bn={bn} r={r}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
-            if (bn, r) == (0, 0):
-                tot += ms
-    print(f"  sum of default-variant conv layers (conv3_2/4_2/5_1 counted once): {tot:.3f} ms for batch {batch}")
+            if (bn, r) == (0, 0) and cin != 20:
+                tot += ms * (2 if (H, cin, pool) in ((56, 256, 0), (28, 512, 0), (14, 512, 0)) else 1)
+    print(f"  spatial-stream conv total, default variants: {tot:.3f} ms for batch {batch} = {tot/batch*1e3:.1f} us/snippet")
+    # FC layers
+    for (fin, fout, f32) in ((25088, 4096, False), (4096, 4096, False), (4096, 256, True)):
+        x = torch.randn(batch, fin, device="cuda").bfloat16()
+        w = torch.randn(fout, fin, device="cuda") * 0.01
+        b = torch.zeros(fout, device="cuda")
+        for _ in range(2):
+            ops.linear(x, w, b, out_f32=f32)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            ops.linear(x, w, b, out_f32=f32)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"  fc {fin}->{fout}: {e0.elapsed_time(e1)/4:.3f} ms (includes the fp32->bf16 weight pack of this test entry)")
 
 
 if __name__ == "__main__":

@@ -79,10 +79,10 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int CK, int R>
+template <int BN, int CK, int R, int S>
 const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const CUtensorMap& tO,
                            const ConvKernelParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = conv_tc_kernel<BN, CK, R>;
+  auto kfn = conv_tc_kernel<BN, CK, R, S>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -92,7 +92,7 @@ const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const C
   count_launch();
   kfn<<<grid, kConvThreads, smem, st>>>(tA, tW, tO, p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return errf("conv_tc_kernel<%d,%d,%d> launch: %s", BN, CK, R, cudaGetErrorString(e));
+  if (e != cudaSuccess) return errf("conv_tc_kernel<%d,%d,%d,%d> launch: %s", BN, CK, R, S, cudaGetErrorString(e));
   return nullptr;
 }
 
@@ -120,10 +120,21 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.tiles_w = d.W / p.w_t; p.tiles_h = d.H / p.h_t; p.tiles_n = (d.n + p.n_t - 1) / p.n_t;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
 
-  int R = 1;
+  // Kernel variant.  R=3 (one haloed A box serves a filter column) needs single-image tiles whose rows are whole
+  // swizzle atoms; it pays where the N tile is narrow (Cout <= 128, i.e. the 224^2 / 112^2 layers), where the
+  // layer is L2->SM bound.  S=3 (whole filter per stage) is for the first layer (Cin_pad 16/32, one channel chunk).
+  const bool r3_ok = d.ks == 3 && p.n_t == 1 && p.w_t % 8 == 0;
+  int R = 1, S = 1;
   if (d.force_r == 3) {
-    if (!(d.ks == 3 && p.n_t == 1 && p.w_t % 8 == 0)) return "force_r=3 needs ks=3 and a single-image tile with w_t%8==0";
+    if (!r3_ok) return "force_r=3 needs ks=3 and a single-image tile with w_t%8==0";
     R = 3;
+  } else if (d.force_r == 0 && r3_ok && d.Cout <= 128) {
+    R = 3;
+  }
+  if (R == 3 && CK < 64 && d.force_r != 3) S = 3;
+  if (d.force_r == 9) {   // test hook: whole-filter stages
+    if (!r3_ok || CK == 64) return "force_r=9 (S=3) needs an R=3-capable tile and Cin_pad 16/32";
+    R = 3; S = 3;
   }
   const int sms = sm_count();
   int BN = d.force_bn;
@@ -159,14 +170,15 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   const int rowb = CK * 2;
   const int a_rows = p.n_t * (p.h_t + (R - 1)) * p.w_t;
   p.a_tx_bytes = (uint32_t)a_rows * rowb;
-  p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-  const uint32_t stage_bytes = p.a_stage_bytes + conv_b_stage_bytes(BN, CK, R);
+  p.a_box_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+  p.staging_bytes = d.pool ? 4096u : 16384u;
+  const uint32_t stage_bytes = S * p.a_box_bytes + conv_b_stage_bytes(BN, CK, R, S);
   const size_t smem_cap = 227 * 1024;
-  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, p.a_stage_bytes, 0)) / stage_bytes);
+  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, p.a_box_bytes, p.staging_bytes, 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return errf("not enough shared memory for 2 stages (stage %u B)", stage_bytes);
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(BN, CK, R, p.a_stage_bytes, stages);
+  const size_t smem = conv_smem_bytes(BN, CK, R, S, p.a_box_bytes, p.staging_bytes, stages);
 
   CUtensorMap tA, tW, tO;
   {
@@ -176,7 +188,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   }
   {
     const uint64_t dims[3] = {(uint64_t)d.cin_pad, (uint64_t)d.Cout, (uint64_t)(d.ks * d.ks)};
-    const uint32_t box[3] = {(uint32_t)CK, (uint32_t)BN, (uint32_t)R};
+    const uint32_t box[3] = {(uint32_t)CK, (uint32_t)BN, (uint32_t)(R * S)};
     if (const char* e = encode_bf16(&tW, d.w_packed, 3, dims, box, rowb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
   }
   if (!d.y_f32) {
@@ -189,12 +201,13 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
 
-#define VA_CASE(bn, ck, r) \
-  if (BN == bn && CK == ck && R == r) return launch_variant<bn, ck, r>(tA, tW, tO, p, grid, smem, st);
-  VA_CASE(64, 16, 1) VA_CASE(64, 32, 1) VA_CASE(64, 64, 1) VA_CASE(128, 64, 1) VA_CASE(256, 64, 1)
-  VA_CASE(64, 64, 3) VA_CASE(128, 64, 3)
+#define VA_CASE(bn, ck, r, sv) \
+  if (BN == bn && CK == ck && R == r && S == sv) return launch_variant<bn, ck, r, sv>(tA, tW, tO, p, grid, smem, st);
+  VA_CASE(64, 16, 1, 1) VA_CASE(64, 32, 1, 1) VA_CASE(64, 64, 1, 1) VA_CASE(128, 64, 1, 1) VA_CASE(256, 64, 1, 1)
+  VA_CASE(64, 64, 3, 1) VA_CASE(128, 64, 3, 1) VA_CASE(64, 16, 3, 1) VA_CASE(64, 32, 3, 1)
+  VA_CASE(64, 16, 3, 3) VA_CASE(64, 32, 3, 3)
 #undef VA_CASE
-  return errf("no kernel variant for BN=%d CK=%d R=%d", BN, CK, R);
+  return errf("no kernel variant for BN=%d CK=%d R=%d S=%d", BN, CK, R, S);
 }
 
 }  // namespace va

@@ -12,6 +12,9 @@
 //     out-of-bounds part (the zero halo, and partial batches) is zero-filled by the TMA unit.
 //   * R==3 ("vertical reuse"): one TMA box of h_t+2 rows serves the three taps r=0..2 of a filter
 //     column s; the three MMAs address it at row offsets r*w_t (whole 8-row swizzle atoms).
+//   * S==3 ("whole-filter stage", first layer): a stage holds the three column-shifted boxes and all 9
+//     weight taps, i.e. one pipeline stage per tile -- the K=27/180 layers are otherwise bound by the
+//     per-stage latency of the single producer / MMA threads, not by bytes.
 //   * accumulators live in TMEM (2 stages x BN fp32 columns) so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; epilogue = tcgen05.ld -> +bias -> ReLU -> bf16 -> (2x2 max-pool by warp
 //     shuffles) -> 128B-swizzled smem staging -> TMA store (clips partial tiles).
@@ -36,21 +39,21 @@ struct ConvKernelParams {
   int pool, relu, out_f32;
   int Cout;
   int num_stages;
-  uint32_t a_stage_bytes;          // smem bytes reserved per stage for A (multiple of 1024)
+  uint32_t a_box_bytes;            // smem bytes reserved per A box (multiple of 1024); a stage holds S of them
   uint32_t a_tx_bytes;             // bytes one A TMA box delivers
+  uint32_t staging_bytes;          // one output staging buffer (16 KB, or 4 KB when the 2x2 pool is fused)
   const float* bias;               // [Cout]
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
 };
 
 constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
-constexpr int kStagingBytes = 16384;   // one 128-row x 64-channel bf16 chunk
 
-__host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R) { return R * BN * CK * 2; }
+__host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R, int S) { return R * S * BN * CK * 2; }
 
-inline size_t conv_smem_bytes(int BN, int CK, int R, uint32_t a_stage_bytes, int stages) {
-  return 1024 /*align slack*/ + (size_t)stages * (a_stage_bytes + conv_b_stage_bytes(BN, CK, R)) +
-         2 * kStagingBytes + 256 * sizeof(float) + 256;
+inline size_t conv_smem_bytes(int BN, int CK, int R, int S, uint32_t a_box_bytes, uint32_t staging_bytes, int stages) {
+  return 1024 /*align slack*/ + (size_t)stages * (S * a_box_bytes + conv_b_stage_bytes(BN, CK, R, S)) +
+         2 * (size_t)staging_bytes + 256 * sizeof(float) + 256;
 }
 
 __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
@@ -60,22 +63,24 @@ __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&m);
 }
 
-template <int BN, int CK, int R>
+template <int BN, int CK, int R, int S>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
   static_assert(CK == 16 || CK == 32 || CK == 64, "CK");
   static_assert(R == 1 || R == 3, "R");
+  static_assert(S == 1 || (S == 3 && R == 3), "S");
   constexpr int ROWB = CK * 2;
-  constexpr uint32_t B_STAGE = conv_b_stage_bytes(BN, CK, R);
+  constexpr uint32_t B_STAGE = conv_b_stage_bytes(BN, CK, R, S);
   constexpr uint32_t TMEM_COLS = 2 * BN;   // 128 / 256 / 512: powers of two >= 32
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t stage_bytes = p.a_stage_bytes + B_STAGE;
+  const uint32_t a_stage_bytes = S * p.a_box_bytes;
+  const uint32_t stage_bytes = a_stage_bytes + B_STAGE;
   uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;
-  float* bias_s = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * p.staging_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
@@ -108,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int groups = (p.ks * p.ks) / R;          // R=1: one group per tap; R=3: one per filter column
+  const int groups = (p.ks * p.ks) / (R * S);    // stages per channel chunk: 9 (per tap), 3 (per filter column) or 1
   const int num_kb = groups * p.cin_chunks;      // pipeline stages consumed per tile
 
   if (warp == 0) {
@@ -122,18 +127,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int th = mt % p.tiles_h;
         const int tn = mt / p.tiles_h;
         const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
+        // taps are walked with counters (no per-stage integer division: this single thread's instruction latency
+        // is what bounds the narrow-N layers).  R=1: g = s*ks + r; R=3: g = s; S=3: g = 0 covers the filter.
+        int s = 0, r = 0;
         for (int g = 0; g < groups; ++g) {
-          const int s = (R == 1) ? (g / p.ks) : g;
-          const int r = (R == 1) ? (g % p.ks) : 0;
+          const int wx = w0 + s - p.pad, hy = h0 + r - p.pad;
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
             uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-            uint8_t* b_dst = a_dst + p.a_stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + B_STAGE);
-            tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * CK, w0 + s - p.pad, h0 + r - p.pad, n0);
-            tma_load_3d(b_dst, &tmW, &full_bar[stage], cc * CK, c0, g * R);
+            uint8_t* b_dst = a_dst + a_stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + B_STAGE);
+#pragma unroll
+            for (int sa = 0; sa < S; ++sa)
+              tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
+            tma_load_3d(b_dst, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
             if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
           }
+          if (R == 1) { if (++r == p.ks) { r = 0; ++s; } } else { ++s; }
         }
       }
     }
@@ -142,6 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
       const uint32_t a_r_stride = (uint32_t)p.w_t * ROWB;   // bytes per input row of the A box (R==3, n_t==1)
+      const uint32_t smem_base_u32 = smem_u32(smem);
       uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
@@ -151,16 +162,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
+          const uint32_t a_addr = smem_base_u32 + stage * stage_bytes;
+          const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
+          const uint64_t db0 = make_smem_desc<ROWB>(a_addr + a_stage_bytes);
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
+          for (int sa = 0; sa < S; ++sa) {
 #pragma unroll
-            for (int k = 0; k < CK / 16; ++k) {
-              const uint64_t da = make_smem_desc<ROWB>(a_addr + r * a_r_stride + k * 32);
-              const uint64_t db = make_smem_desc<ROWB>(b_addr + r * (BN * ROWB) + k * 32);
-              umma_bf16(d_tmem, da, db, idesc, acc);
-              acc = 1;
+            for (int r = 0; r < R; ++r) {
+              const uint32_t a_off = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
+#pragma unroll
+              for (int k = 0; k < CK / 16; ++k) {
+                umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc, acc);
+                acc = 1;
+              }
             }
           }
           umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
@@ -181,6 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_i = m >> (p.log2_w_t + p.log2_h_t);
     uint32_t as = 0, as_phase = 0;
     int sbuf = 0;
+    int bias_c0 = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt = tile % p.n_tiles_cout;
       int mt = tile / p.n_tiles_cout;
@@ -189,9 +205,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tn = mt / p.tiles_h;
       const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
 
-      named_bar_sync(1, 128);             // everyone is done reading the previous tile's bias
-      for (int i = et; i < BN; i += 128) bias_s[i] = __ldg(p.bias + c0 + i);
-      named_bar_sync(1, 128);
+      if (c0 != bias_c0) {                // warp-uniform: the bias slice changes only with the Cout tile
+        named_bar_sync(1, 128);           // everyone is done reading the previous slice
+        for (int i = et; i < BN; i += 128) bias_s[i] = __ldg(p.bias + c0 + i);
+        named_bar_sync(1, 128);
+        bias_c0 = c0;
+      }
 
       mbar_wait(&tfull_bar[as], as_phase, 400 + as);
       tc_fence_after();
@@ -270,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (et == 0) tma_store_wait_read<1>();
         named_bar_sync(2, 128);
         if (writer) {
-          uint8_t* rowp = staging + sbuf * kStagingBytes + row * 128;
+          uint8_t* rowp = staging + sbuf * p.staging_bytes + row * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 val = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -281,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         named_bar_sync(2, 128);
         if (et == 0) {
           const int sh = p.pool ? 1 : 0;
-          tma_store_4d(&tmO, staging + sbuf * kStagingBytes, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
+          tma_store_4d(&tmO, staging + sbuf * p.staging_bytes, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
           tma_store_commit();
         }
         sbuf ^= 1;
