@@ -176,6 +176,7 @@ va_status va_load_weights(va_handle* h, const void* const* tensors, int n_tensor
 va_status va_preprocess(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
                         const int32_t* index_table, int n, int planes, int crop, const float* mean, const float* std,
                         int c_pad, int out_mode, void* out, va_stream_t stream) {
+  if (n == 0) return VA_OK;
   if (!images || !index_table || !mean || !std || !out) return fail(VA_ERR_INVALID, "va_preprocess: NULL argument");
   if (n < 0 || planes < 1 || img_c < 1 || planes * img_c > 32) return fail(VA_ERR_INVALID, "va_preprocess: bad shape");
   if (crop > img_h || crop > img_w || crop < 1) return fail(VA_ERR_INVALID, "va_preprocess: crop %d vs image %dx%d", crop, img_h, img_w);

@@ -162,6 +162,9 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
 
   p.n_tiles_cout = d.Cout / BN;
   p.total_tiles = tiles_m * p.n_tiles_cout;
+  p.div_cout = FastDiv::make((uint32_t)p.n_tiles_cout);
+  p.div_w = FastDiv::make((uint32_t)p.tiles_w);
+  p.div_h = FastDiv::make((uint32_t)p.tiles_h);
   p.ks = d.ks; p.pad = (d.ks - 1) / 2;
   p.cin_chunks = d.cin_pad / CK;
   p.pool = d.pool; p.relu = d.relu; p.out_f32 = d.y_f32 ? 1 : 0;

@@ -19,13 +19,35 @@
 //     MMAs of tile i+1; epilogue = tcgen05.ld -> +bias -> ReLU -> bf16 -> (2x2 max-pool by warp
 //     shuffles) -> 128B-swizzled smem staging -> TMA store (clips partial tiles).
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer
-// (+TMEM alloc), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer
+// (+TMEM alloc), warps 2..5 and 6..9 = two epilogue warpgroups (TMEM lane quarter = warp_idx % 4).  Group g owns
+// TMEM accumulator stage g and drains the CTA's even / odd tiles, so two tile epilogues run concurrently: for
+// the N=64/128 layers one 128-thread epilogue (~1.5k clk per 64 columns) was slower than the tile's MMAs.
 #pragma once
 #include <cuda.h>
 #include "va_ptx.cuh"
 
 namespace va {
+
+// Division by a runtime constant as multiply-high + shift (exact for dividends < 2^31).  The tile decode runs on
+// the single producer thread, where a hardware-less 32-bit divide (~40 dependent instructions) per coordinate was
+// the per-tile bottleneck of the narrow layers.
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __host__ static FastDiv make(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;                     // ceil(log2(d))
+    const uint64_t p = 31 + l;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = (uint32_t)(p - 32);
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return d == 1 ? x : (__umulhi(x, mul) >> shr); }
+  __device__ __forceinline__ void divmod(uint32_t x, uint32_t& q, uint32_t& r) const { q = div(x); r = x - q * d; }
+};
 
 struct ConvKernelParams {
   int n_img, H, W;                 // input (== pre-pool output) spatial size
@@ -34,6 +56,7 @@ struct ConvKernelParams {
   int tiles_w, tiles_h, tiles_n;   // ceil-div tile counts
   int n_tiles_cout;                // Cout / BN
   int total_tiles;
+  FastDiv div_cout, div_w, div_h;  // by n_tiles_cout, tiles_w, tiles_h
   int ks, pad;                     // 3/1 or 1/0
   int cin_chunks;                  // Cin_pad / CK
   int pool, relu, out_f32;
@@ -46,14 +69,14 @@ struct ConvKernelParams {
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
 };
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;
 constexpr int kMaxStages = 8;
 
 __host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R, int S) { return R * S * BN * CK * 2; }
 
 inline size_t conv_smem_bytes(int BN, int CK, int R, int S, uint32_t a_box_bytes, uint32_t staging_bytes, int stages) {
   return 1024 /*align slack*/ + (size_t)stages * (S * a_box_bytes + conv_b_stage_bytes(BN, CK, R, S)) +
-         2 * (size_t)staging_bytes + 256 * sizeof(float) + 256;
+         2 * (size_t)staging_bytes + 2 * 256 * sizeof(float) + 256;
 }
 
 __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
@@ -81,7 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_stage_bytes + B_STAGE;
   uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + 2 * p.staging_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 256);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -121,11 +144,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int nt = tile % p.n_tiles_cout;
-        int mt = tile / p.n_tiles_cout;
-        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tn = mt / p.tiles_h;
+        uint32_t nt, mt, tw, th, tn;
+        p.div_cout.divmod((uint32_t)tile, mt, nt);
+        p.div_w.divmod(mt, mt, tw);
+        p.div_h.divmod(mt, tn, th);
         const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
         // taps are walked with counters (no per-stage integer division: this single thread's instruction latency
         // is what bounds the narrow-N layers).  R=1: g = s*ks + r; R=3: g = s; S=3: g = 0 covers the filter.
@@ -187,28 +209,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================== epilogue (4 warps, 128 threads)
+    // ===================================================== epilogue (2 groups x 4 warps)
+    const int eg = (warp - 2) >> 2;       // epilogue group == TMEM accumulator stage it drains
     const int q = warp & 3;               // TMEM lane quarter accessible to this warp
     const int m = q * 32 + lane;          // accumulator row == pixel index inside the tile
-    const int et = threadIdx.x - 64;      // 0..127
+    const int et = threadIdx.x - 64 - eg * 128;   // 0..127 within the group
+    float* bias_g = bias_s + eg * 256;
+    uint8_t* stage_out = staging + eg * p.staging_bytes;
     const int w_i = m & (p.w_t - 1);
     const int h_i = (m >> p.log2_w_t) & (p.h_t - 1);
     const int n_i = m >> (p.log2_w_t + p.log2_h_t);
-    uint32_t as = 0, as_phase = 0;
-    int sbuf = 0;
+    const uint32_t as = (uint32_t)eg;
     int bias_c0 = -1;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt = tile % p.n_tiles_cout;
-      int mt = tile / p.n_tiles_cout;
-      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int tn = mt / p.tiles_h;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != eg) continue;       // the other group's tile
+      const uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
+      uint32_t nt, mt, tw, th, tn;
+      p.div_cout.divmod((uint32_t)tile, mt, nt);
+      p.div_w.divmod(mt, mt, tw);
+      p.div_h.divmod(mt, tn, th);
       const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
 
       if (c0 != bias_c0) {                // warp-uniform: the bias slice changes only with the Cout tile
-        named_bar_sync(1, 128);           // everyone is done reading the previous slice
-        for (int i = et; i < BN; i += 128) bias_s[i] = __ldg(p.bias + c0 + i);
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + eg, 128);      // everyone in the group is done reading the previous slice
+        for (int i = et; i < BN; i += 128) bias_g[i] = __ldg(p.bias + c0 + i);
+        named_bar_sync(1 + eg, 128);
         bias_c0 = c0;
       }
 
@@ -227,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        const float* bs = bias_s + chunk * 64;
+        const float* bs = bias_g + chunk * 64;
         if (p.out_f32) {
           // fully-connected tail (H=W=1, tile = 128 images): fp32 rows straight to global.
           const int img = n0 + m;
@@ -285,11 +311,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           writer = ((w_i | h_i) & 1) == 0;
           row = ((n_i * (p.h_t >> 1)) + (h_i >> 1)) * (p.w_t >> 1) + (w_i >> 1);
         }
-        // staging buffer `sbuf` was last read by the TMA store issued two chunks ago
-        if (et == 0) tma_store_wait_read<1>();
-        named_bar_sync(2, 128);
+        // the group's staging buffer was last read by the TMA store of its previous chunk
+        if (et == 0) tma_store_wait_read<0>();
+        named_bar_sync(3 + eg, 128);
         if (writer) {
-          uint8_t* rowp = staging + sbuf * p.staging_bytes + row * 128;
+          uint8_t* rowp = stage_out + row * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 val = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -297,16 +323,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(3 + eg, 128);
         if (et == 0) {
           const int sh = p.pool ? 1 : 0;
-          tma_store_4d(&tmO, staging + sbuf * p.staging_bytes, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
+          tma_store_4d(&tmO, stage_out, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
           tma_store_commit();
         }
-        sbuf ^= 1;
       }
-      as ^= 1;
-      if (as == 0) as_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all();
   }

@@ -35,6 +35,9 @@ struct PreprocessParams {
   const int32_t* table;   // [n][planes][4]
   int n, planes, crop;
   float mean[32], stdv[32];
+  int n_luts;             // distinct (mean, std) pairs, <= 3; 0 = compute per pixel (generic path)
+  float lut_mean[3], lut_std[3];
+  unsigned char lut_of[32];   // channel -> LUT index
   void* out;
 };
 
@@ -45,6 +48,14 @@ struct PreprocessParams {
 // generic (runtime-shaped, slower) instance.
 template <int C_PAD, int MODE, int PLANES, int IMG_C>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams p) {
+  // u8 input has 256 possible values per (mean, std): tabulate ((u/255) - mean)/std once per block with the same
+  // IEEE ops the per-pixel path uses (bit-identical), instead of two fp32 divisions per channel per pixel.
+  __shared__ float lut[3][256];
+  for (int k = 0; k < p.n_luts; ++k)
+    for (int u = threadIdx.x; u < 256; u += blockDim.x)
+      lut[k][u] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), p.lut_mean[k]), p.lut_std[k]);
+  if (p.n_luts > 0) __syncthreads();
+  const bool use_lut = p.n_luts > 0;
   const int pix_per = p.crop * p.crop;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)p.n * pix_per) return;
@@ -67,8 +78,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams 
           p.images + (size_t)e.x * p.image_bytes + ((size_t)(e.y + y) * p.img_w + (e.z + xs)) * IMG_C;
 #pragma unroll
       for (int k = 0; k < IMG_C; ++k) {
-        const float u = (float)__ldg(src + k);
-        vals[pl * IMG_C + k] = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), p.mean[pl * IMG_C + k]), p.stdv[pl * IMG_C + k]);
+        const unsigned char ub = __ldg(src + k);
+        vals[pl * IMG_C + k] = use_lut ? lut[p.lut_of[pl * IMG_C + k]][ub]
+                                       : __fdiv_rn(__fsub_rn(__fdiv_rn((float)ub, 255.0f), p.mean[pl * IMG_C + k]), p.stdv[pl * IMG_C + k]);
       }
     }
   } else {
@@ -116,7 +128,17 @@ cudaError_t launch_preprocess(const uint8_t* images, size_t image_bytes, int img
   p.table = table; p.n = n; p.planes = planes; p.crop = crop; p.out = out;
   const int nch = planes * img_c;
   if (nch > 32 || (out_mode == 0 && nch > c_pad)) return cudaErrorInvalidValue;
-  for (int i = 0; i < 32; ++i) { p.mean[i] = i < nch ? mean[i] : 0.f; p.stdv[i] = i < nch ? stdv[i] : 1.f; }
+  for (int i = 0; i < 32; ++i) { p.mean[i] = i < nch ? mean[i] : 0.f; p.stdv[i] = i < nch ? stdv[i] : 1.f; p.lut_of[i] = 0; }
+  p.n_luts = 0;
+  for (int i = 0; i < nch; ++i) {
+    int k = 0;
+    while (k < p.n_luts && !(p.lut_mean[k] == mean[i] && p.lut_std[k] == stdv[i])) ++k;
+    if (k == p.n_luts) {
+      if (p.n_luts == 3) { p.n_luts = 0; break; }          // more than 3 distinct pairs: per-pixel arithmetic
+      p.lut_mean[k] = mean[i]; p.lut_std[k] = stdv[i]; ++p.n_luts;
+    }
+    p.lut_of[i] = (unsigned char)k;
+  }
   const long long total = (long long)n * crop * crop;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (blocks == 0) return cudaSuccess;
@@ -224,8 +246,18 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ des
   for (int d = threadIdx.x; d < D; d += blockDim.x) sd[d] = desc[(size_t)n * D + d];
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = b4[c];
-    for (int d = 0; d < D; ++d) acc = fmaf(sd[d], w4t[(size_t)d * C + c], acc);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int d = 0;
+    for (; d + 8 <= D; d += 8) {   // 8 independent loads in flight, 4 accumulation chains
+      const float w0 = __ldg(w4t + (size_t)(d + 0) * C + c), w1 = __ldg(w4t + (size_t)(d + 1) * C + c),
+                  w2 = __ldg(w4t + (size_t)(d + 2) * C + c), w3 = __ldg(w4t + (size_t)(d + 3) * C + c),
+                  w4 = __ldg(w4t + (size_t)(d + 4) * C + c), w5 = __ldg(w4t + (size_t)(d + 5) * C + c),
+                  w6 = __ldg(w4t + (size_t)(d + 6) * C + c), w7 = __ldg(w4t + (size_t)(d + 7) * C + c);
+      a0 = fmaf(sd[d + 0], w0, a0); a1 = fmaf(sd[d + 1], w1, a1); a2 = fmaf(sd[d + 2], w2, a2); a3 = fmaf(sd[d + 3], w3, a3);
+      a0 = fmaf(sd[d + 4], w4, a0); a1 = fmaf(sd[d + 5], w5, a1); a2 = fmaf(sd[d + 6], w6, a2); a3 = fmaf(sd[d + 7], w7, a3);
+    }
+    for (; d < D; ++d) a0 = fmaf(sd[d], __ldg(w4t + (size_t)d * C + c), a0);
+    const float acc = ((a0 + a1) + (a2 + a3)) + b4[c];
     sl[c] = acc;
     if (logits) logits[(size_t)n * C + c] = acc;
   }
