@@ -34,6 +34,7 @@ SIGNATURES = {
     "va_consensus_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "va_pack_input_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "va_synth_fill": (_i, [_vp, _sz, _i, _i, _i, _i, _u32, _u32, _vp]),
+    "va_debug_conv_counters": (_i, [_vp]),
     "va_profile_enable": (_i, [_i]),
     "va_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "va_launch_count": (C.c_uint64, []),

@@ -311,6 +311,11 @@ va_status va_pack_input_nchw(const float* x_nchw, int n, int channels, int heigh
   return VA_OK;
 }
 
+va_status va_debug_conv_counters(long long* dev_counters16) {
+  va::conv_set_debug_counters(dev_counters16);
+  return VA_OK;
+}
+
 va_status va_profile_enable(int on) {
   g_prof_on = on != 0;
   return VA_OK;

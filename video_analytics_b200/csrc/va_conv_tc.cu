@@ -98,6 +98,9 @@ const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const C
 
 }  // namespace
 
+static long long* g_dbg_counters = nullptr;
+void conv_set_debug_counters(long long* dev_buf) { g_dbg_counters = dev_buf; }
+
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   if (d.n <= 0) return nullptr;
   if (d.ks != 1 && d.ks != 3) return "ks must be 1 or 3";
@@ -169,7 +172,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.cin_chunks = d.cin_pad / CK;
   p.pool = d.pool; p.relu = d.relu; p.out_f32 = d.y_f32 ? 1 : 0;
   p.Cout = d.Cout;
-  p.bias = d.bias; p.out_f32_ptr = d.y_f32;
+  p.bias = d.bias; p.out_f32_ptr = d.y_f32; p.dbg = g_dbg_counters;
   const int rowb = CK * 2;
   const int a_rows = p.n_t * (p.h_t + (R - 1)) * p.w_t;
   p.a_tx_bytes = (uint32_t)a_rows * rowb;

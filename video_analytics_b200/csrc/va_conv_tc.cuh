@@ -67,7 +67,16 @@ struct ConvKernelParams {
   uint32_t staging_bytes;          // one output staging buffer (16 KB, or 4 KB when the 2x2 pool is fused)
   const float* bias;               // [Cout]
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
+  long long* dbg;                  // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
 };
+
+// wait on an mbarrier, charging the stalled cycles to *acc when diagnostics are on
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int tag, bool on, long long& acc) {
+  if (!on) { mbar_wait(bar, parity, tag); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, tag);
+  acc += clock64() - t0;
+}
 
 constexpr int kConvThreads = 320;
 constexpr int kMaxStages = 8;
@@ -141,21 +150,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        uint32_t nt, mt, tw, th, tn;
-        p.div_cout.divmod((uint32_t)tile, mt, nt);
-        p.div_w.divmod(mt, mt, tw);
-        p.div_h.divmod(mt, tn, th);
-        const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
-        // taps are walked with counters (no per-stage integer division: this single thread's instruction latency
-        // is what bounds the narrow-N layers).  R=1: g = s*ks + r; R=3: g = s; S=3: g = 0 covers the filter.
-        int s = 0, r = 0;
-        for (int g = 0; g < groups; ++g) {
-          const int wx = w0 + s - p.pad, hy = h0 + r - p.pad;
-          for (int cc = 0; cc < p.cin_chunks; ++cc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+    // The whole warp walks the loop convergently and ONE elected lane issues: inside a divergent `if (lane == 0)`
+    // every uniform-register operand of UTMALDG / UTCHMMA is fetched through a per-instruction "waterfall" loop
+    // (ELECT + R2UR.BROADCAST + BRA.U.ANY, ~100 clk per MMA measured), which bounded the narrow-N layers.
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+    long long t_wait = 0, t_begin = clock64();
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      uint32_t nt, mt, tw, th, tn;
+      p.div_cout.divmod((uint32_t)tile, mt, nt);
+      p.div_w.divmod(mt, mt, tw);
+      p.div_h.divmod(mt, tn, th);
+      const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
+      // taps are walked with counters.  R=1: g = s*ks + r; R=3: g = s; S=3: g = 0 covers the whole filter.
+      int s = 0, r = 0;
+      for (int g = 0; g < groups; ++g) {
+        const int wx = w0 + s - p.pad, hy = h0 + r - p.pad;
+        for (int cc = 0; cc < p.cin_chunks; ++cc) {
+          mbar_wait_t(&empty_bar[stage], phase ^ 1, 100 + stage, dbg, t_wait);
+          if (elect_one()) {
             uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
             uint8_t* b_dst = a_dst + a_stage_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + B_STAGE);
@@ -163,31 +176,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int sa = 0; sa < S; ++sa)
               tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
             tma_load_3d(b_dst, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
-            if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
           }
-          if (R == 1) { if (++r == p.ks) { r = 0; ++s; } } else { ++s; }
+          __syncwarp();
+          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
         }
+        if (R == 1) { if (++r == p.ks) { r = 0; ++s; } } else { ++s; }
       }
     }
+    if (dbg && lane == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = t_wait; }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-      const uint32_t a_r_stride = (uint32_t)p.w_t * ROWB;   // bytes per input row of the A box (R==3, n_t==1)
-      const uint32_t smem_base_u32 = smem_u32(smem);
-      uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
+    // ===================================================== MMA issuer (convergent warp, one elected lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    const uint32_t a_r_stride = (uint32_t)p.w_t * ROWB;   // bytes per input row of the A box (R==3, n_t==1)
+    const uint32_t smem_base_u32 = smem_u32(smem);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
+    uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+    long long t_full = 0, t_tempty = 0, t_begin = clock64(), n_tiles = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      ++n_tiles;
+      mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + as * BN;
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        uint32_t acc = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 300 + stage);
-          tc_fence_after();
-          // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
-          const uint32_t a_addr = smem_base_u32 + stage * stage_bytes;
-          const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
-          const uint64_t db0 = make_smem_desc<ROWB>(a_addr + a_stage_bytes);
+        // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
+        const uint32_t a_addr = smem_base_u32 + stage * stage_bytes;
+        const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
+        const uint64_t db0 = make_smem_desc<ROWB>(a_addr + a_stage_bytes);
+        if (elect_one()) {
 #pragma unroll
           for (int sa = 0; sa < S; ++sa) {
 #pragma unroll
@@ -195,19 +214,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t a_off = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
 #pragma unroll
               for (int k = 0; k < CK / 16; ++k) {
-                umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc, acc);
-                acc = 1;
+                umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
+                          (sa | r | k) ? 1u : acc);
               }
             }
           }
           umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
-          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[as]);         // accumulator complete -> epilogue
-        as ^= 1;
-        if (as == 0) as_phase ^= 1;
+        __syncwarp();
+        acc = 1;
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
       }
+      as ^= 1;
+      if (as == 0) as_phase ^= 1;
     }
+    if (dbg && lane == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = t_full; p.dbg[4] = t_tempty; p.dbg[11] = n_tiles; }
   } else {
     // ===================================================== epilogue (2 groups x 4 warps)
     const int eg = (warp - 2) >> 2;       // epilogue group == TMEM accumulator stage it drains
@@ -220,6 +242,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int h_i = (m >> p.log2_w_t) & (p.h_t - 1);
     const int n_i = m >> (p.log2_w_t + p.log2_h_t);
     const uint32_t as = (uint32_t)eg;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && et == 0;
+    long long t_tfull = 0, t_stage = 0, t_begin = clock64();
     int bias_c0 = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -238,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bias_c0 = c0;
       }
 
-      mbar_wait(&tfull_bar[as], as_phase, 400 + as);
+      mbar_wait_t(&tfull_bar[as], as_phase, 400 + as, dbg, t_tfull);
       tc_fence_after();
 
 #pragma unroll 1
@@ -312,8 +336,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           row = ((n_i * (p.h_t >> 1)) + (h_i >> 1)) * (p.w_t >> 1) + (w_i >> 1);
         }
         // the group's staging buffer was last read by the TMA store of its previous chunk
-        if (et == 0) tma_store_wait_read<0>();
+        const long long ts0 = dbg ? clock64() : 0;
+        if (et < 32) {                       // the group's first warp; its elected lane owns the bulk-store groups
+          if (elect_one()) tma_store_wait_read<0>();
+          __syncwarp();
+        }
         named_bar_sync(3 + eg, 128);
+        if (dbg) t_stage += clock64() - ts0;
         if (writer) {
           uint8_t* rowp = stage_out + row * 128;
 #pragma unroll
@@ -324,14 +353,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         named_bar_sync(3 + eg, 128);
-        if (et == 0) {
-          const int sh = p.pool ? 1 : 0;
-          tma_store_4d(&tmO, stage_out, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
-          tma_store_commit();
+        if (et < 32) {
+          if (elect_one()) {
+            const int sh = p.pool ? 1 : 0;
+            tma_store_4d(&tmO, stage_out, c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
+            tma_store_commit();
+          }
+          __syncwarp();
         }
       }
     }
-    if (et == 0) tma_store_wait_all();
+    if (et < 32) {
+      if (elect_one()) tma_store_wait_all();
+      __syncwarp();
+    }
+    if (dbg) { p.dbg[5 + 3 * eg] = clock64() - t_begin; p.dbg[6 + 3 * eg] = t_tfull; p.dbg[7 + 3 * eg] = t_stage; }
   }
 
   tc_fence_before();

@@ -46,5 +46,6 @@ struct ConvLayerDesc {
 // Plans (tile shape, kernel variant, tensor maps) and launches one layer.  Returns nullptr on success or a
 // static/thread-local error string.
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st);
+void conv_set_debug_counters(long long* dev_buf);   // diagnostics: per-role stall cycles of CTA 0 (nullptr = off)
 
 }  // namespace va
