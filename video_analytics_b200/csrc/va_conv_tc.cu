@@ -178,11 +178,6 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.a_tx_bytes = (uint32_t)a_rows * rowb;
   p.a_box_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
   p.staging_bytes = d.pool ? 4096u : 16384u;
-  {
-    const int mmas_per_tile = (d.ks * d.ks) * (d.cin_pad / 16);
-    p.nacc = (BN == 256 || mmas_per_tile < 2) ? 1 : 2;
-    if (const char* e = getenv("VA_CONV_NACC")) p.nacc = (atoi(e) == 1 || BN == 256) ? 1 : p.nacc;   // experiment switch
-  }
   const uint32_t stage_bytes = S * p.a_box_bytes + conv_b_stage_bytes(BN, CK, R, S);
   const size_t smem_cap = 227 * 1024;
   int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, p.a_box_bytes, p.staging_bytes, 0)) / stage_bytes);

@@ -65,7 +65,6 @@ struct ConvKernelParams {
   uint32_t a_box_bytes;            // smem bytes reserved per A box (multiple of 1024); a stage holds S of them
   uint32_t a_tx_bytes;             // bytes one A TMA box delivers
   uint32_t staging_bytes;          // one output staging buffer (16 KB, or 4 KB when the 2x2 pool is fused)
-  int nacc;                        // accumulators the K loop is dealt over (1 or 2); the epilogue sums them
   const float* bias;               // [Cout]
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
   long long* dbg;                  // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
@@ -106,12 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(S == 1 || (S == 3 && R == 3), "S");
   constexpr int ROWB = CK * 2;
   constexpr uint32_t B_STAGE = conv_b_stage_bytes(BN, CK, R, S);
-  // Back-to-back MMAs into ONE accumulator serialise on the accumulate latency (~85 clk measured), far above the
-  // 32/64-clk execution time of an N=64/128 MMA.  For BN <= 128 the K loop is therefore dealt round-robin over two
-  // TMEM accumulators (independent dependency chains) which the epilogue adds.
-  constexpr uint32_t NACC = (BN == 256) ? 1 : 2;
-  constexpr uint32_t ACC_COLS = NACC * BN;          // TMEM columns per accumulator stage
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;      // 256 / 512 / 512: powers of two >= 32
+  constexpr uint32_t TMEM_COLS = 2 * BN;   // 128 / 256 / 512: powers of two >= 32
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -203,8 +197,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ++n_tiles;
       mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_u + as * ACC_COLS;
-      uint32_t j0 = 0;                                  // MMAs issued so far for this tile
+      const uint32_t d_tmem = tmem_u + as * BN;
+      uint32_t acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
         tc_fence_after();
@@ -220,10 +214,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t a_off = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
 #pragma unroll
               for (int k = 0; k < CK / 16; ++k) {
-                const uint32_t j = j0 + (uint32_t)((sa * R + r) * (CK / 16) + k);
-                const uint32_t which = (p.nacc == 2) ? (j & 1u) : 0u;
-                umma_bf16(d_tmem + which * BN, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k,
-                          idesc, j >= (uint32_t)p.nacc ? 1u : 0u);
+                umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
+                          (sa | r | k) ? 1u : acc);
               }
             }
           }
@@ -231,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
         __syncwarp();
-        j0 += S * R * (CK / 16);
+        acc = 1;
         if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
       }
       as ^= 1;
@@ -276,21 +268,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 64; ++chunk) {
         uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS + chunk * 64;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + chunk * 64;
         tmem_ld32(taddr, v0);
         tmem_ld32(taddr + 32, v1);
         tmem_ld_wait();
-        if (NACC == 2 && p.nacc == 2) {      // add the second K-split accumulator
-          uint32_t u0[32], u1[32];
-          tmem_ld32(taddr + BN, u0);
-          tmem_ld32(taddr + BN + 32, u1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(u0[i]));
-            v1[i] = __float_as_uint(__uint_as_float(v1[i]) + __uint_as_float(u1[i]));
-          }
-        }
         if (chunk == BN / 64 - 1) {        // accumulator stage fully drained into registers
           tc_fence_before();
           __syncwarp();
