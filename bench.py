@@ -187,6 +187,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback for the product path)")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version banner there)
     rank, world, local = init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -79,10 +79,10 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int CK, int R, int S>
+template <int BN, int CK, int R, int S, bool WRES>
 const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const CUtensorMap& tO,
                            const ConvKernelParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = conv_tc_kernel<BN, CK, R, S>;
+  auto kfn = conv_tc_kernel<BN, CK, R, S, WRES>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -92,7 +92,7 @@ const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const C
   count_launch();
   kfn<<<grid, kConvThreads, smem, st>>>(tA, tW, tO, p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return errf("conv_tc_kernel<%d,%d,%d,%d> launch: %s", BN, CK, R, S, cudaGetErrorString(e));
+  if (e != cudaSuccess) return errf("conv_tc_kernel<%d,%d,%d,%d,%d> launch: %s", BN, CK, R, S, (int)WRES, cudaGetErrorString(e));
   return nullptr;
 }
 
@@ -178,13 +178,17 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.a_tx_bytes = (uint32_t)a_rows * rowb;
   p.a_box_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
   p.staging_bytes = d.pool ? 4096u : 16384u;
-  const uint32_t stage_bytes = S * p.a_box_bytes + conv_b_stage_bytes(BN, CK, R, S);
+  // Resident weights: the layer's whole weight set stays in smem (one Cout tile, one channel chunk, R=3 variants)
+  const int groups = (d.ks * d.ks) / (R * S);
+  const bool wres = R == 3 && p.n_tiles_cout == 1 && p.cin_chunks == 1 && BN == 64 && getenv("VA_CONV_NO_WRES") == nullptr &&
+                    (size_t)groups * conv_b_stage_bytes(BN, CK, R, S) <= 80 * 1024;
+  const uint32_t stage_bytes = S * p.a_box_bytes + (wres ? 0u : conv_b_stage_bytes(BN, CK, R, S));
   const size_t smem_cap = 227 * 1024;
-  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, p.a_box_bytes, p.staging_bytes, 0)) / stage_bytes);
+  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return errf("not enough shared memory for 2 stages (stage %u B)", stage_bytes);
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(BN, CK, R, S, p.a_box_bytes, p.staging_bytes, stages);
+  const size_t smem = conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, stages);
 
   CUtensorMap tA, tW, tO;
   {
@@ -207,13 +211,16 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
 
-#define VA_CASE(bn, ck, r, sv) \
-  if (BN == bn && CK == ck && R == r && S == sv) return launch_variant<bn, ck, r, sv>(tA, tW, tO, p, grid, smem, st);
-  VA_CASE(64, 16, 1, 1) VA_CASE(64, 32, 1, 1) VA_CASE(64, 64, 1, 1) VA_CASE(128, 64, 1, 1) VA_CASE(256, 64, 1, 1)
-  VA_CASE(64, 64, 3, 1) VA_CASE(128, 64, 3, 1) VA_CASE(64, 16, 3, 1) VA_CASE(64, 32, 3, 1)
-  VA_CASE(64, 16, 3, 3) VA_CASE(64, 32, 3, 3)
+#define VA_CASE(bn, ck, r, sv, wr) \
+  if (BN == bn && CK == ck && R == r && S == sv && wres == wr) \
+    return launch_variant<bn, ck, r, sv, wr>(tA, tW, tO, p, grid, smem, st);
+  VA_CASE(64, 16, 1, 1, false) VA_CASE(64, 32, 1, 1, false) VA_CASE(64, 64, 1, 1, false) VA_CASE(128, 64, 1, 1, false)
+  VA_CASE(256, 64, 1, 1, false) VA_CASE(64, 64, 3, 1, false) VA_CASE(128, 64, 3, 1, false) VA_CASE(64, 16, 3, 1, false)
+  VA_CASE(64, 32, 3, 1, false) VA_CASE(64, 16, 3, 3, false) VA_CASE(64, 32, 3, 3, false)
+  VA_CASE(64, 64, 3, 1, true) VA_CASE(64, 16, 3, 1, true) VA_CASE(64, 32, 3, 1, true) VA_CASE(64, 16, 3, 3, true)
+  VA_CASE(64, 32, 3, 3, true)
 #undef VA_CASE
-  return errf("no kernel variant for BN=%d CK=%d R=%d S=%d", BN, CK, R, S);
+  return errf("no kernel variant for BN=%d CK=%d R=%d S=%d wres=%d", BN, CK, R, S, (int)wres);
 }
 
 }  // namespace va

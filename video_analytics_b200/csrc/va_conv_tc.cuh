@@ -15,6 +15,10 @@
 //   * S==3 ("whole-filter stage", first layer): a stage holds the three column-shifted boxes and all 9
 //     weight taps, i.e. one pipeline stage per tile -- the K=27/180 layers are otherwise bound by the
 //     per-stage latency of the single producer / MMA threads, not by bytes.
+//   * WRES ("resident weights", Cout == BN and one channel chunk: conv1_1, conv1_2): all 9 taps' weights are
+//     TMA-loaded into smem once per CTA instead of once per tile.  These layers are shared-memory-bandwidth
+//     bound (MMA operand reads + TMA writes + epilogue staging share ~128-156 B/clk), so every byte not
+//     re-written per tile is time.
 //   * accumulators live in TMEM (2 stages x BN fp32 columns) so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; epilogue = tcgen05.ld -> +bias -> ReLU -> bf16 -> (2x2 max-pool by warp
 //     shuffles) -> 128B-swizzled smem staging -> TMA store (clips partial tiles).
@@ -83,8 +87,10 @@ constexpr int kMaxStages = 8;
 
 __host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R, int S) { return R * S * BN * CK * 2; }
 
-inline size_t conv_smem_bytes(int BN, int CK, int R, int S, uint32_t a_box_bytes, uint32_t staging_bytes, int stages) {
-  return 1024 /*align slack*/ + (size_t)stages * (S * a_box_bytes + conv_b_stage_bytes(BN, CK, R, S)) +
+inline size_t conv_smem_bytes(int BN, int CK, int R, int S, bool wres, int groups, uint32_t a_box_bytes,
+                              uint32_t staging_bytes, int stages) {
+  const size_t b = conv_b_stage_bytes(BN, CK, R, S);
+  return 1024 /*align slack*/ + (wres ? (size_t)groups * b : 0) + (size_t)stages * (S * a_box_bytes + (wres ? 0 : b)) +
          2 * (size_t)staging_bytes + 2 * 256 * sizeof(float) + 256;
 }
 
@@ -95,7 +101,7 @@ __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&m);
 }
 
-template <int BN, int CK, int R, int S>
+template <int BN, int CK, int R, int S, bool WRES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
@@ -109,15 +115,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int groups = (p.ks * p.ks) / (R * S);    // stages per channel chunk: 9 (per tap), 3 (per filter column) or 1
+  const int num_kb = groups * p.cin_chunks;      // pipeline stages consumed per tile
+  const uint32_t wres_bytes = WRES ? (uint32_t)groups * B_STAGE : 0u;   // resident weights sit in front of the ring
   const uint32_t a_stage_bytes = S * p.a_box_bytes;
-  const uint32_t stage_bytes = a_stage_bytes + B_STAGE;
-  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;
+  const uint32_t stage_bytes = a_stage_bytes + (WRES ? 0u : B_STAGE);
+  uint8_t* ring = smem + wres_bytes;
+  uint8_t* staging = ring + (size_t)p.num_stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + 2 * p.staging_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* wres_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,6 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
     }
+    mbar_init(wres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -145,9 +157,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int groups = (p.ks * p.ks) / (R * S);    // stages per channel chunk: 9 (per tap), 3 (per filter column) or 1
-  const int num_kb = groups * p.cin_chunks;      // pipeline stages consumed per tile
-
   if (warp == 0) {
     // ===================================================== TMA producer
     // The whole warp walks the loop convergently and ONE elected lane issues: inside a divergent `if (lane == 0)`
@@ -156,6 +165,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
     long long t_wait = 0, t_begin = clock64();
     uint32_t stage = 0, phase = 0;
+    if (WRES) {   // the layer's whole weight set (Cout == BN, one channel chunk), once per CTA
+      if (elect_one()) {
+        mbar_arrive_expect_tx(wres_bar, wres_bytes);
+        for (int g = 0; g < groups; ++g) tma_load_3d(smem + (size_t)g * B_STAGE, &tmW, wres_bar, 0, 0, g * (R * S));
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       uint32_t nt, mt, tw, th, tn;
       p.div_cout.divmod((uint32_t)tile, mt, nt);
@@ -169,13 +185,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
           mbar_wait_t(&empty_bar[stage], phase ^ 1, 100 + stage, dbg, t_wait);
           if (elect_one()) {
-            uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-            uint8_t* b_dst = a_dst + a_stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + B_STAGE);
+            uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + (WRES ? 0u : B_STAGE));
 #pragma unroll
             for (int sa = 0; sa < S; ++sa)
               tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
-            tma_load_3d(b_dst, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
+            if (!WRES) tma_load_3d(a_dst + a_stage_bytes, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
           }
           __syncwarp();
           if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
@@ -189,7 +204,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc_bf16(128, BN);
     const uint32_t a_r_stride = (uint32_t)p.w_t * ROWB;   // bytes per input row of the A box (R==3, n_t==1)
     const uint32_t smem_base_u32 = smem_u32(smem);
+    const uint32_t ring_u32 = smem_base_u32 + wres_bytes;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
+    if (WRES) mbar_wait(wres_bar, 0, 500);
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
     long long t_full = 0, t_tempty = 0, t_begin = clock64(), n_tiles = 0;
@@ -203,9 +220,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
         tc_fence_after();
         // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
-        const uint32_t a_addr = smem_base_u32 + stage * stage_bytes;
+        const uint32_t a_addr = ring_u32 + stage * stage_bytes;
         const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
-        const uint64_t db0 = make_smem_desc<ROWB>(a_addr + a_stage_bytes);
+        const uint64_t db0 = make_smem_desc<ROWB>(WRES ? smem_base_u32 + (uint32_t)kb * B_STAGE : a_addr + a_stage_bytes);
         if (elect_one()) {
 #pragma unroll
           for (int sa = 0; sa < S; ++sa) {
