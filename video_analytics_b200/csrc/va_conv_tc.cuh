@@ -29,7 +29,6 @@
 // the N=64/128 layers one 128-thread epilogue (~1.5k clk per 64 columns) was slower than the tile's MMAs.
 #pragma once
 #include <cuda.h>
-#include <type_traits>
 #include "va_ptx.cuh"
 
 namespace va {
@@ -73,7 +72,6 @@ struct ConvKernelParams {
   const float* bias;               // [Cout]
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
   long long* dbg;                  // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
-  int dbg_flags;                   // timing experiments only (results become wrong): 1 = no A loads, 2 = no epilogue work
 };
 
 // wait on an mbarrier, charging the stalled cycles to *acc when diagnostics are on
@@ -188,11 +186,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait_t(&empty_bar[stage], phase ^ 1, 100 + stage, dbg, t_wait);
           if (elect_one()) {
             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
-            const bool no_a = (p.dbg_flags & 1) != 0;
-            mbar_arrive_expect_tx(&full_bar[stage], (no_a ? 0u : S * p.a_tx_bytes) + (WRES ? 0u : B_STAGE));
+            mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + (WRES ? 0u : B_STAGE));
 #pragma unroll
             for (int sa = 0; sa < S; ++sa)
-              if (!no_a) tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
+              tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
             if (!WRES) tma_load_3d(a_dst + a_stage_bytes, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
           }
           __syncwarp();
@@ -204,77 +201,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (dbg && lane == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = t_wait; }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (convergent warp, one elected lane issues)
-    // The tensor pipe accepts only a couple of MMAs ahead, so whatever the issuing thread does between the last MMA
-    // of one pipeline stage and the first of the next (barrier try_wait ~90 clk, fences, descriptor setup) is an
-    // exposed bubble -- ~350 clk per stage measured, as much as the MMAs of an N=64 stage.  The loop is therefore
-    // software-pipelined: the NEXT stage's "full" barrier (and the next tile's accumulator) are probed while the
-    // last two MMAs of the current stage are still to be issued, and only a failed probe falls back to a wait.
     constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-    constexpr int KS = CK / 16;
-    constexpr int T = S * R * KS;                       // MMAs per pipeline stage
-    constexpr int PROBE_AT = T > 2 ? T - 2 : 0;
     const uint32_t a_r_stride = (uint32_t)p.w_t * ROWB;   // bytes per input row of the A box (R==3, n_t==1)
     const uint32_t smem_base_u32 = smem_u32(smem);
     const uint32_t ring_u32 = smem_base_u32 + wres_bytes;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
+    if (WRES) mbar_wait(wres_bar, 0, 500);
+    uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
     long long t_full = 0, t_tempty = 0, t_begin = clock64(), n_tiles = 0;
-    uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
-    if (WRES) mbar_wait(wres_bar, 0, 500);
-    if ((int)blockIdx.x < p.total_tiles) {
-      mbar_wait_t(&tempty_bar[0], 1, 200, dbg, t_tempty);
-      mbar_wait_t(&full_bar[0], 0, 300, dbg, t_full);
-    }
-    tc_fence_after();
-
-    // issue MMAs [LO, HI) of the current stage; idx -> (column box sa, tap row r, k step)
-    auto issue = [&](auto lo_c, auto hi_c, uint32_t d_tmem, uint64_t da0, uint64_t db0, bool first_kb) {
-      constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
-#pragma unroll
-      for (int idx = LO; idx < HI; ++idx) {
-        const int k = idx % KS, r = (idx / KS) % R, sa = idx / (KS * R);
-        const uint32_t a_off = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
-        umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
-                  (idx == 0 && first_kb) ? 0u : 1u);
-      }
-    };
-    using std::integral_constant;
-
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       ++n_tiles;
-      const bool last_tile = tile + (int)gridDim.x >= p.total_tiles;
+      mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
+      tc_fence_after();
       const uint32_t d_tmem = tmem_u + as * BN;
-      const uint32_t nas = as ^ 1u, nas_phase = (nas == 0u) ? (as_phase ^ 1u) : as_phase;
+      uint32_t acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const bool last_kb = kb == num_kb - 1;
+        mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
+        tc_fence_after();
         // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
         const uint32_t a_addr = ring_u32 + stage * stage_bytes;
         const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
         const uint64_t db0 = make_smem_desc<ROWB>(WRES ? smem_base_u32 + (uint32_t)kb * B_STAGE : a_addr + a_stage_bytes);
-        uint32_t nstage = stage + 1, nphase = phase;
-        if (nstage == (uint32_t)p.num_stages) { nstage = 0; nphase ^= 1; }
-        const bool has_next = !(last_kb && last_tile);
-
-        if (PROBE_AT > 0) {
-          if (elect_one()) issue(integral_constant<int, 0>{}, integral_constant<int, PROBE_AT>{}, d_tmem, da0, db0, kb == 0);
-          __syncwarp();
-        }
-        bool next_full = has_next ? mbar_try_wait(&full_bar[nstage], nphase) : true;
-        bool next_acc = (last_kb && !last_tile) ? mbar_try_wait(&tempty_bar[nas], nas_phase ^ 1u) : true;
-        next_full = __all_sync(0xffffffffu, next_full);
-        next_acc = __all_sync(0xffffffffu, next_acc);
         if (elect_one()) {
-          issue(integral_constant<int, PROBE_AT>{}, integral_constant<int, T>{}, d_tmem, da0, db0, kb == 0);
-          umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
-          if (last_kb) umma_commit(&tfull_bar[as]);           // accumulator complete -> epilogue
+#pragma unroll
+          for (int sa = 0; sa < S; ++sa) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const uint32_t a_off = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
+#pragma unroll
+              for (int k = 0; k < CK / 16; ++k) {
+                umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
+                          (sa | r | k) ? 1u : acc);
+              }
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (!next_full) mbar_wait_t(&full_bar[nstage], nphase, 300 + nstage, dbg, t_full);
-        if (!next_acc) mbar_wait_t(&tempty_bar[nas], nas_phase ^ 1u, 200 + nas, dbg, t_tempty);
-        tc_fence_after();
-        stage = nstage; phase = nphase;
+        acc = 1;
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
       }
-      as = nas; as_phase = nas_phase;
+      as ^= 1;
+      if (as == 0) as_phase ^= 1;
     }
     if (dbg && lane == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = t_full; p.dbg[4] = t_tempty; p.dbg[11] = n_tiles; }
   } else {
@@ -311,12 +281,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait_t(&tfull_bar[as], as_phase, 400 + as, dbg, t_tfull);
       tc_fence_after();
-      if (p.dbg_flags & 2) {               // experiment: hand the accumulator straight back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        continue;
-      }
 
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 64; ++chunk) {
