@@ -58,6 +58,71 @@ void run(long long* d_out, int nacc, int spread, int kstep, int grid) {
          kstep, grid, (double)h / (iters * 16), BN / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+
+// ---- per-stage overhead: T MMAs, then the bookkeeping a pipelined kernel does between stages -------------------
+// flags: 1 = tcgen05.commit to a barrier, 2 = mbarrier.try_wait on an already-completed phase, 4 = tcgen05.fence,
+//        16 = commit issued AFTER the first MMA of the next group (elect + __syncwarp always)
+template <int BN, int T, int flags>
+__global__ void __launch_bounds__(128, 1) stage_overhead_kernel(long long* out, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_done, bar_commit[8], bar_ready;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done, 1); mbar_init(&bar_ready, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_commit[i], 1);
+    fence_mbar_init();
+    mbar_arrive(&bar_ready);            // phase 0 of bar_ready is complete: try_wait(parity 0) succeeds immediately
+  }
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, slot, 0);
+  if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    const uint32_t base = smem_u32(smem);
+    const uint64_t da0 = make_smem_desc<128>(base);
+    const uint64_t db0 = make_smem_desc<128>(base + 64 * 1024);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (flags & 2) { while (!mbar_try_wait(&bar_ready, 0)) {} }
+      if (flags & 4) tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          const uint32_t off = (((j & 3) * 16384) >> 4) + 2 * (j & 3);
+          umma_bf16(tmem, da0 + off, db0 + off, idesc, 1u);
+          if ((flags & 16) && j == 0 && it > 0) umma_commit(&bar_commit[(it - 1) & 7]);
+        }
+        if ((flags & 1) && !(flags & 16)) umma_commit(&bar_commit[it & 7]);
+      }
+      __syncwarp();
+    }
+    if (threadIdx.x == 32) umma_commit(&bar_done);
+    __syncwarp();
+    mbar_wait(&bar_done, 0, 1);
+    long long t1 = clock64();
+    if (threadIdx.x == 32 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int BN, int T, int flags>
+void run_stage(long long* d_out) {
+  const int iters = 400;
+  cudaFuncSetAttribute(stage_overhead_kernel<BN, T, flags>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  stage_overhead_kernel<BN, T, flags><<<148, 128, 200 * 1024>>>(d_out, iters);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+  const double per_stage = (double)h / iters;
+  const double ideal = T * (BN == 64 ? 48.0 : BN / 2.0);
+  printf("stage N=%3d T=%2d flags=%2d : %7.1f clk/stage (MMA-only %6.1f, overhead %6.1f)  %s\n", BN, T, flags, per_stage, ideal,
+         per_stage - ideal, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 64);
@@ -75,5 +140,7 @@ int main() {
     run<32, 128>(d_out, 1, 1, 1, grid);
     run<16, 128>(d_out, 1, 1, 1, grid);
   }
+#define RUN4(F) run_stage<256, 4, F>(d_out); run_stage<64, 4, F>(d_out); run_stage<64, 12, F>(d_out); run_stage<128, 12, F>(d_out);
+  RUN4(0) RUN4(1) RUN4(2) RUN4(4) RUN4(3) RUN4(7) RUN4(17) RUN4(19) RUN4(23)
   return 0;
 }
