@@ -133,7 +133,7 @@ va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int i
 va_status va_profile_enable(int on);
 va_status va_profile_read(double* tensor_ms, uint64_t* tensor_launches, double* tensor_flops);
 
-/* Diagnostics: when set to a device buffer of 80 int64, CTA 0 of every subsequent layer-kernel launch writes its
+/* Diagnostics: when set to a device buffer of 16 int64, CTA 0 of every subsequent layer-kernel launch writes its
  * per-role cycle counters: [0] producer total, [1] producer stalled on free slots, [2] MMA total, [3] MMA stalled on
  * operands, [4] MMA stalled on a free accumulator, [5..7]/[8..10]... epilogue group 0/1 total, stalled on the
  * accumulator, stalled on the staging buffer; [11] = tiles processed by CTA 0.  NULL switches it off. */

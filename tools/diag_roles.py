@@ -10,7 +10,7 @@ from video_analytics_b200 import _lib, ops
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 125
 lib = _lib.load()
-cnt = torch.zeros(80, dtype=torch.int64, device="cuda")
+cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
 cfg = [("conv1_1 spatial", 224, 16, 3, 64, 0, 0, 0), ("conv1_1 temporal", 224, 32, 20, 64, 0, 0, 0),
        ("conv1_1 spatial r=1", 224, 16, 3, 64, 0, 0, 1),
        ("conv1_2", 224, 64, 64, 64, 1, 0, 0), ("conv1_2 r=1", 224, 64, 64, 64, 1, 0, 1),
@@ -31,9 +31,6 @@ for (name, H, cin_pad, cin, cout, pool, bn, r) in cfg:
     lib.va_debug_conv_counters(None)
     c = cnt.cpu().tolist()
     tiles = max(1, c[11])
-    if os.environ.get("VA_TIMELINE"):
-        print("   timeline: " + "  ".join(
-            f"[kb{c[19+4*i]} wait {c[17+4*i]-c[16+4*i]} issue {c[18+4*i]-c[17+4*i]} gap {(c[16+4*(i+1)]-c[18+4*i]) if i < 11 else 0}]" for i in range(12)))
     print(f"{name:22s} {e0.elapsed_time(e1):7.3f} ms tiles/CTA {tiles:5d} clk/tile {c[2]/tiles:8.0f} | producer wait-empty {100*c[1]/max(1,c[0]):5.1f}% | "
           f"MMA wait-full {100*c[3]/max(1,c[2]):5.1f}% wait-tempty {100*c[4]/max(1,c[2]):5.1f}% | "
           f"epi0 wait-tfull {100*c[6]/max(1,c[5]):5.1f}% wait-staging {100*c[7]/max(1,c[5]):5.1f}% | "

@@ -173,8 +173,6 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.pool = d.pool; p.relu = d.relu; p.out_f32 = d.y_f32 ? 1 : 0;
   p.Cout = d.Cout;
   p.bias = d.bias; p.out_f32_ptr = d.y_f32; p.dbg = g_dbg_counters;
-  p.dbg_flags = 0;
-  if (const char* e = getenv("VA_CONV_DBG_FLAGS")) p.dbg_flags = atoi(e);
   const int rowb = CK * 2;
   const int a_rows = p.n_t * (p.h_t + (R - 1)) * p.w_t;
   p.a_tx_bytes = (uint32_t)a_rows * rowb;

@@ -74,8 +74,7 @@ struct ConvKernelParams {
   uint32_t staging_bytes;          // one output staging buffer (16 KB, or 4 KB when the 2x2 pool is fused)
   const float* bias;               // [Cout]
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
-  long long* dbg;                  // optional [80] per-role cycle counters written by CTA 0 (diagnostics only)
-  int dbg_flags;                   // timing experiments only (results become wrong): 1 = no A loads, 2 = no epilogue work
+  long long* dbg;                  // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
 };
 
 // wait on an mbarrier, charging the stalled cycles to *acc when diagnostics are on
@@ -191,11 +190,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait_t(&empty_bar[stage], phase ^ 1, 100 + stage, dbg, t_wait);
           if (elect_one()) {
             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
-            const bool no_a = (p.dbg_flags & 1) != 0;
-            mbar_arrive_expect_tx(&full_bar[stage], (no_a ? 0u : S * p.a_tx_bytes) + (WRES ? 0u : B_STAGE));
+            mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + (WRES ? 0u : B_STAGE));
 #pragma unroll
             for (int sa = 0; sa < S; ++sa)
-              if (!no_a) tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
+              tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
             if (!WRES) tma_load_3d(a_dst + a_stage_bytes, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
           }
           __syncwarp();
@@ -223,66 +221,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
     long long t_full = 0, t_tempty = 0, t_begin = clock64(), n_tiles = 0;
-    int n_rec = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       ++n_tiles;
       mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + as * BN;
       uint32_t acc = 0;
-      // Two pipeline stages per iteration: the ~100-clk latency of a (successful) mbarrier try_wait and the
-      // commit/loop bookkeeping are paid once per pair instead of once per stage -- the tensor pipe only buffers an
-      // MMA or two, so everything this warp does between MMAs is an exposed bubble (profiles/r01_*timeline*).
-      for (int kb = 0; kb < num_kb; kb += 2) {
-        const int nst = (num_kb - kb) >= 2 ? 2 : 1;
-        uint32_t stage_b = stage + 1, phase_b = phase;
-        if (stage_b == (uint32_t)p.num_stages) { stage_b = 0; phase_b ^= 1; }
-        const bool rec = dbg && n_rec < 12 && n_tiles >= 3;          // timeline of a few steady-state iterations
-        const long long r0 = rec ? clock64() : 0;
-        if (nst == 2) {
-          if (dbg) { const long long t0 = clock64(); mbar_wait2(&full_bar[stage], phase, &full_bar[stage_b], phase_b, 300); t_full += clock64() - t0; }
-          else mbar_wait2(&full_bar[stage], phase, &full_bar[stage_b], phase_b, 300);
-        } else {
-          mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
-        }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
         tc_fence_after();
-        const long long r1 = rec ? clock64() : 0;
+        // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
+        const uint32_t a_addr = ring_u32 + stage * stage_bytes;
+        const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
+        const uint64_t db0 = make_smem_desc<ROWB>(WRES ? smem_base_u32 + (uint32_t)kb * B_STAGE : a_addr + a_stage_bytes);
         if (elect_one()) {
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (u < nst) {
-              const uint32_t st_u = u ? stage_b : stage;
-              // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
-              const uint32_t a_addr = ring_u32 + st_u * stage_bytes;
-              const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
-              const uint64_t db0 = make_smem_desc<ROWB>(WRES ? smem_base_u32 + (uint32_t)(kb + u) * B_STAGE : a_addr + a_stage_bytes);
+          for (int sa = 0; sa < S; ++sa) {
 #pragma unroll
-              for (int sa = 0; sa < S; ++sa) {
+            for (int r = 0; r < R; ++r) {
+              const uint32_t a_off = a_win[sa * R + r];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                  const uint32_t a_off = a_win[sa * R + r];
-#pragma unroll
-                  for (int k = 0; k < CK / 16; ++k) {
-                    umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
-                              (sa | r | k) ? 1u : acc);
-                  }
-                }
+              for (int k = 0; k < CK / 16; ++k) {
+                umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
+                          (sa | r | k) ? 1u : acc);
               }
-              umma_commit(&empty_bar[st_u]);   // smem slot reusable once these MMAs retire
-              acc = 1;
             }
           }
-          if (kb + nst == num_kb) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
+          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
         __syncwarp();
         acc = 1;
-        if (rec) {
-          const long long r2 = clock64();
-          if (lane == 0) { p.dbg[16 + 4 * n_rec] = r0; p.dbg[17 + 4 * n_rec] = r1; p.dbg[18 + 4 * n_rec] = r2; p.dbg[19 + 4 * n_rec] = kb; }
-          ++n_rec;
-        }
-        for (int u = 0; u < nst; ++u)
-          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
       }
       as ^= 1;
       if (as == 0) as_phase ^= 1;
@@ -322,12 +292,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait_t(&tfull_bar[as], as_phase, 400 + as, dbg, t_tfull);
       tc_fence_after();
-      if (p.dbg_flags & 2) {               // experiment: hand the accumulator straight back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        continue;
-      }
 
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 64; ++chunk) {

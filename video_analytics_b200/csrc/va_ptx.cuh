@@ -69,23 +69,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
-// Wait on two mbarrier phases with both try_waits in flight together (their ~100-clk latencies overlap); falls back
-// to the blocking wait (with watchdog) for whichever is not yet complete.
-__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t par_a, uint64_t* bar_b, uint32_t par_b, int tag) {
-  uint32_t oka, okb;
-  asm volatile(
-      "{\n\t.reg .pred PA, PB;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 PA, [%2], %3;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 PB, [%4], %5;\n\t"
-      "selp.u32 %0, 1, 0, PA;\n\t"
-      "selp.u32 %1, 1, 0, PB;\n\t}"
-      : "=r"(oka), "=r"(okb)
-      : "r"(smem_u32(bar_a)), "r"(par_a), "r"(smem_u32(bar_b)), "r"(par_b)
-      : "memory");
-  if (!oka) mbar_wait(bar_a, par_a, tag);
-  if (!okb) mbar_wait(bar_b, par_b, tag + 1);
-}
-
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
