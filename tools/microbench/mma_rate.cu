@@ -123,9 +123,123 @@ void run_stage(long long* d_out) {
          per_stage - ideal, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+// ---- do warps that spin on mbarrier.try_wait slow the tensor pipe?  SPIN: 0 none, 1 = 8 warps x 32 lanes poll one
+// never-completing barrier, 2 = same but only lane 0 of each warp polls, 3 = poll with __nanosleep(64) back-off
+template <int BN, int SPIN>
+__global__ void __launch_bounds__(320, 1) spin_kernel(long long* out, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_done, bar_never;
+  __shared__ uint32_t slot;
+  __shared__ volatile int stop;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar_done, 1); mbar_init(&bar_never, 1); fence_mbar_init(); stop = 0; }
+  if (warp == 9) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, slot, 0);
+  if (warp == 9) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    const uint32_t base = smem_u32(smem);
+    const uint64_t da0 = make_smem_desc<128>(base);
+    const uint64_t db0 = make_smem_desc<128>(base + 64 * 1024);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          const uint32_t off = (((j & 3) * 16384) >> 4) + 2 * (j & 3);
+          umma_bf16(tmem, da0 + off, db0 + off, idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar_done);
+    __syncwarp();
+    mbar_wait(&bar_done, 0, 1);
+    long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    stop = 1;
+  } else if (warp < 8 && SPIN > 0) {
+    while (!stop) {
+      if (SPIN == 1) (void)mbar_try_wait(&bar_never, 0);
+      if (SPIN == 2) { if (lane == 0) (void)mbar_try_wait(&bar_never, 0); __syncwarp(); }
+      if (SPIN == 3) { (void)mbar_try_wait(&bar_never, 0); __nanosleep(64); }
+    }
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+template <int BN, int SPIN>
+void run_spin(long long* d_out) {
+  const int iters = 300;
+  cudaFuncSetAttribute(spin_kernel<BN, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  spin_kernel<BN, SPIN><<<148, 320, 200 * 1024>>>(d_out, iters);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("spin N=%3d mode=%d : %7.1f clk/MMA  %s\n", BN, SPIN, (double)h / (iters * 12), e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+// ---- the conv kernel's exact operand addressing for an R=3 stage of conv1_2 (BN=64, CK=64): 12 MMAs reading the
+// haloed 160-row A box at row offsets r*16 and k steps of 32 B, weights at r*8 KB.  MODE bits: 1 = D at TMEM column 64,
+// 2 = alternate between two stage buffers, 4 = A windows do NOT overlap (r*16 KB instead of r*2 KB)
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) pattern_kernel(long long* out, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar_done, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, slot, 0);
+  if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+    const uint32_t base = smem_u32(smem);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t st = (MODE & 2) ? (uint32_t)(it & 1) : 0u;
+      const uint64_t da0 = make_smem_desc<128>(base + 72 * 1024 + st * 20480);
+      const uint64_t db0 = make_smem_desc<128>(base + (it % 3) * 24576);
+      const uint32_t d = tmem + ((MODE & 1) ? 64u : 0u);
+      if (elect_one()) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, da0 + ((r * ((MODE & 4) ? 16384 : 2048)) >> 4) + 2 * k, db0 + ((r * 8192) >> 4) + 2 * k, idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar_done);
+    __syncwarp();
+    mbar_wait(&bar_done, 0, 1);
+    long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+template <int MODE>
+void run_pattern(long long* d_out) {
+  const int iters = 300;
+  cudaFuncSetAttribute(pattern_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  pattern_kernel<MODE><<<148, 128, 220 * 1024>>>(d_out, iters);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("pattern mode=%d : %7.1f clk/MMA  %s\n", MODE, (double)h / (iters * 12), e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 64);
+  run_pattern<0>(d_out); run_pattern<1>(d_out); run_pattern<2>(d_out); run_pattern<3>(d_out); run_pattern<4>(d_out); run_pattern<7>(d_out);
+  run_spin<64, 0>(d_out); run_spin<64, 1>(d_out); run_spin<64, 2>(d_out); run_spin<64, 3>(d_out);
+  run_spin<256, 0>(d_out); run_spin<256, 1>(d_out); run_spin<128, 0>(d_out); run_spin<128, 1>(d_out);
   for (int grid : {1, 148}) {
     run<64, 128>(d_out, 1, 0, 0, grid);
     run<64, 128>(d_out, 2, 0, 0, grid);
