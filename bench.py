@@ -317,6 +317,39 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = snippets / float(e2e_s.item())
 
+    # ---- HBM-bound kernels of the path, timed alone (CUDA events, inputs >> L2): algorithmic bytes of SURVEY.md 8d
+    aux = []
+    if rank == 0:
+        def timed(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        nvid = 4
+        tabs = [ev.tables_for(v) for v in range(nvid)]
+        ts_, tt_ = torch.cat([t[0] for t in tabs]), torch.cat([t[1] for t in tabs])
+        nsn = ts_.shape[0]
+        ms_s = timed(lambda: ops.preprocess(store.rgb, layout.rgb_shape, ts_, ev.mean_s, ev.std_s, c_pad=spatial.c_pad))
+        ms_t = timed(lambda: ops.preprocess(store.flow, layout.flow_shape, tt_, ev.mean_t, ev.std_t, c_pad=temporal.c_pad))
+        gv = 512
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        fd = [torch.rand((gv * SNIPPETS_PER_VIDEO, D), device=dev, generator=gen) for _ in range(2)]
+        fs = [torch.rand((gv * SNIPPETS_PER_VIDEO, C), device=dev, generator=gen) for _ in range(2)]
+        offs = torch.arange(0, (gv + 1) * SNIPPETS_PER_VIDEO, SNIPPETS_PER_VIDEO, dtype=torch.int32, device=dev)
+        fout = ev.alloc_outputs(gv, D, C, with_svm=True)
+        ms_f = timed(lambda: combined.fuse(fd[0], fd[1], fs[0], fs[1], offs, out=fout))
+        hbm = read_peaks()["hbm"]
+        for name, nbytes, ms_k in (("preprocess_kernel (RGB, 3->16ch bf16 NHWC)", 451_584 * nsn, ms_s),
+                                   ("preprocess_kernel (flow stack, 20->32ch bf16 NHWC)", 3_010_560 * nsn, ms_t),
+                                   ("fuse_kernel (consensus + late fusion + SVM scoring)", (714_000 + (2 * D + C) * 4 + 8 + C * 8) * gv, ms_f)):
+            gbs = nbytes / (ms_k * 1e-3) / 1e9
+            aux.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                        "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": nbytes})
+        del fd, fs, fout
+
     if rank == 0:
         peaks = read_peaks()
         achieved = (t_f.value / 1e12) / (t_ms.value * 1e-3) if t_ms.value > 0 else 0.0
@@ -337,6 +370,7 @@ def main():
                          "peak_source": peaks["src"], "launches": int(t_l.value), "avg_launch_ms": t_ms.value / max(1, t_l.value),
                          "flops_per_launch": t_f.value / max(1, t_l.value),
                          "share_of_step": t_ms.value / total_ms if total_ms > 0 else None},
+            "aux_rooflines": aux,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
