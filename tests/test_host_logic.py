@@ -191,3 +191,25 @@ def test_layout_is_deterministic_and_valid():
         assert m.flowy_first == m.flowx_first + m.n_flows
     line = a.list_line(3, "train")
     assert U.videoInfo(line, "train")[1] == a.videos[3].name
+
+
+def test_fastdiv_magic_numbers():
+    """The magic-number division used for tile decode (csrc/va_conv_tc.cuh::FastDiv), restated: exact for every
+    dividend < 2^31 and every divisor the planner can produce."""
+    def make(d):
+        if d == 1:
+            return 0, 0
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        p = 31 + l
+        return (((1 << p) + d - 1) // d) & 0xFFFFFFFF, p - 32
+
+    import random
+    rng = random.Random(0)
+    for d in list(range(1, 300)) + [392, 784, 3063, 12544, 49000, 98000]:
+        mul, shr = make(d)
+        assert ((1 << (31 + (shr if d > 1 else 0) + (1 if d > 1 else 0))) + d - 1) // d <= 0xFFFFFFFF or d == 1
+        for x in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1] + [rng.randrange(0, 1 << 31) for _ in range(200)]:
+            q = x if d == 1 else ((x * mul) >> 32) >> shr
+            assert q == x // d, (d, x)
