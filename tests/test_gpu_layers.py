@@ -55,6 +55,12 @@ CONV_CASES = [
     (2, 32, 64, 64, 64, 1, 64, 1),                 # forced one-tap-per-stage on an R=3-capable shape
     (2, 32, 64, 64, 64, 1, 64, 3),                 # vertical tap reuse
     (2, 32, 128, 128, 128, 0, 128, 3),
+    (2, 32, 128, 128, 256, 0, 256, 0),             # CTA-pair kernel (cta_group::2): auto variant for Cout >= 256
+    (1, 56, 128, 128, 256, 1, 0, 0),               # ... odd number of M tiles (49): the pair's tail tile is out of bounds
+    (3, 56, 256, 256, 256, 0, 0, 0),
+    (5, 28, 256, 256, 512, 1, 0, 0),               # ... two N tiles
+    (33, 14, 512, 512, 512, 1, 0, 0),
+    (70, 14, 512, 512, 512, 0, 0, 0),              # ... more work units than clusters
     (2, 224, 64, 64, 64, 1, 64, 0),                # full-size conv1_2, auto variant
 ]
 

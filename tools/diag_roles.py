@@ -15,7 +15,9 @@ cfg = [("conv1_1 spatial", 224, 16, 3, 64, 0, 0, 0), ("conv1_1 temporal", 224, 3
        ("conv1_1 spatial r=1", 224, 16, 3, 64, 0, 0, 1),
        ("conv1_2", 224, 64, 64, 64, 1, 0, 0), ("conv1_2 r=1", 224, 64, 64, 64, 1, 0, 1),
        ("conv2_1", 112, 64, 64, 128, 0, 0, 0), ("conv2_2", 112, 128, 128, 128, 1, 0, 0),
-       ("conv3_2", 56, 256, 256, 256, 0, 0, 0), ("conv4_2", 28, 512, 512, 512, 0, 0, 0), ("conv5_1", 14, 512, 512, 512, 0, 0, 0)]
+       ("conv3_2", 56, 256, 256, 256, 0, 0, 0), ("conv4_2", 28, 512, 512, 512, 0, 0, 0), ("conv5_1", 14, 512, 512, 512, 0, 0, 0),
+       ("conv3_2 1-CTA", 56, 256, 256, 256, 0, 0, 1), ("conv4_2 1-CTA", 28, 512, 512, 512, 0, 0, 1),
+       ("conv5_1 1-CTA", 14, 512, 512, 512, 0, 0, 1), ("conv3_1", 56, 128, 128, 256, 0, 0, 0), ("conv3_1 1-CTA", 56, 128, 128, 256, 0, 0, 1)]
 for (name, H, cin_pad, cin, cout, pool, bn, r) in cfg:
     x = torch.randn(batch, H, H, cin_pad, device="cuda").bfloat16()
     w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05

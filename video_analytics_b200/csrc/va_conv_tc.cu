@@ -1,6 +1,7 @@
 // Host-side planner/launcher for the tcgen05 implicit-GEMM layer kernel (va_conv_tc.cuh).
 #include "va_internal.h"
 #include "va_conv_tc.cuh"
+#include "va_conv_tc2.cuh"
 
 #include <mutex>
 #include <stdarg.h>
@@ -163,6 +164,9 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   if (CK != 64 && BN != 64) return "CK<64 variants are built for BN=64 only";
   if (R == 3 && BN == 256) return "R=3 not built for BN=256";
 
+  // CTA-pair kernel (cta_group::2, UMMA M=256) for the wide 3x3 layers: 6 x 32 KB stages instead of 4 x 48 KB.
+  const bool pair = BN == 256 && CK == 64 && R == 1 && S == 1 && d.ks == 3 && !d.y_f32 && d.force_r != 1 &&
+                    getenv("VA_CONV_NO_PAIR") == nullptr;
   p.n_tiles_cout = d.Cout / BN;
   p.total_tiles = tiles_m * p.n_tiles_cout;
   p.div_cout = FastDiv::make((uint32_t)p.n_tiles_cout);
@@ -210,6 +214,32 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     tO = tA;   // unused by the fp32 epilogue; must still be a valid descriptor
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (pair) {
+    const int pairs_m = (tiles_m + 1) / 2;
+    ConvKernelParams p2 = p;
+    p2.total_tiles = pairs_m * p.n_tiles_cout;                    // work units of a CTA pair
+    const size_t smem_cap2 = 227 * 1024;
+    int st2 = (int)((smem_cap2 - conv2_smem_bytes(p.staging_bytes, 0)) / 32768);
+    if (st2 > kMaxStages) st2 = kMaxStages;
+    p2.num_stages = st2;
+    const size_t smem2 = conv2_smem_bytes(p.staging_bytes, st2);
+    // weights box: this CTA's half of the N tile
+    const uint64_t wdims[3] = {(uint64_t)d.cin_pad, (uint64_t)d.Cout, (uint64_t)(d.ks * d.ks)};
+    const uint32_t wbox[3] = {64u, 128u, 1u};
+    if (const char* e = encode_bf16(&tW, d.w_packed, 3, wdims, wbox, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
+    static size_t configured2 = 0;
+    if (configured2 < smem2) {
+      cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e != cudaSuccess) return errf("cudaFuncSetAttribute(pair, smem=%zu): %s", smem2, cudaGetErrorString(e));
+      configured2 = smem2;
+    }
+    int clusters = p2.total_tiles < sms / 2 ? p2.total_tiles : sms / 2;
+    count_launch();
+    conv_tc2_kernel<<<2 * clusters, kConv2Threads, smem2, st>>>(tA, tW, tO, p2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return errf("conv_tc2_kernel launch: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
 
 #define VA_CASE(bn, ck, r, sv, wr) \
   if (BN == bn && CK == ck && R == r && S == sv && wres == wr) \
