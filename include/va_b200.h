@@ -41,6 +41,11 @@ va_status va_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   in_channels: 3 (spatial) or 2*L = 20 (temporal).  max_batch: snippets per internal chunk (workspace size).
  * --------------------------------------------------------------------------------------------------------- */
 va_status va_create(va_handle** out, int stream_kind, int in_channels, int n_classes, int desc_dim, int max_batch);
+/* Same with an arithmetic mode: precision 0 = bf16 storage / fp32 accumulate (the throughput path); 1 = fp32-accuracy
+ * parity mode: every activation and weight is carried as three bf16 slices (hi, mid, lo) and each layer's GEMM sums
+ * the six leading cross terms (K is 6x longer), reproducing an fp32 forward to ~1e-6 relative (north_star: 1e-5). */
+va_status va_create_ex(va_handle** out, int stream_kind, int in_channels, int n_classes, int desc_dim, int max_batch,
+                       int precision);
 va_status va_destroy(va_handle* h);
 
 /* channels the NHWC bf16 network input must be padded to for this handle (16 for 3, 32 for 20) */
@@ -120,6 +125,11 @@ va_status va_consensus_update(float* sum, int32_t* count, const int32_t* video_i
  * [n][height][width][c_pad] for va_forward. */
 va_status va_pack_input_nchw(const float* x_nchw, int n, int channels, int height, int width, int c_pad,
                              void* out_nhwc, va_stream_t stream);
+
+/* Same for a precision-1 handle: bf16 NHWC [n][height][width][k6_pad] with the six slice blocks (hi,hi,hi,mid,mid,lo)
+ * of each channel; k6_pad = va_input_channels_padded(h) (32 for 3 channels, 128 for 20). */
+va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, int height, int width, int k6_pad,
+                                    void* out_nhwc, va_stream_t stream);
 
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */

@@ -195,3 +195,46 @@ def test_full_video_protocol_vs_oracle(nets, world):
     margin = ofused.sort(descending=True).values
     if float(margin[0] - margin[1]) > 2 * float((got["video_scores"][0].cpu() - ofused).abs().max()):
         assert int(got["score_pred"][0]) == int(ofused.argmax())
+
+
+FP32_RTOL = 1e-5       # north_star: fused class scores within 1e-5 relative in the fp32 mode
+
+
+@pytest.mark.parametrize("kind", ["spatial", "temporal"])
+def test_fp32_mode_vs_oracle(kind, world):
+    """precision="fp32" (bf16x3 slices, six cross terms, fp32 accumulate) reproduces the oracle's fp32 forward."""
+    from oracle import two_stream as ts
+    from video_analytics_b200 import ops
+    lay, store, ost = world
+    m = lay.videos[1]
+    if kind == "spatial":
+        model = ts.build_spatial_model(seed=3)
+        snips, _ = ts.video_snippets_spatial(ost, m.name)
+        net = ops.StreamNet(ops.STREAM_SPATIAL, 3, max_batch=2, precision="fp32")
+    else:
+        model = ts.build_temporal_model(seed=3)
+        snips, _ = ts.video_snippets_temporal(ost, m.name)
+        net = ops.StreamNet(ops.STREAM_TEMPORAL, 20, max_batch=2, precision="fp32")
+    net.load_state_dict(model.state_dict())
+    sel = [1, 64, 200]
+    x = net.pack_input(snips[sel])
+    assert x.shape[-1] == (32 if kind == "spatial" else 128)
+    # the six blocks reconstruct the fp32 input exactly: hi + mid + lo
+    c = snips.shape[1]
+    blocks = x[..., :6 * c].float().reshape(3, 224, 224, 6, c).cpu()
+    recon = blocks[..., 0, :] + blocks[..., 3, :] + blocks[..., 5, :]
+    assert torch.equal(blocks[..., 0, :], blocks[..., 1, :]) and torch.equal(blocks[..., 3, :], blocks[..., 4, :])
+    assert float((recon - snips[sel].permute(0, 2, 3, 1)).abs().max()) <= 2.0 ** -22 * float(snips[sel].abs().max())
+    desc, logits, probs, pred = net.forward(x)              # n=3 with max_batch=2 -> two chunks
+    fv, ol, opred = ts.forward_eval(model, snips[sel])
+    op = torch.softmax(ol, 1)
+    perr = float(((probs.cpu() - op).abs() / op).max())
+    derr = float((desc.cpu() - fv).abs().max() / fv.abs().max())
+    lerr = float((logits.cpu() - ol).abs().max() / ol.abs().max())
+    assert perr < FP32_RTOL, perr
+    assert derr < 1e-4 and lerr < 1e-4, (derr, lerr)
+    # top-1: exact agreement wherever the oracle's own margin exceeds our (tiny) logit error
+    srt = ol.sort(dim=1, descending=True).values
+    decidable = (srt[:, 0] - srt[:, 1]) > 2 * float((logits.cpu() - ol).abs().max())
+    assert bool((pred.cpu().long() == opred)[decidable].all())
+    net.close()

@@ -23,6 +23,7 @@ SIGNATURES = {
     "va_abi_version": (_i, []),
     "va_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "va_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "va_create_ex": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
     "va_destroy": (_i, [_vp]),
     "va_input_channels_padded": (_i, [_vp]),
     "va_load_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp]),
@@ -33,6 +34,7 @@ SIGNATURES = {
     "va_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "va_consensus_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "va_pack_input_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "va_pack_input_nchw_split6": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "va_synth_fill": (_i, [_vp, _sz, _i, _i, _i, _i, _u32, _u32, _vp]),
     "va_debug_conv_counters": (_i, [_vp]),
     "va_profile_enable": (_i, [_i]),

@@ -56,6 +56,7 @@ constexpr int kFcHidden = 4096;
 
 struct va_handle {
   int stream_kind, cin, cin_pad, n_classes, desc_dim, max_batch;
+  int precision;    // 0 = bf16 storage; 1 = fp32-accuracy (bf16x3 slices, six cross terms along K)
   bool loaded;
   void* wconv[13];
   float* bconv[13];
@@ -95,7 +96,13 @@ static va_status require_sm100() {
 }
 
 va_status va_create(va_handle** out, int stream_kind, int in_channels, int n_classes, int desc_dim, int max_batch) {
+  return va_create_ex(out, stream_kind, in_channels, n_classes, desc_dim, max_batch, 0);
+}
+
+va_status va_create_ex(va_handle** out, int stream_kind, int in_channels, int n_classes, int desc_dim, int max_batch,
+                       int precision) {
   if (!out) return fail(VA_ERR_INVALID, "va_create: out is NULL");
+  if (precision != 0 && precision != 1) return fail(VA_ERR_INVALID, "precision %d (0 = bf16, 1 = fp32x3)", precision);
   *out = nullptr;
   if (va_status s = require_sm100()) return s;
   if (in_channels < 1 || in_channels > 32) return fail(VA_ERR_INVALID, "in_channels %d not in [1,32]", in_channels);
@@ -106,26 +113,33 @@ va_status va_create(va_handle** out, int stream_kind, int in_channels, int n_cla
   if (!h) return fail(VA_ERR_INVALID, "out of host memory");
   memset(h, 0, sizeof(*h));
   h->stream_kind = stream_kind; h->cin = in_channels; h->cin_pad = in_channels <= 16 ? 16 : 32;
+  h->precision = precision;
+  const int kmul = precision ? 6 : 1;    // K multiplier of every layer but the first
+  if (precision) {
+    if (6 * in_channels <= 32) h->cin_pad = 32;
+    else if (6 * in_channels <= 128) h->cin_pad = 128;
+    else { delete h; return fail(VA_ERR_INVALID, "fp32x3 mode supports up to 21 input channels"); }
+  }
   h->n_classes = n_classes; h->desc_dim = desc_dim; h->max_batch = max_batch;
   int cin = h->cin_pad;
   for (int i = 0; i < 13; ++i) {
-    const size_t wbytes = (size_t)9 * kVgg16[i].cout * cin * 2;
+    const size_t wbytes = (size_t)9 * kVgg16[i].cout * cin * 2;   // cin already carries the K multiplier
     if (cudaMalloc(&h->wconv[i], wbytes) != cudaSuccess || cudaMalloc(&h->bconv[i], kVgg16[i].cout * 4) != cudaSuccess) {
       va_destroy(h);
       return fail(VA_ERR_CUDA, "cudaMalloc conv weights failed");
     }
-    cin = kVgg16[i].cout;
+    cin = kVgg16[i].cout * kmul;
   }
   const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
   const int fout[3] = {kFcHidden, kFcHidden, desc_dim};
   for (int i = 0; i < 3; ++i) {
-    if (cudaMalloc(&h->wfc[i], (size_t)fin[i] * fout[i] * 2) != cudaSuccess ||
+    if (cudaMalloc(&h->wfc[i], (size_t)fin[i] * kmul * fout[i] * 2) != cudaSuccess ||
         cudaMalloc(&h->bfc[i], fout[i] * 4) != cudaSuccess) {
       va_destroy(h);
       return fail(VA_ERR_CUDA, "cudaMalloc fc weights failed");
     }
   }
-  h->act_bytes = (size_t)max_batch * kCrop * kCrop * 64 * 2;
+  h->act_bytes = (size_t)max_batch * kCrop * kCrop * 64 * 2 * kmul;
   if (cudaMalloc(&h->w4t, (size_t)desc_dim * n_classes * 4) != cudaSuccess ||
       cudaMalloc(&h->b4, n_classes * 4) != cudaSuccess || cudaMalloc(&h->act[0], h->act_bytes) != cudaSuccess ||
       cudaMalloc(&h->act[1], h->act_bytes) != cudaSuccess ||
@@ -155,16 +169,23 @@ va_status va_load_weights(va_handle* h, const void* const* tensors, int n_tensor
   int cin = h->cin, cin_pad = h->cin_pad;
   for (int i = 0; i < 13; ++i) {
     const int cout = kVgg16[i].cout;
-    VA_CUDA(va::launch_pack_conv_w(static_cast<const float*>(tensors[2 * i]), h->wconv[i], cout, cin, cin_pad, 3, st));
+    if (h->precision)
+      VA_CUDA(va::launch_pack_conv_w_split6(static_cast<const float*>(tensors[2 * i]), h->wconv[i], cout, cin, cin_pad, 3, st));
+    else
+      VA_CUDA(va::launch_pack_conv_w(static_cast<const float*>(tensors[2 * i]), h->wconv[i], cout, cin, cin_pad, 3, st));
     VA_CUDA(cudaMemcpyAsync(h->bconv[i], tensors[2 * i + 1], cout * 4, cudaMemcpyDeviceToDevice, st));
-    cin = cout; cin_pad = cout;
+    cin = cout; cin_pad = cout * (h->precision ? 6 : 1);
   }
   const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
   const int fout[3] = {kFcHidden, kFcHidden, h->desc_dim};
   for (int i = 0; i < 3; ++i) {
     // FC1 consumes our NHWC flatten of the [7][7][512] feature map
-    VA_CUDA(va::launch_pack_fc_w(static_cast<const float*>(tensors[26 + 2 * i]), h->wfc[i], fout[i], fin[i],
-                                 i == 0 ? 512 : 0, 49, st));
+    if (h->precision)
+      VA_CUDA(va::launch_pack_fc_w_split6(static_cast<const float*>(tensors[26 + 2 * i]), h->wfc[i], fout[i],
+                                          i == 0 ? 512 : fin[i], i == 0 ? 49 : 1, i == 0 ? 1 : 0, st));
+    else
+      VA_CUDA(va::launch_pack_fc_w(static_cast<const float*>(tensors[26 + 2 * i]), h->wfc[i], fout[i], fin[i],
+                                   i == 0 ? 512 : 0, 49, st));
     VA_CUDA(cudaMemcpyAsync(h->bfc[i], tensors[26 + 2 * i + 1], fout[i] * 4, cudaMemcpyDeviceToDevice, st));
   }
   VA_CUDA(va::launch_transpose_f32(static_cast<const float*>(tensors[32]), h->w4t, h->n_classes, h->desc_dim, st));
@@ -209,10 +230,11 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
       d.x = x; d.n = nb; d.H = H; d.W = H; d.cin_pad = cin_pad;
       d.w_packed = h->wconv[i]; d.bias = h->bconv[i]; d.Cout = kVgg16[i].cout; d.ks = 3;
       d.relu = 1; d.pool = kVgg16[i].pool ? 1 : 0; d.y = h->act[cur]; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0;
+      d.split6 = h->precision;
       if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "conv layer %d: %s", i, e);
       x = h->act[cur]; cur ^= 1;
       if (g_prof_on) { g_prof_flops += 2.0 * nb * H * H * (double)d.Cout * 9.0 * cin_real; ++g_prof_launches; }
-      cin_pad = d.Cout; cin_real = d.Cout;
+      cin_pad = d.Cout * (h->precision ? 6 : 1); cin_real = d.Cout;
       if (d.pool) H >>= 1;
     }
     float* desc_out = descriptors ? descriptors + (size_t)off * h->desc_dim : h->desc_ws;
@@ -220,7 +242,8 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
     const int fout[3] = {kFcHidden, kFcHidden, h->desc_dim};
     for (int i = 0; i < 3; ++i) {
       va::ConvLayerDesc d;
-      d.x = x; d.n = nb; d.H = 1; d.W = 1; d.cin_pad = fin[i];
+      d.x = x; d.n = nb; d.H = 1; d.W = 1; d.cin_pad = fin[i] * (h->precision ? 6 : 1);
+      d.split6 = h->precision;
       d.w_packed = h->wfc[i]; d.bias = h->bfc[i]; d.Cout = fout[i]; d.ks = 1;
       d.relu = 1; d.pool = 0; d.force_bn = 0; d.force_r = 0;
       d.y = (i < 2) ? h->act[cur] : nullptr;
@@ -251,7 +274,7 @@ va_status va_conv2d_nhwc(const void* x, int n, int H, int W, int cin, int cin_pa
   VA_CUDA(va::launch_pack_conv_w(w, wp, cout, cin, cin_pad, ks, st));
   va::ConvLayerDesc d;
   d.x = x; d.n = n; d.H = H; d.W = W; d.cin_pad = cin_pad; d.w_packed = wp; d.bias = bias; d.Cout = cout; d.ks = ks;
-  d.relu = relu; d.pool = pool; d.y = y; d.y_f32 = nullptr; d.force_bn = force_bn; d.force_r = force_r;
+  d.relu = relu; d.pool = pool; d.y = y; d.y_f32 = nullptr; d.force_bn = force_bn; d.force_r = force_r; d.split6 = 0;
   const char* e = va::conv_layer_run(d, st);
   cudaFreeAsync(wp, st);
   if (e) return fail(VA_ERR_CUDA, "va_conv2d_nhwc: %s", e);
@@ -270,7 +293,7 @@ va_status va_linear(const void* x, int n, int in_features, const float* w, const
   VA_CUDA(va::launch_pack_fc_w(w, wp, out_features, in_features, 0, 0, st));
   va::ConvLayerDesc d;
   d.x = x; d.n = n; d.H = 1; d.W = 1; d.cin_pad = in_features; d.w_packed = wp; d.bias = bias; d.Cout = out_features;
-  d.ks = 1; d.relu = relu; d.pool = 0; d.y = y_bf16; d.y_f32 = y_f32; d.force_bn = force_bn; d.force_r = 0;
+  d.ks = 1; d.relu = relu; d.pool = 0; d.y = y_bf16; d.y_f32 = y_f32; d.force_bn = force_bn; d.force_r = 0; d.split6 = 0;
   const char* e = va::conv_layer_run(d, st);
   cudaFreeAsync(wp, st);
   if (e) return fail(VA_ERR_CUDA, "va_linear: %s", e);
@@ -337,6 +360,17 @@ va_status va_profile_read(double* tensor_ms, uint64_t* tensor_launches, double* 
   if (tensor_flops) *tensor_flops = g_prof_flops;
   g_prof_launches = 0;
   g_prof_flops = 0.0;
+  return VA_OK;
+}
+
+va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, int height, int width, int k6_pad,
+                                    void* out_nhwc, va_stream_t stream) {
+  if (!x_nchw || !out_nhwc) return fail(VA_ERR_INVALID, "va_pack_input_nchw_split6: NULL argument");
+  if (6 * channels > k6_pad || !(k6_pad == 32 || k6_pad == 128))
+    return fail(VA_ERR_INVALID, "va_pack_input_nchw_split6: channels %d / k6_pad %d", channels, k6_pad);
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_nchw_to_nhwc_split6(x_nchw, n, channels, height * width, k6_pad, out_nhwc,
+                                         static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }
 

@@ -165,7 +165,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   if (R == 3 && BN == 256) return "R=3 not built for BN=256";
 
   // CTA-pair kernel (cta_group::2, UMMA M=256) for the wide 3x3 layers: 6 x 32 KB stages instead of 4 x 48 KB.
-  const bool pair = BN == 256 && CK == 64 && R == 1 && S == 1 && d.ks == 3 && !d.y_f32 && d.force_r != 1 &&
+  const bool pair = BN == 256 && CK == 64 && R == 1 && S == 1 && d.ks == 3 && !d.y_f32 && d.force_r != 1 && !d.split6 &&
                     getenv("VA_CONV_NO_PAIR") == nullptr;
   p.n_tiles_cout = d.Cout / BN;
   p.total_tiles = tiles_m * p.n_tiles_cout;
@@ -175,6 +175,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.ks = d.ks; p.pad = (d.ks - 1) / 2;
   p.cin_chunks = d.cin_pad / CK;
   p.pool = d.pool; p.relu = d.relu; p.out_f32 = d.y_f32 ? 1 : 0;
+  p.split6 = (d.split6 && !d.y_f32) ? 1 : 0;
   p.Cout = d.Cout;
   p.bias = d.bias; p.out_f32_ptr = d.y_f32; p.dbg = g_dbg_counters;
   const int rowb = CK * 2;
@@ -207,7 +208,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   }
   if (!d.y_f32) {
     const int sh = d.pool ? 1 : 0;
-    const uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)(d.W >> sh), (uint64_t)(d.H >> sh), (uint64_t)d.n};
+    const uint64_t dims[4] = {(uint64_t)d.Cout * (d.split6 ? 6 : 1), (uint64_t)(d.W >> sh), (uint64_t)(d.H >> sh), (uint64_t)d.n};
     const uint32_t box[4] = {64u, (uint32_t)(p.w_t >> sh), (uint32_t)(p.h_t >> sh), (uint32_t)p.n_t};
     if (const char* e = encode_bf16(&tO, d.y, 4, dims, box, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
   } else {

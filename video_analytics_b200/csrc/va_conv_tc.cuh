@@ -67,6 +67,7 @@ struct ConvKernelParams {
   int ks, pad;                     // 3/1 or 1/0
   int cin_chunks;                  // Cin_pad / CK
   int pool, relu, out_f32;
+  int split6;                      // fp32-accuracy mode: outputs written as 6 bf16 slice blocks (hi,hi,hi,mid,mid,lo)
   int Cout;
   int num_stages;
   uint32_t a_box_bytes;            // smem bytes reserved per A box (multiple of 1024); a stage holds S of them
@@ -330,6 +331,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               o.w = __uint_as_float(v1[i + 3]) + bs[32 + i + 3];
               if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
               *reinterpret_cast<float4*>(dst + 32 + i) = o;
+            }
+          }
+          continue;
+        }
+        if (p.split6) {
+          // fp32-accuracy ("bf16x3") mode: keep fp32 through bias/ReLU/pool, then write the value as three bf16 slices
+          // hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) into six channel blocks (hi,hi,hi,mid,mid,lo) of
+          // the next layer's K dimension; its weights are packed (hi,mid,lo,hi,mid,hi), so the GEMM sums the six
+          // leading cross terms with fp32 accumulation (dropped terms are O(2^-24)).
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = __uint_as_float(v0[i]) + bs[i], b = __uint_as_float(v1[i]) + bs[32 + i];
+            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            if (p.pool) {
+              a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+              a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, p.w_t));
+              b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, 1));
+              b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, p.w_t));
+            }
+            v0[i] = __float_as_uint(a); v1[i] = __float_as_uint(b);
+          }
+          const bool wr = p.pool ? (((w_i | h_i) & 1) == 0) : true;
+          const int prow = p.pool ? ((n_i * (p.h_t >> 1)) + (h_i >> 1)) * (p.w_t >> 1) + (w_i >> 1) : m;
+          const int sh = p.pool ? 1 : 0;
+#pragma unroll 1
+          for (int sl = 0; sl < 3; ++sl) {
+            uint32_t ps[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = __uint_as_float(v0[2 * i]), b = __uint_as_float(v0[2 * i + 1]);
+              const float c = __uint_as_float(v1[2 * i]), d = __uint_as_float(v1[2 * i + 1]);
+              __nv_bfloat162 lo2 = __floats2bfloat162_rn(a, b), hi2 = __floats2bfloat162_rn(c, d);
+              ps[i] = *reinterpret_cast<uint32_t*>(&lo2);
+              ps[16 + i] = *reinterpret_cast<uint32_t*>(&hi2);
+              // residual for the next slice (exact in fp32)
+              v0[2 * i] = __float_as_uint(__fsub_rn(a, __low2float(lo2)));
+              v0[2 * i + 1] = __float_as_uint(__fsub_rn(b, __high2float(lo2)));
+              v1[2 * i] = __float_as_uint(__fsub_rn(c, __low2float(hi2)));
+              v1[2 * i + 1] = __float_as_uint(__fsub_rn(d, __high2float(hi2)));
+            }
+            if (et < 32) {
+              if (elect_one()) tma_store_wait_read<0>();
+              __syncwarp();
+            }
+            named_bar_sync(3 + eg, 128);
+            if (wr) {
+              uint8_t* rowp = stage_out + prow * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4 val = make_uint4(ps[4 * c], ps[4 * c + 1], ps[4 * c + 2], ps[4 * c + 3]);
+                *reinterpret_cast<uint4*>(rowp + ((c ^ (prow & 7)) << 4)) = val;
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3 + eg, 128);
+            if (et < 32) {
+              if (elect_one()) {
+                // slice sl goes to blocks {0,1,2} (hi), {3,4} (mid), {5} (lo)
+                const int b0 = sl == 0 ? 0 : (sl == 1 ? 3 : 5), b1 = sl == 0 ? 3 : (sl == 1 ? 5 : 6);
+                for (int blk = b0; blk < b1; ++blk)
+                  tma_store_4d(&tmO, stage_out, blk * p.Cout + c0 + chunk * 64, w0 >> sh, h0 >> sh, n0);
+                tma_store_commit();
+              }
+              __syncwarp();
             }
           }
           continue;

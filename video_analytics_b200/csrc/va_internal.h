@@ -29,6 +29,9 @@ cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* s
 cudaError_t launch_consensus_update(float* sum, int32_t* count, const int32_t* video_ids, const float* fv, int B, int D,
                                     cudaStream_t st);
 
+cudaError_t launch_pack_conv_w_split6(const float* w, void* out, int Cout, int Cin, int k6_pad, int ks, cudaStream_t st);
+cudaError_t launch_pack_fc_w_split6(const float* w, void* out, int n_out, int chan, int hw, int permute, cudaStream_t st);
+cudaError_t launch_nchw_to_nhwc_split6(const float* x, int n, int c, int hw, int k6_pad, void* out, cudaStream_t st);
 cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad, void* out, cudaStream_t st);
 
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
@@ -42,6 +45,7 @@ struct ConvLayerDesc {
   void* y;              // bf16 NHWC [n][H>>pool][W>>pool][Cout] (unless y_f32)
   float* y_f32;         // fp32 [n][Cout] (H=W=1 only)
   int force_bn, force_r;
+  int split6;           // fp32-accuracy mode: y has 6*Cout channels (slice blocks), x/w_packed already carry 6x channels
 };
 // Plans (tile shape, kernel variant, tensor maps) and launches one layer.  Returns nullptr on success or a
 // static/thread-local error string.

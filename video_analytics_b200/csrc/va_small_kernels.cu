@@ -572,4 +572,93 @@ cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad,
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ fp32-accuracy mode
+// bf16x3 split: x = hi + mid + lo with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) (24 mantissa bits).
+// Activations carry six channel blocks (hi,hi,hi,mid,mid,lo), weights (hi,mid,lo,hi,mid,hi): one GEMM over the 6x
+// longer K sums the six leading cross terms in fp32.
+__device__ __forceinline__ __nv_bfloat16 bf16_slice(float x, int slice) {
+  __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  if (slice == 0) return hi;
+  const float r1 = __fsub_rn(x, __bfloat162float(hi));
+  __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  if (slice == 1) return mid;
+  return __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(mid)));
+}
+__device__ __constant__ int kActSlice[6] = {0, 0, 0, 1, 1, 2};
+__device__ __constant__ int kWgtSlice[6] = {0, 1, 2, 0, 1, 0};
+
+// OIHW fp32 -> [tap' = s*ks + r][Cout][k6_pad] bf16 with k index blk*Cin + c
+__global__ void pack_conv_w_split6_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                          int k6_pad, int ks) {
+  const size_t total = (size_t)ks * ks * Cout * k6_pad;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(g % k6_pad);
+    const int o = (int)((g / k6_pad) % Cout);
+    const int tap = (int)(g / ((size_t)k6_pad * Cout));
+    const int s = tap / ks, r = tap % ks;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (j < 6 * Cin) {
+      const int blk = j / Cin, c = j % Cin;
+      v = bf16_slice(w[(((size_t)o * Cin + c) * ks + r) * ks + s], kWgtSlice[blk]);
+    }
+    out[g] = v;
+  }
+}
+// [out][chan*hw] fp32 -> bf16 [out][hw][6][chan]; `permute`: the source index is the reference's NCHW flatten c*hw + p
+__global__ void pack_fc_w_split6_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int n_out, int chan,
+                                        int hw, int permute) {
+  const size_t n_in = (size_t)chan * hw;
+  const size_t total = (size_t)n_out * n_in * 6;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = g / (n_in * 6);
+    const size_t k = g % (n_in * 6);
+    const int pp = (int)(k / (6 * (size_t)chan));
+    const int blk = (int)((k / chan) % 6);
+    const int c = (int)(k % chan);
+    const size_t src = permute ? ((size_t)c * hw + pp) : ((size_t)pp * chan + c);
+    out[g] = bf16_slice(w[o * n_in + src], kWgtSlice[blk]);
+  }
+}
+// fp32 NCHW -> split6 bf16 NHWC [n][hw][k6_pad], channel index blk*c + ch
+template <int K6_PAD>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split6_kernel(const float* __restrict__ x, int n, int c, int hw,
+                                                                  __nv_bfloat16* __restrict__ out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n * hw) return;
+  const int img = (int)(g / hw), pix = (int)(g % hw);
+  const float* src = x + (size_t)img * c * hw + pix;
+  __nv_bfloat16* dst = out + (size_t)g * K6_PAD;
+  for (int j = 0; j < K6_PAD; ++j) {
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (j < 6 * c) v = bf16_slice(__ldg(src + (size_t)(j % c) * hw), kActSlice[j / c]);
+    dst[j] = v;
+  }
+}
+
+cudaError_t launch_pack_conv_w_split6(const float* w, void* out, int Cout, int Cin, int k6_pad, int ks, cudaStream_t st) {
+  const size_t total = (size_t)ks * ks * Cout * k6_pad;
+  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  count_launch();
+  pack_conv_w_split6_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cout, Cin, k6_pad, ks);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_fc_w_split6(const float* w, void* out, int n_out, int chan, int hw, int permute, cudaStream_t st) {
+  const size_t total = (size_t)n_out * chan * hw * 6;
+  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  count_launch();
+  pack_fc_w_split6_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), n_out, chan, hw, permute);
+  return cudaGetLastError();
+}
+cudaError_t launch_nchw_to_nhwc_split6(const float* x, int n, int c, int hw, int k6_pad, void* out, cudaStream_t st) {
+  const long long total = (long long)n * hw;
+  if (total == 0) return cudaSuccess;
+  if (6 * c > k6_pad) return cudaErrorInvalidValue;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  count_launch();
+  if (k6_pad == 32) nchw_to_nhwc_split6_kernel<32><<<blocks, 256, 0, st>>>(x, n, c, hw, reinterpret_cast<__nv_bfloat16*>(out));
+  else if (k6_pad == 128) nchw_to_nhwc_split6_kernel<128><<<blocks, 256, 0, st>>>(x, n, c, hw, reinterpret_cast<__nv_bfloat16*>(out));
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 }  // namespace va

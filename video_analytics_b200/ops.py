@@ -132,11 +132,18 @@ STATE_DICT_KEYS = [f"features.{i}.{p}" for i in (0, 2, 5, 7, 10, 12, 14, 17, 19,
 class StreamNet:
     """One VGG16-D stream (spatial: 3 input channels, temporal: 2L=20) resident on the current CUDA device."""
 
-    def __init__(self, stream_kind: int, in_channels: int, n_classes: int = 101, desc_dim: int = 256, max_batch: int = 64):
+    def __init__(self, stream_kind: int, in_channels: int, n_classes: int = 101, desc_dim: int = 256, max_batch: int = 64,
+                 precision: str = "bf16"):
+        """precision: "bf16" (throughput path: bf16 storage, fp32 accumulate) or "fp32" (parity mode: bf16x3 slices,
+        six cross terms per layer; ~6x the FLOPs and activation memory -- use a small max_batch)."""
+        if precision not in ("bf16", "fp32"):
+            raise VAError(f"precision {precision!r}: expected 'bf16' or 'fp32'")
         lib = _lib.load()
         h = C.c_void_p()
-        check(lib.va_create(C.byref(h), stream_kind, in_channels, n_classes, desc_dim, max_batch), "va_create")
+        check(lib.va_create_ex(C.byref(h), stream_kind, in_channels, n_classes, desc_dim, max_batch,
+                               1 if precision == "fp32" else 0), "va_create_ex")
         self._h = h
+        self.precision = precision
         self.stream_kind, self.in_channels = stream_kind, in_channels
         self.n_classes, self.desc_dim, self.max_batch = n_classes, desc_dim, max_batch
         self.c_pad = lib.va_input_channels_padded(h)
@@ -154,6 +161,20 @@ class StreamNet:
         arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         check(_lib.load().va_load_weights(self._h, arr, len(tensors), stream_ptr()), "va_load_weights")
         torch.cuda.current_stream().synchronize()   # packing done; fp32 staging copies may be freed
+
+    def pack_input(self, ip: torch.Tensor) -> torch.Tensor:
+        """Reference-layout snippets (float [n,C,H,W], what the reference feeds as `ip`) -> this handle's network
+        input layout (bf16 NHWC, zero-padded channels; six slice blocks per channel for precision "fp32")."""
+        ip = ip.detach().to(device="cuda", dtype=torch.float32).contiguous()
+        n, c, hh, ww = ip.shape
+        x = torch.empty((n, hh, ww, self.c_pad), dtype=torch.bfloat16, device="cuda")
+        lib = _lib.load()
+        if self.precision == "fp32":
+            check(lib.va_pack_input_nchw_split6(ptr(ip), n, c, hh, ww, self.c_pad, ptr(x), stream_ptr()),
+                  "va_pack_input_nchw_split6")
+        else:
+            check(lib.va_pack_input_nchw(ptr(ip), n, c, hh, ww, self.c_pad, ptr(x), stream_ptr()), "va_pack_input_nchw")
+        return x
 
     def forward(self, x_nhwc: torch.Tensor, *, want_logits=True, want_probs=True, want_pred=True):
         """x bf16 [n,224,224,c_pad] -> (descriptors [n,D] f32, logits [n,C] f32, probs [n,C] f32, pred [n] i32)."""

@@ -151,12 +151,7 @@ class _StreamNetwork(object):
         if isinstance(ip, SnippetBatch):
             x = ip.nhwc
         else:
-            ip = ip.detach().to(device="cuda", dtype=torch.float32).contiguous()
-            n, c, hh, ww = ip.shape
-            x = torch.empty((n, hh, ww, self.net.c_pad), dtype=torch.bfloat16, device="cuda")
-            from . import _lib
-            _lib.check(_lib.load().va_pack_input_nchw(_lib.ptr(ip), n, c, hh, ww, self.net.c_pad, _lib.ptr(x),
-                                                      _lib.stream_ptr()), "va_pack_input_nchw")
+            x = self.net.pack_input(ip)
         return self.net.forward(x)
 
     def train(self):
