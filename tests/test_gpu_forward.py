@@ -228,10 +228,22 @@ def test_fp32_mode_vs_oracle(kind, world):
     desc, logits, probs, pred = net.forward(x)              # n=3 with max_batch=2 -> two chunks
     fv, ol, opred = ts.forward_eval(model, snips[sel])
     op = torch.softmax(ol, 1)
-    perr = float(((probs.cpu() - op).abs() / op).max())
+    # the same restated reference evaluated in fp64: separates OUR rounding from the fp32 CPU run's own rounding
+    fv64, ol64, _ = ts.forward_eval(model.double(), snips[sel].double())
+    op64 = torch.softmax(ol64, 1)
+    model.float()
+    perr = float(((probs.cpu() - op).abs() / op).max())                       # ours vs torch fp32 (the reference run)
+    perr64 = float(((probs.cpu().double() - op64).abs() / op64).max())         # ours vs exact
+    ref_err64 = float(((op.double() - op64).abs() / op64).max())               # torch fp32 vs exact
     derr = float((desc.cpu() - fv).abs().max() / fv.abs().max())
     lerr = float((logits.cpu() - ol).abs().max() / ol.abs().max())
-    assert perr < FP32_RTOL, perr
+    print(f"[fp32 mode {kind}] probs rel err: ours-vs-torch32 {perr:.3e}, ours-vs-fp64 {perr64:.3e}, torch32-vs-fp64 {ref_err64:.3e}; "
+          f"desc {derr:.3e} logits {lerr:.3e}")
+    # north_star: 1e-5 relative for fp32.  Two independent fp32 evaluations of a 16-layer network each sit a few 1e-6
+    # from the exact result, so the bound is applied to the distance from the exact (fp64) evaluation of the reference,
+    # and the distance to the fp32 CPU run is allowed the sum of both roundings.
+    assert perr64 < FP32_RTOL, (perr64, ref_err64)
+    assert perr < FP32_RTOL + ref_err64, (perr, ref_err64)
     assert derr < 1e-4 and lerr < 1e-4, (derr, lerr)
     # top-1: exact agreement wherever the oracle's own margin exceeds our (tiny) logit error
     srt = ol.sort(dim=1, descending=True).values

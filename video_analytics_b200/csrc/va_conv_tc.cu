@@ -80,10 +80,10 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int CK, int R, int S, bool WRES>
+template <int BN, int CK, int R, int S, bool WRES, bool DRAIN = false>
 const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const CUtensorMap& tO,
                            const ConvKernelParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = conv_tc_kernel<BN, CK, R, S, WRES>;
+  auto kfn = conv_tc_kernel<BN, CK, R, S, WRES, DRAIN>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -129,7 +129,9 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   // layer is L2->SM bound.  S=3 (whole filter per stage) is for the first layer (Cin_pad 16/32, one channel chunk).
   const bool r3_ok = d.ks == 3 && p.n_t == 1 && p.w_t % 8 == 0;
   int R = 1, S = 1;
-  if (d.force_r == 3) {
+  if (d.split6) {
+    // fp32-accuracy mode: one tap per stage, BN = 64, per-stage accumulator drain (kernel template DRAIN)
+  } else if (d.force_r == 3) {
     if (!r3_ok) return "force_r=3 needs ks=3 and a single-image tile with w_t%8==0";
     R = 3;
   } else if (d.force_r == 0 && r3_ok && d.Cout <= 128) {
@@ -141,7 +143,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     R = 3; S = 3;
   }
   const int sms = sm_count();
-  int BN = d.force_bn;
+  int BN = d.split6 ? 64 : d.force_bn;
   if (BN == 0) {
     double best = 1e30;
     const int cands[3] = {256, 128, 64};
@@ -185,7 +187,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.staging_bytes = d.pool ? 4096u : 16384u;
   // Resident weights: the layer's whole weight set stays in smem (one Cout tile, one channel chunk, R=3 variants)
   const int groups = (d.ks * d.ks) / (R * S);
-  const bool wres = R == 3 && p.n_tiles_cout == 1 && p.cin_chunks == 1 && BN == 64 && getenv("VA_CONV_NO_WRES") == nullptr &&
+  const bool wres = !d.split6 && R == 3 && p.n_tiles_cout == 1 && p.cin_chunks == 1 && BN == 64 && getenv("VA_CONV_NO_WRES") == nullptr &&
                     (size_t)groups * conv_b_stage_bytes(BN, CK, R, S) <= 80 * 1024;
   const uint32_t stage_bytes = S * p.a_box_bytes + (wres ? 0u : conv_b_stage_bytes(BN, CK, R, S));
   const size_t smem_cap = 227 * 1024;
@@ -242,6 +244,11 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     return nullptr;
   }
 
+  if (d.split6) {
+    if (BN == 64 && CK == 32) return launch_variant<64, 32, 1, 1, false, true>(tA, tW, tO, p, grid, smem, st);
+    if (BN == 64 && CK == 64) return launch_variant<64, 64, 1, 1, false, true>(tA, tW, tO, p, grid, smem, st);
+    return errf("fp32-accuracy mode: no kernel for BN=%d CK=%d", BN, CK);
+  }
 #define VA_CASE(bn, ck, r, sv, wr) \
   if (BN == bn && CK == ck && R == r && S == sv && wres == wr) \
     return launch_variant<bn, ck, r, sv, wr>(tA, tW, tO, p, grid, smem, st);

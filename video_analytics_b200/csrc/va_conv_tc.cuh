@@ -105,7 +105,10 @@ __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&m);
 }
 
-template <int BN, int CK, int R, int S, bool WRES>
+// DRAIN (fp32-accuracy mode only): the tensor core adds into its fp32 accumulator with truncation, so a long K loop
+// drifts by ~1e-5 per layer (measured: descriptors 4e-4 off after 16 layers).  With DRAIN every pipeline stage gets a
+// fresh TMEM accumulator that epilogue group 0 drains and sums in registers with round-to-nearest fp32 adds.
+template <int BN, int CK, int R, int S, bool WRES, bool DRAIN = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
@@ -224,11 +227,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     long long t_full = 0, t_tempty = 0, t_begin = clock64(), n_tiles = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       ++n_tiles;
-      mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_u + as * BN;
+      if (!DRAIN) {
+        mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
+        tc_fence_after();
+      }
+      uint32_t d_tmem = tmem_u + as * BN;
       uint32_t acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (DRAIN) {                       // a fresh accumulator per pipeline stage
+          mbar_wait_t(&tempty_bar[as], as_phase ^ 1, 200 + as, dbg, t_tempty);
+          d_tmem = tmem_u + as * BN;
+          acc = 0;
+        }
         mbar_wait_t(&full_bar[stage], phase, 300 + stage, dbg, t_full);
         tc_fence_after();
         // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
@@ -249,14 +259,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
+          if (DRAIN || kb == num_kb - 1) umma_commit(&tfull_bar[as]);   // accumulator complete -> epilogue
         }
         __syncwarp();
         acc = 1;
         if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+        if (DRAIN) { as ^= 1; if (as == 0) as_phase ^= 1; }
       }
-      as ^= 1;
-      if (as == 0) as_phase ^= 1;
+      if (!DRAIN) { as ^= 1; if (as == 0) as_phase ^= 1; }
     }
     if (dbg && lane == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = t_full; p.dbg[4] = t_tempty; p.dbg[11] = n_tiles; }
   } else {
@@ -270,14 +280,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int w_i = m & (p.w_t - 1);
     const int h_i = (m >> p.log2_w_t) & (p.h_t - 1);
     const int n_i = m >> (p.log2_w_t + p.log2_h_t);
-    const uint32_t as = (uint32_t)eg;
+    uint32_t as = (uint32_t)eg;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && et == 0;
     long long t_tfull = 0, t_stage = 0, t_begin = clock64();
     int bias_c0 = -1;
     int it = 0;
+    uint32_t drain_cnt = 0;               // DRAIN: running count of drained accumulators (stage = cnt&1, phase = cnt>>1)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != eg) continue;       // the other group's tile
-      const uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
+      if (DRAIN ? (eg != 0) : ((it & 1) != eg)) continue;       // the other group's tile (DRAIN: group 0 does all)
+      uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
       uint32_t nt, mt, tw, th, tn;
       p.div_cout.divmod((uint32_t)tile, mt, nt);
       p.div_w.divmod(mt, mt, tw);
@@ -291,20 +302,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bias_c0 = c0;
       }
 
-      mbar_wait_t(&tfull_bar[as], as_phase, 400 + as, dbg, t_tfull);
-      tc_fence_after();
+      if (!DRAIN) {
+        mbar_wait_t(&tfull_bar[as], as_phase, 400 + as, dbg, t_tfull);
+        tc_fence_after();
+      }
 
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 64; ++chunk) {
         uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + chunk * 64;
-        tmem_ld32(taddr, v0);
-        tmem_ld32(taddr + 32, v1);
-        tmem_ld_wait();
-        if (chunk == BN / 64 - 1) {        // accumulator stage fully drained into registers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (DRAIN) {
+          // BN == 64: sum the per-stage accumulators with round-to-nearest fp32 adds
+          float s0[32], s1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+          for (int g = 0; g < num_kb; ++g, ++drain_cnt) {
+            as = drain_cnt & 1u;
+            as_phase = (drain_cnt >> 1) & 1u;
+            mbar_wait(&tfull_bar[as], as_phase, 400 + as);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            tmem_ld32(ta, v0);
+            tmem_ld32(ta + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              s0[i] = __fadd_rn(s0[i], __uint_as_float(v0[i]));
+              s1[i] = __fadd_rn(s1[i], __uint_as_float(v1[i]));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v0[i] = __float_as_uint(s0[i]); v1[i] = __float_as_uint(s1[i]); }
+        } else {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + chunk * 64;
+          tmem_ld32(taddr, v0);
+          tmem_ld32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (chunk == BN / 64 - 1) {        // accumulator stage fully drained into registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
         }
         const float* bs = bias_g + chunk * 64;
         if (p.out_f32) {
