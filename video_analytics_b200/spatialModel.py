@@ -104,7 +104,7 @@ class _StreamNetwork(object):
         raise NotImplementedError
 
     def _init_common(self, nActionClasses, nEpochs, lr, momentumVal, descriptorDim, trainLoader, testLoader, lrMilestones,
-                     ckpLoc, gpu, pretrained, maxBatch):
+                     ckpLoc, gpu, pretrained, maxBatch, precision="bf16"):
         import torch.optim.lr_scheduler as slr
         self.nActionClasses, self.nEpochs, self.lr = nActionClasses, nEpochs, lr
         self.trainLoader, self.testLoader = trainLoader, testLoader
@@ -133,7 +133,8 @@ class _StreamNetwork(object):
         self.testDict = DeviceVideoDict(descriptorDim)
         self.model = nn.DataParallel(self.model)                           # reference :133 -- gives "module." keys
         self.epoch = 0
-        self.net = ops.StreamNet(self._stream_kind, self._in_channels, nActionClasses, descriptorDim, max_batch=maxBatch)
+        self.net = ops.StreamNet(self._stream_kind, self._in_channels, nActionClasses, descriptorDim, max_batch=maxBatch,
+                                 precision=precision)
         self.sync_weights()
 
     def sync_weights(self):
@@ -149,6 +150,9 @@ class _StreamNetwork(object):
 
     def _forward_full(self, ip):
         if isinstance(ip, SnippetBatch):
+            if self.net.precision != "bf16":
+                raise VAError("loader batches are bf16 snippets; feed the fp32 mode reference-layout float tensors "
+                              "(dataset[i][0] / torch.stack) so that no input bits are lost")
             x = ip.nhwc
         else:
             x = self.net.pack_input(ip)
@@ -239,10 +243,10 @@ class SpatialNetwork(_StreamNetwork):
     """A wrapper for the spatial stream (reference spatialModel.py:85-283)."""
 
     def __init__(self, nActionClasses, nEpochs, lr, momentumVal, descriptorDim, trainLoader, testLoader, lrMilestones,
-                 ckpLoc, gpu=False, pretrained=False, maxBatch=GPU_MAX_BATCH):
+                 ckpLoc, gpu=False, pretrained=False, maxBatch=GPU_MAX_BATCH, precision="bf16"):
         super().__init__()
         self._init_common(nActionClasses, nEpochs, lr, momentumVal, descriptorDim, trainLoader, testLoader, lrMilestones,
-                          ckpLoc, gpu, pretrained, maxBatch)
+                          ckpLoc, gpu, pretrained, maxBatch, precision)
 
     def _build_torch_model(self, pretrained):
         return build_spatial_torch_model(self.nActionClasses, self.descriptorDim, pretrained)

@@ -117,12 +117,12 @@ class TemporalNetwork(_StreamNetwork):
     _stream_kind = ops.STREAM_TEMPORAL
 
     def __init__(self, nActionClasses, flowSampleSize, nEpochs, lr, momentumVal, descriptorDim, trainLoader, testLoader,
-                 lrMilestones, ckpLoc, gpu=False, pretrained=False, maxBatch=GPU_MAX_BATCH):
+                 lrMilestones, ckpLoc, gpu=False, pretrained=False, maxBatch=GPU_MAX_BATCH, precision="bf16"):
         super().__init__()
         self.flowSampleSize = flowSampleSize
         self._in_channels = 2 * flowSampleSize
         self._init_common(nActionClasses, nEpochs, lr, momentumVal, descriptorDim, trainLoader, testLoader, lrMilestones,
-                          ckpLoc, gpu, pretrained, maxBatch)
+                          ckpLoc, gpu, pretrained, maxBatch, precision)
 
     def _build_torch_model(self, pretrained):
         return build_temporal_torch_model(self.nActionClasses, self.flowSampleSize, self.descriptorDim, pretrained)
