@@ -131,6 +131,45 @@ va_status va_pack_input_nchw(const float* x_nchw, int n, int channels, int heigh
 va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, int height, int width, int k6_pad,
                                     void* out_nhwc, va_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Training-step primitives.  Replace loss.backward() + optimizer.step() of
+ * train() (reference spatialModel.py:178-181: CrossEntropyLoss, SGD(lr, momentum=0.9)) and the train-mode forward
+ * (Dropout after FC1..FC3, :141-152).  Activations / activation gradients are bf16 NHWC, parameter gradients fp32
+ * in the reference's own layouts (OIHW, [out][in]) so that they line up with the fp32 master parameters.
+ *   va_maxpool2x2_nhwc   : MaxPool2d(2,2) forward (training keeps the un-pooled activation for the backward pass)
+ *   va_relu_pool_bwd     : dZ = un-pool(dout) * (Y > 0); pooled=0: dout is already the gradient of Y
+ *   va_bias_grad         : db[c] = sum_rows dZ[row][c]
+ *   va_dropout           : y = x * scale where mask (u8) != 0 else 0 (forward and backward are the same map)
+ *   va_conv2d_dgrad      : dX = conv3x3(dZ, rot180(W) with channel roles swapped)  -- tcgen05 layer kernel
+ *   va_linear_dgrad      : dX = dY . W                                            -- tcgen05 layer kernel
+ *   va_wgrad             : dW[co][ci][r][s] = sum_pixels dZ[p][co] X[p + (r,s)][ci] -- tcgen05 weight-gradient GEMM
+ *                          (ks=1, H=1, W=batch gives the fully-connected dW = dY^T . X)
+ *   va_ce_train          : fp32 logit layer forward + mean cross-entropy + its backward (dlogits, dW4, db4, dx)
+ *   va_transpose_bf16    : [n][A][B] -> [n][B][A] (NHWC <-> the reference's NCHW flatten order in front of FC1)
+ *   va_relu_bwd_f32_to_bf16, va_f32_to_bf16 : glue between the fp32 descriptor layer and the bf16 stack
+ *   va_sgd_momentum      : buf = g (first step) | momentum*buf + g;  p -= lr*buf   (grad_scale multiplies g first,
+ *                          e.g. 1/world_size after a gradient all-reduce)
+ * --------------------------------------------------------------------------------------------------------- */
+va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, va_stream_t stream);
+va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ,
+                           va_stream_t stream);
+va_status va_bias_grad(const void* dZ, long long rows, int C, float* db, va_stream_t stream);
+va_status va_dropout(const void* x, const uint8_t* mask, long long total, float scale, int is_f32, void* y,
+                     va_stream_t stream);
+va_status va_conv2d_dgrad(const void* dZ, int n, int H, int W, int cout, const float* w, int cin, void* dX,
+                          va_stream_t stream);
+va_status va_linear_dgrad(const void* dY, int n, int out_features, const float* w, int in_features, void* dX,
+                          va_stream_t stream);
+va_status va_wgrad(const void* dZ, const void* X, int n, int H, int W, int cout, int cin, int cin_pad, int ks, float* dW,
+                   va_stream_t stream);
+va_status va_ce_train(const float* x, const float* w4, const float* b4, const int64_t* labels, int n, int D, int C,
+                      float* logits, float* dlogits, float* loss, float* dw4, float* db4, float* dx, va_stream_t stream);
+va_status va_relu_bwd_f32_to_bf16(const float* dy, const float* y, long long n, void* dz, va_stream_t stream);
+va_status va_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                          int first_step, float grad_scale, va_stream_t stream);
+va_status va_transpose_bf16(const void* x, int n, int A, int B, void* y, va_stream_t stream);
+va_status va_f32_to_bf16(const float* x, long long n, void* y, va_stream_t stream);
+
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,

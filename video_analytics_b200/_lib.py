@@ -35,6 +35,18 @@ SIGNATURES = {
     "va_consensus_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "va_pack_input_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "va_pack_input_nchw_split6": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "va_maxpool2x2_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "va_relu_pool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "va_bias_grad": (_i, [_vp, C.c_longlong, _i, _vp, _vp]),
+    "va_dropout": (_i, [_vp, _vp, C.c_longlong, _f, _i, _vp, _vp]),
+    "va_conv2d_dgrad": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "va_linear_dgrad": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "va_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "va_ce_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "va_relu_bwd_f32_to_bf16": (_i, [_vp, _vp, C.c_longlong, _vp, _vp]),
+    "va_sgd_momentum": (_i, [_vp, _vp, _vp, C.c_longlong, _f, _f, _i, _f, _vp]),
+    "va_transpose_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "va_f32_to_bf16": (_i, [_vp, C.c_longlong, _vp, _vp]),
     "va_synth_fill": (_i, [_vp, _sz, _i, _i, _i, _i, _u32, _u32, _vp]),
     "va_debug_conv_counters": (_i, [_vp]),
     "va_profile_enable": (_i, [_i]),

@@ -374,6 +374,132 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
   return VA_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ training primitives
+va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, va_stream_t stream) {
+  if (!x || !y) return fail(VA_ERR_INVALID, "va_maxpool2x2_nhwc: NULL argument");
+  if ((H | W) & 1 || C % 8) return fail(VA_ERR_INVALID, "va_maxpool2x2_nhwc: H, W must be even and C a multiple of 8");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_maxpool_fwd(x, y, n, H, W, C, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ,
+                           va_stream_t stream) {
+  if (!dout || !Y || !dZ) return fail(VA_ERR_INVALID, "va_relu_pool_bwd: NULL argument");
+  if (C % 2 || (pooled && ((H | W) & 1))) return fail(VA_ERR_INVALID, "va_relu_pool_bwd: bad shape");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_relu_pool_bwd(dout, Y, dZ, n, H, W, C, pooled, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_bias_grad(const void* dZ, long long rows, int C, float* db, va_stream_t stream) {
+  if (!dZ || !db) return fail(VA_ERR_INVALID, "va_bias_grad: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_bias_grad(dZ, db, rows, C, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_dropout(const void* x, const uint8_t* mask, long long total, float scale, int is_f32, void* y,
+                     va_stream_t stream) {
+  if (!x || !mask || !y) return fail(VA_ERR_INVALID, "va_dropout: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_dropout(x, mask, y, total, scale, is_f32, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_conv2d_dgrad(const void* dZ, int n, int H, int W, int cout, const float* w, int cin, void* dX,
+                          va_stream_t stream) {
+  if (!dZ || !w || !dX) return fail(VA_ERR_INVALID, "va_conv2d_dgrad: NULL argument");
+  if (cin % 64 || cout % 64) return fail(VA_ERR_INVALID, "va_conv2d_dgrad: channels must be multiples of 64 (got %d -> %d)", cout, cin);
+  if (va_status s = require_sm100()) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* wt = nullptr; void* wp = nullptr; float* zero_bias = nullptr;
+  VA_CUDA(cudaMallocAsync(&wt, (size_t)cout * cin * 9 * 4, st));
+  VA_CUDA(cudaMallocAsync(&wp, (size_t)9 * cin * cout * 2, st));
+  VA_CUDA(cudaMallocAsync(&zero_bias, (size_t)cin * 4, st));
+  VA_CUDA(cudaMemsetAsync(zero_bias, 0, (size_t)cin * 4, st));
+  VA_CUDA(va::launch_flip_transpose_conv_w(w, wt, cout, cin, 3, st));          // OIHW' [cin][cout][3][3]
+  VA_CUDA(va::launch_pack_conv_w(wt, wp, cin, cout, cout, 3, st));             // the dgrad conv: cout -> cin channels
+  va::ConvLayerDesc d;
+  d.x = dZ; d.n = n; d.H = H; d.W = W; d.cin_pad = cout; d.w_packed = wp; d.bias = zero_bias; d.Cout = cin; d.ks = 3;
+  d.relu = 0; d.pool = 0; d.y = dX; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0; d.split6 = 0;
+  const char* e = va::conv_layer_run(d, st);
+  cudaFreeAsync(wt, st); cudaFreeAsync(wp, st); cudaFreeAsync(zero_bias, st);
+  if (e) return fail(VA_ERR_CUDA, "va_conv2d_dgrad: %s", e);
+  return VA_OK;
+}
+va_status va_linear_dgrad(const void* dY, int n, int out_features, const float* w, int in_features, void* dX,
+                          va_stream_t stream) {
+  if (!dY || !w || !dX) return fail(VA_ERR_INVALID, "va_linear_dgrad: NULL argument");
+  if (in_features % 64 || out_features % 64) return fail(VA_ERR_INVALID, "va_linear_dgrad: features must be multiples of 64");
+  if (va_status s = require_sm100()) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* wp = nullptr; float* zero_bias = nullptr;
+  VA_CUDA(cudaMallocAsync(&wp, (size_t)in_features * out_features * 2, st));
+  VA_CUDA(cudaMallocAsync(&zero_bias, (size_t)in_features * 4, st));
+  VA_CUDA(cudaMemsetAsync(zero_bias, 0, (size_t)in_features * 4, st));
+  VA_CUDA(va::launch_pack_fc_w_t(w, wp, out_features, in_features, st));      // bf16 [in][out]
+  va::ConvLayerDesc d;
+  d.x = dY; d.n = n; d.H = 1; d.W = 1; d.cin_pad = out_features; d.w_packed = wp; d.bias = zero_bias; d.Cout = in_features;
+  d.ks = 1; d.relu = 0; d.pool = 0; d.y = dX; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0; d.split6 = 0;
+  const char* e = va::conv_layer_run(d, st);
+  cudaFreeAsync(wp, st); cudaFreeAsync(zero_bias, st);
+  if (e) return fail(VA_ERR_CUDA, "va_linear_dgrad: %s", e);
+  return VA_OK;
+}
+va_status va_wgrad(const void* dZ, const void* X, int n, int H, int W, int cout, int cin, int cin_pad, int ks, float* dW,
+                   va_stream_t stream) {
+  if (!dZ || !X || !dW) return fail(VA_ERR_INVALID, "va_wgrad: NULL argument");
+  if (ks != 1 && ks != 3) return fail(VA_ERR_INVALID, "va_wgrad: ks must be 1 or 3");
+  if (cin_pad < cin || n <= 0 || (long long)n * H > 65535)
+    return fail(VA_ERR_INVALID, "va_wgrad: bad shape (n=%d H=%d cin=%d cin_pad=%d; n*H must be <= 65535)", n, H, cin, cin_pad);
+  if (va_status s = require_sm100()) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Wp = (W + 7) & ~7;
+  void *dzt = nullptr, *xt = nullptr; float* ws = nullptr;
+  VA_CUDA(cudaMallocAsync(&dzt, (size_t)n * cout * H * Wp * 2, st));
+  VA_CUDA(cudaMallocAsync(&xt, (size_t)ks * n * cin * H * Wp * 2, st));   // ks horizontally pre-shifted copies
+  VA_CUDA(cudaMallocAsync(&ws, (size_t)ks * ks * cout * cin * 4, st));
+  VA_CUDA(va::launch_nhwc_to_nchw_bf16(dZ, dzt, n, H, W, Wp, cout, cout, 1, st));
+  // X may carry zero-padded channels (first layer): only the first `cin` are transposed
+  VA_CUDA(va::launch_nhwc_to_nchw_bf16(X, xt, n, H, W, Wp, cin, cin_pad, ks, st));
+  const char* e = va::wgrad_run(dzt, xt, n, H, W, Wp, cout, cin, ks, ws, dW, st);
+  cudaFreeAsync(dzt, st); cudaFreeAsync(xt, st); cudaFreeAsync(ws, st);
+  if (e) return fail(VA_ERR_CUDA, "va_wgrad: %s", e);
+  return VA_OK;
+}
+va_status va_ce_train(const float* x, const float* w4, const float* b4, const int64_t* labels, int n, int D, int C,
+                      float* logits, float* dlogits, float* loss, float* dw4, float* db4, float* dx, va_stream_t stream) {
+  if (!x || !w4 || !b4 || !labels || !dlogits || !loss || !dw4 || !db4 || !dx) return fail(VA_ERR_INVALID, "va_ce_train: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_ce_train(x, w4, b4, labels, n, D, C, logits, dlogits, loss, dw4, db4, dx, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_relu_bwd_f32_to_bf16(const float* dy, const float* y, long long n, void* dz, va_stream_t stream) {
+  if (!dy || !y || !dz) return fail(VA_ERR_INVALID, "va_relu_bwd_f32_to_bf16: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_relu_bwd_f32_to_bf16(dy, y, dz, n, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                          int first_step, float grad_scale, va_stream_t stream) {
+  if (!param || !grad || !momentum_buf) return fail(VA_ERR_INVALID, "va_sgd_momentum: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_sgd_momentum(param, grad, momentum_buf, n, lr, momentum, first_step, grad_scale,
+                                  static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_transpose_bf16(const void* x, int n, int A, int B, void* y, va_stream_t stream) {
+  if (!x || !y) return fail(VA_ERR_INVALID, "va_transpose_bf16: NULL argument");
+  if (n > 65535) return fail(VA_ERR_INVALID, "va_transpose_bf16: n must be <= 65535");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_nhwc_to_nchw_bf16(x, y, n, 1, A, A, B, B, 1, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_f32_to_bf16(const float* x, long long n, void* y, va_stream_t stream) {
+  if (!x || !y) return fail(VA_ERR_INVALID, "va_f32_to_bf16: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_f32_to_bf16(x, y, n, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c, uint32_t seed,
                         uint32_t first_id, va_stream_t stream) {
   if (!images) return fail(VA_ERR_INVALID, "va_synth_fill: NULL");

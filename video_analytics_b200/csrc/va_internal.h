@@ -34,6 +34,24 @@ cudaError_t launch_pack_fc_w_split6(const float* w, void* out, int n_out, int ch
 cudaError_t launch_nchw_to_nhwc_split6(const float* x, int n, int c, int hw, int k6_pad, void* out, cudaStream_t st);
 cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad, void* out, cudaStream_t st);
 
+// ---- training-step kernels (va_train_kernels.cu, va_wgrad_tc.cu)
+cudaError_t launch_maxpool_fwd(const void* x, void* y, int n, int H, int W, int C, cudaStream_t st);
+cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, int n, int H, int W, int C, int pooled, cudaStream_t st);
+cudaError_t launch_bias_grad(const void* dZ, float* db, long long rows, int C, cudaStream_t st);
+cudaError_t launch_dropout(const void* x, const uint8_t* mask, void* y, long long total, float scale, int is_f32, cudaStream_t st);
+cudaError_t launch_nhwc_to_nchw_bf16(const void* x, void* y, int n, int H, int W, int Wp, int C, int Cs, int nshift,
+                                     cudaStream_t st);
+cudaError_t launch_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t st);
+cudaError_t launch_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, int first_step,
+                                float grad_scale, cudaStream_t st);
+cudaError_t launch_ce_train(const float* x, const float* w4, const float* b4, const int64_t* labels, int n, int D, int C,
+                            float* logits, float* dlogits, float* loss, float* dw4, float* db4, float* dx, cudaStream_t st);
+cudaError_t launch_relu_bwd_f32_to_bf16(const float* dy, const float* y, void* dz, long long n, cudaStream_t st);
+cudaError_t launch_flip_transpose_conv_w(const float* w, float* out, int Cout, int Cin, int ks, cudaStream_t st);
+cudaError_t launch_pack_fc_w_t(const float* w, void* out, int n_out, int n_in, cudaStream_t st);
+const char* wgrad_run(const void* dz_nchw, const void* x_nchw, int n, int H, int W, int Wp, int Cout, int Cin, int ks,
+                      float* dwt_ws, float* dw_oihw, cudaStream_t st);
+
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
 struct ConvLayerDesc {
   const void* x;        // bf16 NHWC [n][H][W][cin_pad]

@@ -1,0 +1,161 @@
+"""Python call layer over the training-step primitives of the C-ABI (include/va_b200.h, "Training-step primitives").
+
+Same rules as ops.py: torch only owns device memory and the stream; every function launches hand-written sm_100a
+kernels and raises `VAError` on failure.  Activations and activation gradients are bf16 NHWC, parameter gradients
+fp32 in the reference's own layouts (Conv2d OIHW, Linear [out][in]).
+Reference being replaced: loss.backward() / optimizer.step() in train() (Sheet03/spatialModel.py:178-181).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .ops import _need_cuda
+
+
+def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
+    """bf16 NHWC [n,H,W,C] -> [n,H/2,W/2,C]  (MaxPool2d(2,2))."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16
+    n, H, W, Cc = x.shape
+    y = torch.empty((n, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().va_maxpool2x2_nhwc(ptr(x), n, H, W, Cc, ptr(y), stream_ptr()), "va_maxpool2x2_nhwc")
+    return y
+
+
+def relu_pool_bwd(dout: torch.Tensor, y: torch.Tensor, *, pooled: bool) -> torch.Tensor:
+    """Gradient w.r.t. the pre-activation z of y = relu(z) [n,H,W,C], given the gradient of pool(y) (pooled=True,
+    dout [n,H/2,W/2,C]) or of y itself (pooled=False)."""
+    _need_cuda(dout, y)
+    assert dout.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+    n, H, W, Cc = y.shape
+    dz = torch.empty_like(y)
+    check(_lib.load().va_relu_pool_bwd(ptr(dout), ptr(y), n, H, W, Cc, int(pooled), ptr(dz), stream_ptr()),
+          "va_relu_pool_bwd")
+    return dz
+
+
+def bias_grad(dz: torch.Tensor) -> torch.Tensor:
+    """db[c] = sum over all leading dims of dz[..., c]  (fp32)."""
+    _need_cuda(dz)
+    assert dz.dtype == torch.bfloat16
+    Cc = dz.shape[-1]
+    rows = dz.numel() // Cc
+    db = torch.zeros((Cc,), dtype=torch.float32, device=dz.device)
+    check(_lib.load().va_bias_grad(ptr(dz), rows, Cc, ptr(db), stream_ptr()), "va_bias_grad")
+    return db
+
+
+def dropout(x: torch.Tensor, mask: torch.Tensor, p: float = 0.5) -> torch.Tensor:
+    """y = x / (1-p) where mask else 0; the same map is its own backward.  mask: uint8, caller-supplied (the parity
+    tests share it with the oracle; the training loop draws it with torch's generator)."""
+    _need_cuda(x, mask)
+    assert mask.dtype == torch.uint8 and mask.numel() == x.numel()
+    assert x.dtype in (torch.bfloat16, torch.float32)
+    y = torch.empty_like(x)
+    check(_lib.load().va_dropout(ptr(x), ptr(mask), x.numel(), 1.0 / (1.0 - p), int(x.dtype == torch.float32), ptr(y),
+                                 stream_ptr()), "va_dropout")
+    return y
+
+
+def conv2d_dgrad(dz: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dX of a 3x3/s1/p1 convolution: dz bf16 [n,H,W,cout], w fp32 OIHW [cout,cin,3,3] -> bf16 [n,H,W,cin]."""
+    _need_cuda(dz, w)
+    assert dz.dtype == torch.bfloat16 and w.dtype == torch.float32
+    n, H, W, cout = dz.shape
+    assert w.shape[0] == cout and tuple(w.shape[2:]) == (3, 3)
+    cin = w.shape[1]
+    dx = torch.empty((n, H, W, cin), dtype=torch.bfloat16, device=dz.device)
+    check(_lib.load().va_conv2d_dgrad(ptr(dz), n, H, W, cout, ptr(w), cin, ptr(dx), stream_ptr()), "va_conv2d_dgrad")
+    return dx
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dX = dY . W: dy bf16 [n,out], w fp32 [out,in] -> bf16 [n,in]."""
+    _need_cuda(dy, w)
+    assert dy.dtype == torch.bfloat16 and w.dtype == torch.float32
+    n, fout = dy.shape
+    fin = w.shape[1]
+    dx = torch.empty((n, fin), dtype=torch.bfloat16, device=dy.device)
+    check(_lib.load().va_linear_dgrad(ptr(dy), n, fout, ptr(w), fin, ptr(dx), stream_ptr()), "va_linear_dgrad")
+    return dx
+
+
+def conv2d_wgrad(dz: torch.Tensor, x: torch.Tensor, cin: int, ks: int = 3) -> torch.Tensor:
+    """dW fp32 OIHW [cout,cin,ks,ks] from dz bf16 [n,H,W,cout] and the layer input x bf16 [n,H,W,cin_pad>=cin]."""
+    _need_cuda(dz, x)
+    assert dz.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    n, H, W, cout = dz.shape
+    assert tuple(x.shape[:3]) == (n, H, W)
+    dw = torch.empty((cout, cin, ks, ks), dtype=torch.float32, device=dz.device)
+    check(_lib.load().va_wgrad(ptr(dz), ptr(x), n, H, W, cout, cin, x.shape[3], ks, ptr(dw), stream_ptr()), "va_wgrad")
+    return dw
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW = dY^T . X fp32 [out,in] from dy bf16 [n,out], x bf16 [n,in]  (the batch is the GEMM's K dimension)."""
+    _need_cuda(dy, x)
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    n, fout = dy.shape
+    fin = x.shape[1]
+    dw = torch.empty((fout, fin), dtype=torch.float32, device=dy.device)
+    check(_lib.load().va_wgrad(ptr(dy), ptr(x), 1, 1, n, fout, fin, fin, 1, ptr(dw), stream_ptr()), "va_wgrad")
+    return dw
+
+
+def ce_train(x: torch.Tensor, w4: torch.Tensor, b4: torch.Tensor, labels: torch.Tensor):
+    """fp32 logit layer + mean cross-entropy, forward and backward in one call.
+    x fp32 [n,D] (descriptors after dropout), w4 [C,D], b4 [C], labels int64 [n].
+    Returns dict(logits, loss (1-element tensor), dlogits, dw4, db4, dx)."""
+    _need_cuda(x, w4, b4, labels)
+    assert x.dtype == torch.float32 and labels.dtype == torch.int64
+    n, D = x.shape
+    Cc = w4.shape[0]
+    dev = x.device
+    out = dict(logits=torch.empty((n, Cc), dtype=torch.float32, device=dev),
+               dlogits=torch.empty((n, Cc), dtype=torch.float32, device=dev),
+               loss=torch.zeros((1,), dtype=torch.float32, device=dev),
+               dw4=torch.empty((Cc, D), dtype=torch.float32, device=dev),
+               db4=torch.empty((Cc,), dtype=torch.float32, device=dev),
+               dx=torch.empty((n, D), dtype=torch.float32, device=dev))
+    check(_lib.load().va_ce_train(ptr(x), ptr(w4), ptr(b4), ptr(labels), n, D, Cc, ptr(out["logits"]), ptr(out["dlogits"]),
+                                  ptr(out["loss"]), ptr(out["dw4"]), ptr(out["db4"]), ptr(out["dx"]), stream_ptr()),
+          "va_ce_train")
+    return out
+
+
+def relu_bwd_f32_to_bf16(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    _need_cuda(dy, y)
+    assert dy.dtype == torch.float32 and y.dtype == torch.float32
+    dz = torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device)
+    check(_lib.load().va_relu_bwd_f32_to_bf16(ptr(dy), ptr(y), dy.numel(), ptr(dz), stream_ptr()), "va_relu_bwd_f32_to_bf16")
+    return dz
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[n,A,B] -> [n,B,A] (bf16)."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 3
+    n, A, B = x.shape
+    y = torch.empty((n, B, A), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().va_transpose_bf16(ptr(x), n, A, B, ptr(y), stream_ptr()), "va_transpose_bf16")
+    return y
+
+
+def f32_to_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dtype == torch.float32
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().va_f32_to_bf16(ptr(x), x.numel(), ptr(y), stream_ptr()), "va_f32_to_bf16")
+    return y
+
+
+def sgd_momentum_(param: torch.Tensor, grad: torch.Tensor, buf: torch.Tensor, *, lr: float, momentum: float,
+                  first_step: bool, grad_scale: float = 1.0) -> None:
+    """In place torch.optim.SGD(lr, momentum) update (dampening 0, no nesterov, no weight decay;
+    reference spatialModel.py:116)."""
+    _need_cuda(param, grad, buf)
+    assert param.dtype == grad.dtype == buf.dtype == torch.float32 and param.numel() == grad.numel() == buf.numel()
+    check(_lib.load().va_sgd_momentum(ptr(param), ptr(grad), ptr(buf), param.numel(), lr, momentum, int(first_step),
+                                      grad_scale, stream_ptr()), "va_sgd_momentum")
