@@ -8,6 +8,8 @@ What is executed from the reference itself (unmodified, imported or exec'd from 
   * Sheet03/spatialModel.py class SpatialDataset       -> source lines exec'd (the class is py3-clean; the module is
                                                           not: print statements further down)
   * Sheet03/combinedModel.py def combineDescriptors    -> source lines exec'd (same reason)
+  * Sheet03/spatialModel.py train() loop body (forward, CrossEntropyLoss, zero_grad/backward/step) -> source lines
+    exec'd on a shim `self`, with real nn.Dropout modules
 What cannot run (Python-2 only; restated in oracle/two_stream.py, unpinned by reference code):
   TemporalDataset.__getitem__ (`it.next()`, float randint), Spatial/TemporalNetwork (print statements, Variable/
   `.cuda(async=True)`), combinedModel.main (sklearn.externals).
@@ -192,6 +194,47 @@ def main():
                    "csv_spatial": open(ps, newline="").read(), "csv_temporal": open(pt, newline="").read()},
                   open(os.path.join(GOLD, "combine_descriptors.json"), "w"))
     report["combineDescriptors_vs_reference_function"] = "equal"
+
+    # ---- (h) training step: the reference's own loop-body lines (spatialModel.py train(), "op = self.features(ip)" ..
+    #          "self.optimizer.step()") exec'd on a shim `self` with REAL nn.Dropout modules, vs ts.train_step with the
+    #          masks ts.draw_dropout_masks draws from the same RNG state.  Two consecutive steps (momentum path).
+    import copy
+    import textwrap
+    import types
+    with open(os.path.join(REF, "spatialModel.py")) as f:
+        lines = f.readlines()
+    first = next(i for i, l in enumerate(lines) if "op = self.features(ip)" in l)
+    last = next(i for i, l in enumerate(lines) if i > first and "self.optimizer.step()" in l)
+    body = textwrap.dedent("".join(lines[first:last + 1]).expandtabs(4))
+    model_r = ts.build_spatial_model(seed=5)
+    model_o = copy.deepcopy(model_r)
+    shim = types.SimpleNamespace(features=model_r.features, classifierList=list(model_r.classifier),
+                                 classifierLen=len(list(model_r.classifier)), criterion=torch.nn.CrossEntropyLoss(),
+                                 optimizer=torch.optim.SGD(model_r.parameters(), 0.1, momentum=0.9))
+    opt_o = torch.optim.SGD(model_o.parameters(), 0.1, momentum=0.9)
+    g = torch.Generator().manual_seed(77)
+    steps = []
+    for it in range(2):
+        ip = torch.randn(2, 3, 224, 224, generator=g)
+        labelVar = torch.randint(1, 101, (2,), generator=g)
+        model_r.train()
+        torch.manual_seed(1000 + it)
+        ns3 = {"self": shim, "ip": ip, "labelVar": labelVar}
+        exec(body, ns3)
+        torch.manual_seed(1000 + it)
+        masks = ts.draw_dropout_masks([(2, 4096), (2, 4096), (2, ref_params.VIDEO_DESCRIPTOR_DIM)])
+        loss_o, fv_o, op_o = ts.train_step(model_o, opt_o, torch.nn.CrossEntropyLoss(), ip, labelVar, masks)
+        assert torch.equal(ns3["loss"].detach(), loss_o), (it, float(ns3["loss"]), float(loss_o))
+        assert torch.equal(ns3["featureVectors"].detach(), fv_o)
+        for pr, po in zip(model_r.parameters(), model_o.parameters()):
+            assert torch.equal(pr, po)
+        steps.append(dict(loss=float(loss_o), fv_abs_mean=float(fv_o.abs().mean()), logits_abs_max=float(op_o.abs().max()),
+                          w0_abs_mean=float(model_o.features[0].weight.abs().mean()),
+                          w_last_abs_mean=float(model_o.classifier[9].weight.abs().mean())))
+    json.dump({"model_seed": 5, "input_seed": 77, "mask_seed_base": 1000, "lr": 0.1, "momentum": 0.9, "batch": 2,
+               "reference_lines": [first + 1, last + 1], "steps": steps},
+              open(os.path.join(GOLD, "train_step.json"), "w"), indent=1)
+    report["train_step_vs_reference_loop_body"] = [st["loss"] for st in steps]
 
     # ---- (g) oracle forward vectors (restated model; pins the oracle to itself across machines)
     lay = make_layout(2)

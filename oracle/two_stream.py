@@ -246,6 +246,42 @@ def forward_eval(model, ip: torch.Tensor):
     return featureVectors, op, pred
 
 
+# ----------------------------------------------------------------------------------------------- N5 training step
+def draw_dropout_masks(shapes, p=0.5):
+    """The keep-masks nn.Dropout(p) draws in train mode on CPU, in call order: torch's dropout is
+    input.new_empty(shape).bernoulli_(1 - p) (then .div_(1 - p) and a multiply).  Drawing them here with the same global
+    RNG state gives the masks the reference's classifier would use -- tests/test_oracle_golden.py pins that."""
+    return [torch.empty(s).bernoulli_(1 - p) for s in shapes]
+
+
+def train_step(model, optimizer, criterion, ip: torch.Tensor, labels: torch.Tensor, dropout_masks):
+    """Body of the train() loop (spatialModel.py:171-181 == temporalModel.py same lines) for one batch, with the three
+    Dropout keep-masks supplied by the caller instead of drawn inside nn.Dropout (same arithmetic:
+    x * mask / (1 - p)).  Returns (loss, featureVectors, logits); `optimizer` has stepped."""
+    model.train()                                                           # :165
+    classifierList = list(model.classifier)
+    classifierLen = len(classifierList)
+    masks = iter(dropout_masks)
+
+    def run(cl, op):
+        if isinstance(cl, nn.Dropout):
+            return op * next(masks).to(op.dtype) / (1.0 - cl.p)
+        return cl(op)
+
+    op = model.features(ip)                                                 # :171
+    op = op.view(op.size(0), -1)                                            # :172
+    for cl in classifierList[:(classifierLen - 1)]:                         # :173-174
+        op = run(cl, op)
+    featureVectors = op                                                     # :175
+    for cl in classifierList[(classifierLen - 1):]:                         # :176-177
+        op = run(cl, op)
+    loss = criterion(op, labels)                                            # :178
+    optimizer.zero_grad()                                                   # :179
+    loss.backward()                                                         # :180
+    optimizer.step()                                                        # :181
+    return loss.detach(), featureVectors.detach(), op.detach()
+
+
 # ----------------------------------------------------------------------------------------------- C1 consensus
 def update_video_dict(videoDict: dict, videoNames, labels, featureVectors):
     """spatialModel.py:223-228."""

@@ -119,8 +119,6 @@ def test_network_validate_vs_oracle(setup):
     # second epoch accumulates (dicts never reset, reference Appendix A.5)
     net.validate()
     assert net.testDict[next(iter(odict))][0].count == 2
-    with pytest.raises(NotImplementedError):
-        net.train()
     # CSV dump + checkpoint round trip
     csv_path = s["tmp"] / "spatial_test.csv"
     U.saveVideoDescriptors(net.testDict, str(csv_path), True)

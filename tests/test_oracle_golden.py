@@ -148,3 +148,22 @@ def test_temporal_conv1_init_property():
     a = model.features[0](x)
     b = torch.nn.functional.conv2d(x.sum(1, keepdim=True), w[:, :1], model.features[0].bias, padding=1)
     assert torch.allclose(a, b, atol=1e-4)
+
+
+def test_train_step_vs_golden(golden):
+    """N5: the oracle's train_step reproduces the losses/weights recorded when make_golden.py ran it next to the
+    reference's own loop-body lines (bit-equal there); across machines CPU conv kernels may differ in the last bits."""
+    gold = golden("train_step.json")
+    model = ts.build_spatial_model(seed=gold["model_seed"])
+    opt = torch.optim.SGD(model.parameters(), gold["lr"], momentum=gold["momentum"])
+    g = torch.Generator().manual_seed(gold["input_seed"])
+    for it, st in enumerate(gold["steps"]):
+        ip = torch.randn(gold["batch"], 3, 224, 224, generator=g)
+        labels = torch.randint(1, 101, (gold["batch"],), generator=g)
+        torch.manual_seed(gold["mask_seed_base"] + it)
+        masks = ts.draw_dropout_masks([(gold["batch"], 4096), (gold["batch"], 4096), (gold["batch"], 256)])
+        loss, fv, op = ts.train_step(model, opt, torch.nn.CrossEntropyLoss(), ip, labels, masks)
+        assert abs(float(loss) - st["loss"]) < 1e-4 * abs(st["loss"]), (it, float(loss), st["loss"])
+        assert abs(float(fv.abs().mean()) - st["fv_abs_mean"]) < 1e-3 * st["fv_abs_mean"]
+        assert abs(float(model.features[0].weight.abs().mean()) - st["w0_abs_mean"]) < 1e-4 * st["w0_abs_mean"]
+        assert abs(float(model.classifier[9].weight.abs().mean()) - st["w_last_abs_mean"]) < 1e-4 * st["w_last_abs_mean"]

@@ -394,6 +394,7 @@ va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W,
 va_status va_bias_grad(const void* dZ, long long rows, int C, float* db, va_stream_t stream) {
   if (!dZ || !db) return fail(VA_ERR_INVALID, "va_bias_grad: NULL argument");
   if (va_status s = require_sm100()) return s;
+  VA_CUDA(cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), static_cast<cudaStream_t>(stream)));
   VA_CUDA(va::launch_bias_grad(dZ, db, rows, C, static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }

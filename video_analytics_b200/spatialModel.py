@@ -158,9 +158,34 @@ class _StreamNetwork(object):
             x = self.net.pack_input(ip)
         return self.net.forward(x)
 
+    def _get_trainer(self):
+        if getattr(self, "_trainer", None) is None:
+            from .training import StreamTrainer
+            group = None
+            if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                    torch.distributed.get_world_size() > 1:
+                group = torch.distributed.group.WORLD
+            self._trainer = StreamTrainer(self.model.module, self.optimizer, c_pad=self.net.c_pad, process_group=group)
+        return self._trainer
+
     def train(self):
-        raise NotImplementedError("the training step (backward + SGD, SURVEY.md section 8 row K5) is not built in this "
-                                  "round; there is no fallback to torch autograd")
+        """reference :161-194 -- one epoch of SGD-momentum steps on the K5 kernels (training.py); there is no torch
+        autograd on this path.  The reference's clip_grad_norm_ after the loop (:190) acts on the gradients of the last
+        batch AFTER their step was applied and before the next zero_grad(): it cannot change a parameter and is not
+        reproduced."""
+        if self.net.precision != "bf16":
+            raise VAError("training runs in the bf16 mode only")
+        self.model.train()
+        startTime = time.time()
+        trainer = self._get_trainer()
+        for iBatch, (data, labels, videoNames) in enumerate(self.trainLoader):
+            x = data.nhwc if isinstance(data, SnippetBatch) else self.net.pack_input(data)
+            loss, featureVectors, op = trainer.step(x, labels)
+            self.trainDict.update_batch(videoNames, labels, featureVectors)
+        self.sync_weights()                                                # evaluation handle <- updated parameters
+        duration = time.time() - startTime
+        print("Epoch %d completed in %lf seconds" % (self.epoch, duration))
+        self.save()
 
     def validate(self):
         """reference :197-231 -- eval-mode pass over the test loader; returns (precision, summed CE loss)."""
@@ -189,6 +214,8 @@ class _StreamNetwork(object):
         self.model.load_state_dict(checkpoint["model"])
         self.optimizer.load_state_dict(checkpoint["optimizer"])
         self.scheduler = slr.MultiStepLR(self.optimizer, self.lrMilestones, gamma=0.1, last_epoch=self.startEpoch)
+        if getattr(self, "_trainer", None) is not None:
+            self._trainer._adopt_optimizer_state()
         self.sync_weights()
         print("Loaded checkpoint: starting from epoch: %d" % (self.startEpoch))
         return True
@@ -200,7 +227,7 @@ class _StreamNetwork(object):
                        self.ckpLoc + self._best_file)
 
     def execute(self, evalOnly=False):
-        """reference :265-283.  With evalOnly=True the (unbuilt) training step is skipped and each epoch is one
+        """reference :265-283.  With evalOnly=True the training step is skipped and each epoch is one
         validation pass -- that is the reference's descriptor-accumulation loop (25 epochs = 25 random snippets)."""
         self.resume()
         for self.epoch in range(self.startEpoch, self.nEpochs):

@@ -36,13 +36,21 @@ def relu_pool_bwd(dout: torch.Tensor, y: torch.Tensor, *, pooled: bool) -> torch
     return dz
 
 
-def bias_grad(dz: torch.Tensor) -> torch.Tensor:
-    """db[c] = sum over all leading dims of dz[..., c]  (fp32)."""
+def _out(out, shape, device):
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == int(torch.Size(shape).numel()), \
+        (tuple(out.shape), tuple(shape))
+    return out
+
+
+def bias_grad(dz: torch.Tensor, out=None) -> torch.Tensor:
+    """db[c] = sum over all leading dims of dz[..., c]  (fp32; `out` is overwritten)."""
     _need_cuda(dz)
     assert dz.dtype == torch.bfloat16
     Cc = dz.shape[-1]
     rows = dz.numel() // Cc
-    db = torch.zeros((Cc,), dtype=torch.float32, device=dz.device)
+    db = _out(out, (Cc,), dz.device)
     check(_lib.load().va_bias_grad(ptr(dz), rows, Cc, ptr(db), stream_ptr()), "va_bias_grad")
     return db
 
@@ -82,29 +90,29 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return dx
 
 
-def conv2d_wgrad(dz: torch.Tensor, x: torch.Tensor, cin: int, ks: int = 3) -> torch.Tensor:
+def conv2d_wgrad(dz: torch.Tensor, x: torch.Tensor, cin: int, ks: int = 3, out=None) -> torch.Tensor:
     """dW fp32 OIHW [cout,cin,ks,ks] from dz bf16 [n,H,W,cout] and the layer input x bf16 [n,H,W,cin_pad>=cin]."""
     _need_cuda(dz, x)
     assert dz.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
     n, H, W, cout = dz.shape
     assert tuple(x.shape[:3]) == (n, H, W)
-    dw = torch.empty((cout, cin, ks, ks), dtype=torch.float32, device=dz.device)
+    dw = _out(out, (cout, cin, ks, ks), dz.device)
     check(_lib.load().va_wgrad(ptr(dz), ptr(x), n, H, W, cout, cin, x.shape[3], ks, ptr(dw), stream_ptr()), "va_wgrad")
     return dw
 
 
-def linear_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out=None) -> torch.Tensor:
     """dW = dY^T . X fp32 [out,in] from dy bf16 [n,out], x bf16 [n,in]  (the batch is the GEMM's K dimension)."""
     _need_cuda(dy, x)
     assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
     n, fout = dy.shape
     fin = x.shape[1]
-    dw = torch.empty((fout, fin), dtype=torch.float32, device=dy.device)
+    dw = _out(out, (fout, fin), dy.device)
     check(_lib.load().va_wgrad(ptr(dy), ptr(x), 1, 1, n, fout, fin, fin, 1, ptr(dw), stream_ptr()), "va_wgrad")
     return dw
 
 
-def ce_train(x: torch.Tensor, w4: torch.Tensor, b4: torch.Tensor, labels: torch.Tensor):
+def ce_train(x: torch.Tensor, w4: torch.Tensor, b4: torch.Tensor, labels: torch.Tensor, dw4=None, db4=None):
     """fp32 logit layer + mean cross-entropy, forward and backward in one call.
     x fp32 [n,D] (descriptors after dropout), w4 [C,D], b4 [C], labels int64 [n].
     Returns dict(logits, loss (1-element tensor), dlogits, dw4, db4, dx)."""
@@ -116,8 +124,7 @@ def ce_train(x: torch.Tensor, w4: torch.Tensor, b4: torch.Tensor, labels: torch.
     out = dict(logits=torch.empty((n, Cc), dtype=torch.float32, device=dev),
                dlogits=torch.empty((n, Cc), dtype=torch.float32, device=dev),
                loss=torch.zeros((1,), dtype=torch.float32, device=dev),
-               dw4=torch.empty((Cc, D), dtype=torch.float32, device=dev),
-               db4=torch.empty((Cc,), dtype=torch.float32, device=dev),
+               dw4=_out(dw4, (Cc, D), dev), db4=_out(db4, (Cc,), dev),
                dx=torch.empty((n, D), dtype=torch.float32, device=dev))
     check(_lib.load().va_ce_train(ptr(x), ptr(w4), ptr(b4), ptr(labels), n, D, Cc, ptr(out["logits"]), ptr(out["dlogits"]),
                                   ptr(out["loss"]), ptr(out["dw4"]), ptr(out["db4"]), ptr(out["dx"]), stream_ptr()),

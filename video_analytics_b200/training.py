@@ -1,0 +1,197 @@
+"""K5: one SGD-momentum training step of a VGG16 stream on hand-written sm_100a kernels.
+
+Replaces the body of the reference's train() loop (Sheet03/spatialModel.py:171-181 / temporalModel.py same lines):
+
+    op = features(ip); op = classifier[:-1](op)  [train mode: Dropout(0.5) after FC1..FC3];  featureVectors = op
+    op = classifier[-1](op); loss = CrossEntropyLoss(op, labels); zero_grad(); loss.backward(); optimizer.step()
+
+Layout of the step on the device:
+  * parameters, gradients and momentum buffers live in three flat fp32 arenas (one slice per state_dict tensor, in
+    state_dict order); the torch module's parameters and torch.optim.SGD's momentum buffers are re-pointed at views of
+    the arenas, so `model.state_dict()` / `optimizer.state_dict()` -- the reference's checkpoint format -- stay valid;
+  * forward: the evaluation path's tcgen05 layer kernel (bf16 operands, fp32 accumulate) with the 2x2 max-pool run as
+    its own kernel so that the un-pooled activation is kept for the backward pass; Dropout masks are uint8 tensors
+    (drawn by torch's generator, or supplied by the caller so the oracle can share them);
+  * backward: ReLU/pool routing kernel -> weight-gradient GEMM (tcgen05, split-K fp32 atomics) + bias-gradient
+    reduction -> data-gradient through the layer kernel with rotated/transposed filters; gradients between layers bf16;
+  * multi-GPU: ONE NCCL all-reduce (sum) over the gradient arena, its 1/world scale folded into the update kernel;
+  * update: ONE fused SGD-momentum launch over the whole arena.
+
+There is no torch autograd and no torch compute op on this path; torch owns memory, streams and the process group.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from . import train_ops as T
+from ._lib import VAError
+from .ops import STATE_DICT_KEYS
+
+# torchvision vgg16 "D": conv index -> is it followed by MaxPool2d(2,2)
+POOL_AFTER = (False, True, False, True, False, False, True, False, False, True, False, False, True)
+DROPOUT_P = 0.5          # nn.Dropout() default, reference spatialModel.py:143-150
+
+
+class StreamTrainer:
+    """Owns the flat parameter / gradient / momentum arenas of one stream and runs training steps on them."""
+
+    def __init__(self, module: torch.nn.Module, optimizer: Optional[torch.optim.SGD] = None, *, lr: float = 0.1,
+                 momentum: float = 0.9, c_pad: int = 16, process_group=None):
+        """module: the (unwrapped) torchvision-layout VGG16 with the swapped classifier (parameter container only).
+        optimizer: the torch.optim.SGD over module.parameters(); its lr / momentum are read at every step (so a
+        MultiStepLR scheduler keeps working) and its momentum buffers are re-pointed at the arena."""
+        if not torch.cuda.is_available():
+            raise VAError("training runs on a B200 only (no CPU fallback)")
+        self.module = module.cuda()
+        self.optimizer = optimizer
+        self._lr, self._momentum = lr, momentum
+        self.c_pad = c_pad
+        self.group = process_group
+        sd = dict(self.module.named_parameters())
+        missing = [k for k in STATE_DICT_KEYS if k not in sd]
+        if missing:
+            raise VAError(f"module is missing parameters {missing[:3]}...")
+        self.params: List[torch.nn.Parameter] = [sd[k] for k in STATE_DICT_KEYS]
+        sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + ((s + 63) // 64) * 64)      # 256-byte aligned slices
+        total = self.offsets[-1]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads: List[torch.Tensor] = []
+        self.bufs: List[torch.Tensor] = []
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat_param[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data.to(dev, torch.float32))                              # one-time arena fill
+            p.data = view
+            self.grads.append(self.flat_grad[off:off + p.numel()].view(p.shape))
+            self.bufs.append(self.flat_buf[off:off + p.numel()].view(p.shape))
+        self.steps_done = 0
+        self._adopt_optimizer_state()
+
+    # ---- optimizer state <-> arena (checkpoint compatibility, reference :240-246,255-260)
+    def _adopt_optimizer_state(self):
+        """If the optimizer already carries momentum buffers (resume()), copy them into the arena and re-point."""
+        if self.optimizer is None:
+            return
+        have = 0
+        for p, buf in zip(self.params, self.bufs):
+            st = self.optimizer.state.get(p, {})
+            mb = st.get("momentum_buffer")
+            if mb is not None:
+                buf.copy_(mb.to(buf.device, torch.float32))
+                st["momentum_buffer"] = buf
+                have += 1
+        if have not in (0, len(self.params)):
+            raise VAError("optimizer state holds momentum buffers for only some parameters")
+        self.steps_done = 1 if have else 0
+
+    def _publish_optimizer_state(self):
+        if self.optimizer is None:
+            return
+        for p, buf in zip(self.params, self.bufs):
+            self.optimizer.state[p]["momentum_buffer"] = buf
+
+    def hyper(self):
+        if self.optimizer is not None:
+            g = self.optimizer.param_groups[0]
+            return float(g["lr"]), float(g["momentum"])
+        return self._lr, self._momentum
+
+    def param(self, key: str) -> torch.Tensor:
+        return self.params[STATE_DICT_KEYS.index(key)].data
+
+    def grad(self, key: str) -> torch.Tensor:
+        return self.grads[STATE_DICT_KEYS.index(key)]
+
+    # ---- masks
+    @staticmethod
+    def draw_masks(n: int, desc_dim: int, generator: Optional[torch.Generator] = None, device="cuda"):
+        """Keep-masks (1 = keep) of the three Dropout layers, Bernoulli(1 - p)."""
+        shapes = [(n, 4096), (n, 4096), (n, desc_dim)]
+        return [(torch.rand(s, generator=generator, device=generator.device if generator is not None else device)
+                 >= DROPOUT_P).to(torch.uint8).to(device) for s in shapes]
+
+    # ---- the step
+    def forward_backward(self, x_nhwc: torch.Tensor, labels: torch.Tensor, masks: Optional[Sequence[torch.Tensor]] = None,
+                         keep: Optional[dict] = None):
+        """Fills the gradient arena; returns (loss [1] fp32 tensor, featureVectors [n,D] fp32, logits [n,C] fp32).
+        keep: optional dict that receives the saved forward activations (tests check the backward chain against a
+        reference backward taken over exactly these activations)."""
+        assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.dim() == 4 and x_nhwc.shape[3] == self.c_pad, x_nhwc.shape
+        n = x_nhwc.shape[0]
+        W = [p.data for p in self.params]
+        G = self.grads
+        desc_dim = W[30].shape[0]
+        if masks is None:
+            masks = self.draw_masks(n, desc_dim)
+        labels = labels.to(device=x_nhwc.device, dtype=torch.int64).contiguous()
+
+        # ---------------- forward (train mode), activations kept
+        saved = []                                   # per conv: (input, un-pooled post-ReLU output)
+        x = x_nhwc
+        for i in range(13):
+            y = ops.conv2d_nhwc(x, W[2 * i], W[2 * i + 1], relu=True, pool=False)
+            saved.append((x, y))
+            x = T.maxpool2x2(y) if POOL_AFTER[i] else y
+        hw, ch = x.shape[1] * x.shape[2], x.shape[3]
+        flat = T.transpose_bf16(x.view(n, hw, ch)).view(n, ch * hw)          # the reference's NCHW flatten order
+        h1 = ops.linear(flat, W[26], W[27], relu=True)
+        d1 = T.dropout(h1, masks[0], DROPOUT_P)
+        h2 = ops.linear(d1, W[28], W[29], relu=True)
+        d2 = T.dropout(h2, masks[1], DROPOUT_P)
+        h3 = ops.linear(d2, W[30], W[31], relu=True, out_f32=True)           # descriptor layer: fp32 out
+        d3 = T.dropout(h3, masks[2], DROPOUT_P)                              # featureVectors (reference :176)
+        ce = T.ce_train(d3, W[32], W[33], labels, dw4=G[32], db4=G[33])
+        if keep is not None:
+            keep.update(conv=list(saved), flat=flat, h=[h1, h2, h3], d=[d1, d2, d3], dlogits=ce["dlogits"])
+
+        # ---------------- backward
+        g = T.dropout(ce["dx"], masks[2], DROPOUT_P)
+        dz = T.relu_bwd_f32_to_bf16(g, h3)
+        T.linear_wgrad(dz, d2, out=G[30]); T.bias_grad(dz, out=G[31])
+        g = T.dropout(T.linear_dgrad(dz, W[30]), masks[1], DROPOUT_P)
+        dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h2.view(n, 1, 1, -1), pooled=False).view(n, -1)
+        T.linear_wgrad(dz, d1, out=G[28]); T.bias_grad(dz, out=G[29])
+        g = T.dropout(T.linear_dgrad(dz, W[28]), masks[0], DROPOUT_P)
+        dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h1.view(n, 1, 1, -1), pooled=False).view(n, -1)
+        T.linear_wgrad(dz, flat, out=G[26]); T.bias_grad(dz, out=G[27])
+        g = T.linear_dgrad(dz, W[26])                                        # [n, ch*hw] in NCHW flatten order
+        g = T.transpose_bf16(g.view(n, ch, hw)).view(n, x.shape[1], x.shape[2], ch)
+        for i in range(12, -1, -1):
+            xin, y = saved[i]
+            dz = T.relu_pool_bwd(g, y, pooled=POOL_AFTER[i])
+            cin = W[2 * i].shape[1]
+            T.conv2d_wgrad(dz, xin, cin, out=G[2 * i]); T.bias_grad(dz, out=G[2 * i + 1])
+            if i > 0:
+                g = T.conv2d_dgrad(dz, W[2 * i])
+            saved[i] = None
+        return ce["loss"], d3, ce["logits"]
+
+    def apply_update(self):
+        """Gradient all-reduce (when a process group is given) + the fused SGD-momentum update over the arena."""
+        scale = 1.0
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            scale = 1.0 / dist.get_world_size(self.group)
+        lr, momentum = self.hyper()
+        T.sgd_momentum_(self.flat_param, self.flat_grad, self.flat_buf, lr=lr, momentum=momentum,
+                        first_step=(self.steps_done == 0), grad_scale=scale)
+        if self.steps_done == 0:
+            self._publish_optimizer_state()
+        self.steps_done += 1
+
+    def step(self, x_nhwc: torch.Tensor, labels: torch.Tensor, masks=None):
+        loss, feat, logits = self.forward_backward(x_nhwc, labels, masks)
+        self.apply_update()
+        return loss, feat, logits
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: p.data for k, p in zip(STATE_DICT_KEYS, self.params)}
