@@ -169,7 +169,18 @@ def main():
     ap.add_argument("--max-batch", type=int, default=125, help="snippets per internal network chunk")
     ap.add_argument("--ref-snippets", type=int, default=10, help="snippets per stream per CPU-reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="eval", choices=["eval", "train"],
+                    help="eval: the headline two-stream evaluation (BASELINE configs[2]/[3]); train: the training step "
+                         "(configs[4], bench_train.py)")
+    ap.add_argument("--batch", type=int, default=64, help="--workload train: snippets per stream per GPU per step")
+    ap.add_argument("--lr", type=float, default=0.001, help="--workload train: SGD learning rate")
     args = ap.parse_args()
+    if args.workload == "train":
+        import bench_train
+        if args.steps == 20:
+            args.steps = 8
+        bench_train.main(args)
+        return
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)

@@ -92,6 +92,17 @@ static va_status require_sm100() {
   int major = 0;
   VA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return fail(VA_ERR_UNSUPPORTED, "libva_b200 is built for sm_100a only; device has cc %d.x", major);
+  // Stream-ordered scratch (cudaMallocAsync in the training primitives) must stay cached across synchronisation
+  // points: the default pool releases everything on every sync, which turns each step into GBs of re-allocation.
+  static bool pool_set[64] = {false};
+  if (dev < 64 && !pool_set[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_set[dev] = true;
+  }
   return VA_OK;
 }
 
