@@ -183,3 +183,18 @@ def test_network_train_epoch(tmp_path):
     assert float(l1) != float(l0)
     assert net.resume()                                                  # optimizer state re-adopted into the arena
     net.train()
+
+
+def test_data_parallel_gradients_two_gpus():
+    """N>1: split batch + NCCL all-reduce of the gradient arena == single-GPU gradient of the whole batch; parameters
+    identical on all ranks after the update (tools/check_train_ddp.py under torchrun)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_train_ddp.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert "DDP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

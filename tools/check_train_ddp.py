@@ -1,0 +1,55 @@
+"""Data-parallel training check (run under torchrun, 2+ ranks): the all-reduced, 1/world-scaled gradient arena of a
+batch split across ranks equals the single-GPU gradient of the whole batch, and parameters stay identical on all ranks
+after the update.  Prints one line 'DDP_OK ...' on rank 0."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from video_analytics_b200.distributed import init_from_env  # noqa: E402
+from video_analytics_b200.spatialModel import build_spatial_torch_model  # noqa: E402
+from video_analytics_b200.training import StreamTrainer  # noqa: E402
+
+
+def main():
+    rank, world, local = init_from_env()
+    torch.cuda.set_device(local)
+    per = 2
+    n = per * world
+    g = torch.Generator().manual_seed(11)
+    x_all = torch.randn(n, 224, 224, 16, generator=g).bfloat16()
+    x_all[..., 3:] = 0
+    labels_all = torch.randint(1, 101, (n,), generator=g)
+    masks_all = [(torch.rand(n, d, generator=g) >= 0.5).to(torch.uint8) for d in (4096, 4096, 256)]
+    sl = slice(rank * per, (rank + 1) * per)
+    tr = StreamTrainer(build_spatial_torch_model(101, 256, seed=0), None, lr=0.01, momentum=0.9, c_pad=16,
+                       process_group=dist.group.WORLD)
+    loss, _, _ = tr.forward_backward(x_all[sl].cuda(), labels_all[sl].cuda(), [m[sl].contiguous().cuda() for m in masks_all])
+    dist.all_reduce(tr.flat_grad, op=dist.ReduceOp.SUM)
+    avg = tr.flat_grad / world
+    loss_avg = loss.clone()
+    dist.all_reduce(loss_avg)
+    loss_avg /= world
+    ok = True
+    if rank == 0:
+        ref = StreamTrainer(build_spatial_torch_model(101, 256, seed=0), None, lr=0.01, momentum=0.9, c_pad=16)
+        loss_ref, _, _ = ref.forward_backward(x_all.cuda(), labels_all.cuda(), [m.cuda() for m in masks_all])
+        rel = float((avg - ref.flat_grad).norm() / ref.flat_grad.norm())
+        dl = abs(float(loss_avg) - float(loss_ref))
+        ok = rel < 1e-4 and dl < 1e-5
+        print(f"grad rel diff {rel:.3e}, loss diff {dl:.3e}")
+    # the real update path: step on every rank, then compare parameters across ranks
+    tr.step(x_all[sl].cuda(), labels_all[sl].cuda(), [m[sl].contiguous().cuda() for m in masks_all])
+    mine = tr.flat_param.clone()
+    dist.broadcast(mine, src=0)
+    same = bool(torch.equal(mine, tr.flat_param))
+    flag = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(("DDP_OK" if ok and int(flag) == 1 else "DDP_FAIL"), f"world={world} params_identical={bool(int(flag))}")
+    dist.destroy_process_group()
+
+
+main()

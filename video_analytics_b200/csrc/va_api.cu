@@ -460,20 +460,13 @@ va_status va_wgrad(const void* dZ, const void* X, int n, int H, int W, int cout,
                    va_stream_t stream) {
   if (!dZ || !X || !dW) return fail(VA_ERR_INVALID, "va_wgrad: NULL argument");
   if (ks != 1 && ks != 3) return fail(VA_ERR_INVALID, "va_wgrad: ks must be 1 or 3");
-  if (cin_pad < cin || n <= 0 || (long long)n * H > 65535)
-    return fail(VA_ERR_INVALID, "va_wgrad: bad shape (n=%d H=%d cin=%d cin_pad=%d; n*H must be <= 65535)", n, H, cin, cin_pad);
+  if (cin_pad < cin || n <= 0) return fail(VA_ERR_INVALID, "va_wgrad: bad shape (n=%d cin=%d cin_pad=%d)", n, cin, cin_pad);
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int Wp = (W + 7) & ~7;
-  void *dzt = nullptr, *xt = nullptr; float* ws = nullptr;
-  VA_CUDA(cudaMallocAsync(&dzt, (size_t)n * cout * H * Wp * 2, st));
-  VA_CUDA(cudaMallocAsync(&xt, (size_t)ks * n * cin * H * Wp * 2, st));   // ks horizontally pre-shifted copies
-  VA_CUDA(cudaMallocAsync(&ws, (size_t)ks * ks * cout * cin * 4, st));
-  VA_CUDA(va::launch_nhwc_to_nchw_bf16(dZ, dzt, n, H, W, Wp, cout, cout, 1, st));
-  // X may carry zero-padded channels (first layer): only the first `cin` are transposed
-  VA_CUDA(va::launch_nhwc_to_nchw_bf16(X, xt, n, H, W, Wp, cin, cin_pad, ks, st));
-  const char* e = va::wgrad_run(dzt, xt, n, H, W, Wp, cout, cin, ks, ws, dW, st);
-  cudaFreeAsync(dzt, st); cudaFreeAsync(xt, st); cudaFreeAsync(ws, st);
+  float* ws = nullptr;                       // [tap][cout][cin] accumulation planes of the 3x3 case
+  if (ks != 1) VA_CUDA(cudaMallocAsync(&ws, (size_t)ks * ks * cout * cin * 4, st));
+  const char* e = va::wgrad_run(dZ, X, n, H, W, cout, cin, cin_pad, ks, ws, dW, st);
+  if (ws) cudaFreeAsync(ws, st);
   if (e) return fail(VA_ERR_CUDA, "va_wgrad: %s", e);
   return VA_OK;
 }

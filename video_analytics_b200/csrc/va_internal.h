@@ -49,8 +49,8 @@ cudaError_t launch_ce_train(const float* x, const float* w4, const float* b4, co
 cudaError_t launch_relu_bwd_f32_to_bf16(const float* dy, const float* y, void* dz, long long n, cudaStream_t st);
 cudaError_t launch_flip_transpose_conv_w(const float* w, float* out, int Cout, int Cin, int ks, cudaStream_t st);
 cudaError_t launch_pack_fc_w_t(const float* w, void* out, int n_out, int n_in, cudaStream_t st);
-const char* wgrad_run(const void* dz_nchw, const void* x_nchw, int n, int H, int W, int Wp, int Cout, int Cin, int ks,
-                      float* dwt_ws, float* dw_oihw, cudaStream_t st);
+const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Cout, int Cin, int cin_pad, int ks,
+                      float* dwt_ws, float* dw, cudaStream_t st);
 
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
 struct ConvLayerDesc {

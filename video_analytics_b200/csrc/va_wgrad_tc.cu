@@ -1,17 +1,21 @@
-// K5: weight-gradient GEMM of the conv / fully-connected layers on tcgen05.
+// K5: weight-gradient GEMM of the conv / fully-connected layers on tcgen05, straight from the NHWC tensors.
 //
 //   dW[tap = (r,s)][co][ci] = sum_{n,h,w} dZ[n, h, w, co] * X[n, h + r - pad, w + s - pad, ci]
 //
-// GEMM view: M = co (128-row tiles), N = ci (BN-wide tiles), K = pixels.  UMMA operands must be K-major in shared
-// memory, i.e. the PIXEL index has to be the contiguous one, so both operands are first transposed to NCHW bf16
-// (nhwc_to_nchw_bf16_kernel, rows padded to a 16-byte multiple): a K block is then CKP consecutive pixels of one image
-// row, fetched by ONE 4-D TMA box (w, h, channel, n) per operand.  The vertical tap offset r is the same box at row
-// h + r - pad with TMA zero fill outside the image (the forward kernel's halo trick); the horizontal offset s cannot be
-// a box shift (a TMA box must start 16-byte aligned; one pixel is 2 bytes), so X^T is stored ks times, copy s shifted
-// by s - pad pixels, and tap (r,s) reads copy s (image index s*n + img of the same tensor map).
-// Work unit = (tap, co tile, ci tile, K split); the fp32 TMEM accumulator of a unit is added to dW with
-// red.global.add.f32 (split-K).  Same warp-specialised pipeline as the forward kernel (TMA producer warp, MMA warp,
-// 4 epilogue warps, mbarrier full/empty rings, 2 TMEM accumulator stages).
+// GEMM view: M = co (128-row tiles), N = ci (BN-wide tiles), K = pixels.  In NHWC both operands have the CHANNEL
+// contiguous, i.e. they are "MN-major" UMMA operands (the K index -- the pixel -- is the strided one), which tcgen05
+// takes directly: instruction-descriptor bits a_major = b_major = 1 and the MN-major canonical shared-memory layout
+//     Swizzle<3,4,3> o ((8,n),(8,k)) : ((1,LBO),(8,SBO))      [units of 16 bytes, 128B swizzle]
+// = rows of 64 channels (128 B), one row per pixel, 8-pixel groups SBO = 1024 B apart, 64-channel blocks LBO apart.
+// That is exactly what a 4-D TMA box (64 channels, w_t, h_t, n_t) of the NHWC tensor writes, so a K block is a
+// 64-pixel patch fetched by one box per 64-channel block, and filter tap (r,s) is the SAME box of X shifted by
+// (s - pad, r - pad) pixels with TMA zero fill outside the image -- the forward kernel's halo trick, with no layout
+// pass and no padded rows.  (A first version transposed both tensors to NCHW to get K-major operands; the pixel shift
+// then fell on the contiguous dimension, where TMA cannot start a box at a 2-byte offset, and three pre-shifted copies
+// of X were needed.  The transposes alone cost more than the GEMM.)
+// Work unit = (tap, ci tile, co tile, K split), tap fastest so that the CTAs running together stream the same pixels;
+// the fp32 TMEM accumulator of a unit is added to dW with red.global.add.f32 (split-K).  Warp-specialised like the
+// forward kernel: TMA producer warp, MMA warp, 4 epilogue warps, mbarrier full/empty rings, 2 TMEM accumulator stages.
 // Reference being replaced: loss.backward() for Conv2d/Linear weights (Sheet03/spatialModel.py:180).
 #include "va_internal.h"
 #include "va_conv_tc.cuh"
@@ -22,16 +26,20 @@
 
 namespace va {
 
+constexpr int kWgradKP = 64;          // pixels per pipeline stage (K block)
+
 struct WgradParams {
-  int n, H, wchunks;
-  int ks, pad, Cout, Cin;
+  int n, H, W;
+  int w_t, h_t, n_t;          // pixel patch of a K block: w_t * h_t * n_t == kWgradKP
+  int tiles_w, tiles_h, tiles_n, pixel_tiles;
+  int ks, pad, Cout, Cin;     // Cin = real input channels (epilogue bound); the B tensor may carry padded channels
   int co_tiles, ci_tiles, taps;
-  int total_units, rows_total, rows_per_split;
+  int total_units, tiles_per_split;
   int num_stages;
+  int row_stride;             // elements between output rows (Cin)
+  int plain_store;            // one K split: every output element is written exactly once -> st.global, no memset
   float* dwt;                 // fp32 [taps][Cout][Cin], pre-zeroed
-  int skip;                   // diagnostics: bit0 no TMA, bit1 no MMA, bit2 no TMEM load, bit3 no atomics
-  int* dbg;                   // diagnostics (VA_WGRAD_DEBUG): soft watchdog records the stuck wait's tag instead of trapping
-  FastDiv div_taps, div_ci, div_co, div_h;
+  FastDiv div_taps, div_ci, div_co, div_tw, div_th;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -44,30 +52,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+// MN-major operand descriptor: rows of ROWB bytes (one pixel each) written by TMA with the matching swizzle; 8-row
+// groups are ROWB*8 apart (SBO), blocks of ROWB/2 channels are `lbo_bytes` apart (LBO).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "row bytes");
+  constexpr uint64_t layout = ROWB == 128 ? 2ull : (ROWB == 64 ? 4ull : 6ull);
+  constexpr uint64_t sbo = (ROWB * 8) >> 4;
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= sbo << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
+  return d;
+}
+// kind::f16, A = B = bf16, D = fp32, both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) { return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
+
 constexpr int kWgradThreads = 192;
 
-// mbarrier wait; with a debug buffer a wait that times out records (tag, block, parity) and lets every role run to
-// completion (results are garbage) so that the host can read which barrier stalled.
-__device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity, int tag, int* dbg) {
-  if (dbg == nullptr) { mbar_wait(bar, parity, tag); return; }
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (*reinterpret_cast<volatile int*>(dbg) != 0) return;
-    if (clock64() - t0 > 200000000ll) {
-      if (atomicCAS(dbg, 0, 1) == 0) { dbg[1] = tag; dbg[2] = (int)blockIdx.x; dbg[3] = (int)parity; dbg[4] = (int)threadIdx.x; }
-      return;
-    }
-  }
-}
-
-template <int BN, int CKP>
+// BN = N tile (input channels), CB = channels per B block = TMA box width (64, or the padded 16/32 of the first layer)
+template <int BN, int CB>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
-  constexpr int ROWB = CKP * 2;
-  constexpr uint32_t A_BYTES = 128 * ROWB, B_BYTES = BN * ROWB;
-  constexpr uint32_t A_ALLOC = (A_BYTES + 1023) & ~1023u, B_ALLOC = (B_BYTES + 1023) & ~1023u;
-  constexpr uint32_t STAGE = A_ALLOC + B_ALLOC;
+  static_assert(BN % CB == 0, "BN must be whole B blocks");
+  constexpr int NB = BN / CB;
+  constexpr int ROWB_B = CB * 2;
+  constexpr uint32_t A_BLOCK = kWgradKP * 128, B_BLOCK = kWgradKP * ROWB_B;      // 8 KB, 8/4/2 KB: all multiples of 1024
+  constexpr uint32_t A_BYTES = 2 * A_BLOCK, B_BYTES = NB * B_BLOCK;
+  constexpr uint32_t STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
@@ -93,7 +107,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // unit -> (split, co tile, ci tile, tap); tap fastest so that concurrently running CTAs stream the same rows
   auto decode = [&](int unit, int& tap, int& ci_t, int& co_t, int& split) {
     uint32_t q, t;
     p.div_taps.divmod((uint32_t)unit, q, t); tap = (int)t;
@@ -108,75 +121,59 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int tap, ci_t, co_t, split;
       decode(unit, tap, ci_t, co_t, split);
       const int s = tap / p.ks, r = tap - s * p.ks;        // tap' = s*ks + r (the forward kernel's order)
-      const int row0 = split * p.rows_per_split;
-      const int row1 = min(p.rows_total, row0 + p.rows_per_split);
-      for (int row = row0; row < row1; ++row) {
-        uint32_t img, h;
-        p.div_h.divmod((uint32_t)row, img, h);
-        const int hb = (int)h + r - p.pad;
-        if (hb < 0 || hb >= p.H) continue;                 // the shifted row is all padding: contributes nothing
-        for (int wc = 0; wc < p.wchunks; ++wc) {
-          wg_wait(&empty_bar[stage], phase ^ 1, 100 + stage, p.dbg);
-          if (elect_one()) {
-            uint8_t* a_dst = smem + (size_t)stage * STAGE;
-            if (p.skip & 1) {
-              mbar_arrive(&full_bar[stage]);
-            } else {
-              const int z = (p.skip & 64) ? 0 : 1;
-              mbar_arrive_expect_tx(&full_bar[stage], ((p.skip & 16) ? 0 : A_BYTES) + ((p.skip & 32) ? 0 : B_BYTES));
-              if (!(p.skip & 16)) tma_load_4d(a_dst, &tmA, &full_bar[stage], z * wc * CKP, z * (int)h, z * co_t * 128, z * (int)img);
-              if (!(p.skip & 32)) tma_load_4d(a_dst + A_ALLOC, &tmB, &full_bar[stage], z * wc * CKP, z * hb, z * ci_t * BN, z * (s * p.n + (int)img));
-            }
-          }
-          __syncwarp();
-          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+      const int pt0 = split * p.tiles_per_split;
+      const int pt1 = min(p.pixel_tiles, pt0 + p.tiles_per_split);
+      for (int pt = pt0; pt < pt1; ++pt) {
+        uint32_t q, tw, th, tn;
+        p.div_tw.divmod((uint32_t)pt, q, tw);
+        p.div_th.divmod(q, tn, th);
+        const int w0 = (int)tw * p.w_t, h0 = (int)th * p.h_t, n0 = (int)tn * p.n_t;
+        mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+        if (elect_one()) {
+          uint8_t* a_dst = smem + (size_t)stage * STAGE;
+          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], co_t * 128, w0, h0, n0);
+          tma_load_4d(a_dst + A_BLOCK, &tmA, &full_bar[stage], co_t * 128 + 64, w0, h0, n0);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            tma_load_4d(a_dst + A_BYTES + b * B_BLOCK, &tmB, &full_bar[stage], ci_t * BN + b * CB, w0 + s - p.pad,
+                        h0 + r - p.pad, n0);
         }
+        __syncwarp();
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    constexpr uint32_t idesc = make_idesc_bf16_mn(128, BN);
     const uint32_t smem_base_u32 = smem_u32(smem);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       int tap, ci_t, co_t, split;
       decode(unit, tap, ci_t, co_t, split);
-      const int s = tap / p.ks, r = tap - s * p.ks;
-      const int row0 = split * p.rows_per_split;
-      const int row1 = min(p.rows_total, row0 + p.rows_per_split);
-      wg_wait(&tempty_bar[as], as_phase ^ 1, 200 + as, p.dbg);
+      const int pt0 = split * p.tiles_per_split;
+      const int pt1 = min(p.pixel_tiles, pt0 + p.tiles_per_split);
+      mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + as * BN;
       uint32_t acc = 0;
-      for (int row = row0; row < row1; ++row) {
-        uint32_t img, h;
-        p.div_h.divmod((uint32_t)row, img, h);
-        const int hb = (int)h + r - p.pad;
-        if (hb < 0 || hb >= p.H) continue;
-        for (int wc = 0; wc < p.wchunks; ++wc) {
-          wg_wait(&full_bar[stage], phase, 300 + stage, p.dbg);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base_u32 + stage * STAGE;
-          const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
-          const uint64_t db0 = make_smem_desc<ROWB>(a_addr + A_ALLOC);
-          if (elect_one()) {
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&full_bar[stage], phase, 300 + stage);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base_u32 + stage * STAGE;
+        const uint64_t da0 = make_smem_desc_mn<128>(a_addr, A_BLOCK);
+        const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, B_BLOCK);
+        if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < CKP / 16; ++k)
-              if (!(p.skip & 2)) umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, k ? 1u : acc);
-            umma_commit(&empty_bar[stage]);
-          }
-          __syncwarp();
-          acc = 1;
-          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of B per step
+            umma_bf16(d_tmem, da0 + ((k * 16 * 128) >> 4), db0 + ((k * 16 * ROWB_B) >> 4), idesc, k ? 1u : acc);
+          umma_commit(&empty_bar[stage]);
         }
+        __syncwarp();
+        acc = 1;
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
       }
-      // a unit whose every row was skipped (cannot happen for H >= 2, kept for safety) would leave garbage: zero it
-      if (elect_one()) {
-        if (acc == 0) {
-          // no MMA was issued: signal the epilogue with an "empty" accumulator flag through the barrier anyway
-        }
-        umma_commit(&tfull_bar[as]);
-      }
+      if (elect_one()) umma_commit(&tfull_bar[as]);
       __syncwarp();
       as ^= 1;
       if (as == 0) as_phase ^= 1;
@@ -189,37 +186,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       int tap, ci_t, co_t, split;
       decode(unit, tap, ci_t, co_t, split);
-      const int row0 = split * p.rows_per_split;
-      const int row1 = min(p.rows_total, row0 + p.rows_per_split);
-      wg_wait(&tfull_bar[as], as_phase, 400 + as, p.dbg);
+      mbar_wait(&tfull_bar[as], as_phase, 400 + as);
       tc_fence_after();
       const int co = co_t * 128 + m;
-      float* dst = p.dwt + ((size_t)tap * p.Cout + co) * p.Cin + ci_t * BN;
-      // did this unit issue any MMA?  (same skip rule as above; H >= 2 always leaves at least one row)
-      bool any = false;
-      {
-        const int s = tap / p.ks, r = tap - s * p.ks;
-        for (int row = row0; row < row1 && !any; ++row) {
-          uint32_t img, h;
-          p.div_h.divmod((uint32_t)row, img, h);
-          const int hb = (int)h + r - p.pad;
-          any = (hb >= 0 && hb < p.H);
-        }
-      }
+      float* dst = p.dwt + ((size_t)tap * p.Cout + co) * p.row_stride + ci_t * BN;
 #pragma unroll 1
       for (int c16 = 0; c16 < BN / 16; ++c16) {
         uint32_t v[16];
-        if (!(p.skip & 4)) {
-          tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c16 * 16, v);
-          tmem_ld_wait();
-        } else {
-          for (int i = 0; i < 16; ++i) v[i] = 0;
-        }
-        if (any && co < p.Cout && !(p.skip & 8)) {
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c16 * 16, v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          if (p.plain_store) {
+            if (ci_t * BN + c16 * 16 + 16 <= p.Cin && (p.row_stride & 3) == 0) {
+              float4* d4 = reinterpret_cast<float4*>(dst + c16 * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int ci = ci_t * BN + c16 * 16 + i;
-            if (ci < p.Cin) atomicAdd(dst + c16 * 16 + i, __uint_as_float(v[i]));
+              for (int i = 0; i < 4; ++i)
+                d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                    __uint_as_float(v[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ci_t * BN + c16 * 16 + i < p.Cin) dst[c16 * 16 + i] = __uint_as_float(v[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int ci = ci_t * BN + c16 * 16 + i;
+              if (ci < p.Cin) atomicAdd(dst + c16 * 16 + i, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -235,14 +229,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// [taps][Cout][Cin] (tap' = s*ks + r) -> OIHW fp32 [Cout][Cin][ks][ks]
+// [taps][Cout][Cin] (tap' = s*ks + r) -> OIHW fp32 [Cout][Cin][ks][ks]; one thread per (co, ci): coalesced reads of each
+// tap plane, ks*ks consecutive floats written per thread.
 __global__ void wgrad_to_oihw_kernel(const float* __restrict__ dwt, float* __restrict__ dw, int Cout, int Cin, int ks) {
-  const size_t total = (size_t)Cout * Cin * ks * ks;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-    const int s = (int)(g % ks), r = (int)((g / ks) % ks);
-    const int ci = (int)((g / (ks * ks)) % Cin);
-    const int co = (int)(g / ((size_t)ks * ks * Cin));
-    dw[g] = dwt[((size_t)(s * ks + r) * Cout + co) * Cin + ci];
+  const size_t plane = (size_t)Cout * Cin;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < plane; g += (size_t)gridDim.x * blockDim.x) {
+    float* o = dw + g * ks * ks;
+    for (int r = 0; r < ks; ++r)
+      for (int s = 0; s < ks; ++s) o[r * ks + s] = __ldg(dwt + (size_t)(s * ks + r) * plane + g);
   }
 }
 
@@ -269,29 +263,40 @@ EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// NCHW bf16 [n][C][H][Wp] map with dims (Wp, H, C, n), box (ckp, 1, rows, 1)
-const char* encode_nchw(CUtensorMap* m, const void* addr, int n, int C, int H, int Wp, int ckp, int rows) {
+int sm_count_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+// NHWC bf16 [n][H][W][C] map with dims (C, W, H, n), box (cb, w_t, h_t, n_t), swizzle = cb*2 bytes
+const char* encode_nhwc(CUtensorMap* m, const void* addr, int n, int H, int W, int C, int cb, int w_t, int h_t, int n_t) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return "cuTensorMapEncodeTiled not available";
-  cuuint64_t gdim[4] = {(cuuint64_t)Wp, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)n};
-  cuuint64_t gstr[3] = {(cuuint64_t)Wp * 2, (cuuint64_t)Wp * H * 2, (cuuint64_t)Wp * H * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)ckp, 1u, (cuuint32_t)rows, 1u};
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * W * 2, (cuuint64_t)C * W * H * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)w_t, (cuuint32_t)h_t, (cuuint32_t)n_t};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  const CUtensorMapSwizzle sw = ckp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ckp == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw = cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(addr), gdim, gstr, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return werrf("wgrad tensor map encode failed (%d): n=%d C=%d H=%d Wp=%d ckp=%d rows=%d", (int)r, n, C, H, Wp, ckp, rows);
+  if (r != CUDA_SUCCESS)
+    return werrf("wgrad tensor map encode failed (%d): n=%d H=%d W=%d C=%d box=(%d,%d,%d,%d)", (int)r, n, H, W, C, cb, w_t, h_t, n_t);
   return nullptr;
 }
 
-template <int BN, int CKP>
+template <int BN, int CB>
 const char* launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, WgradParams p, int grid, cudaStream_t st) {
-  constexpr uint32_t A_ALLOC = (128 * CKP * 2 + 1023) & ~1023u, B_ALLOC = (BN * CKP * 2 + 1023) & ~1023u;
-  int stages = (int)((227 * 1024 - 1024 - 256) / (A_ALLOC + B_ALLOC));
+  constexpr uint32_t STAGE = 2 * kWgradKP * 128 + (BN / CB) * kWgradKP * CB * 2;
+  int stages = (int)((227 * 1024 - 1024 - 256) / STAGE);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
-  const size_t smem = 1024 + (size_t)stages * (A_ALLOC + B_ALLOC) + 256;
-  auto kfn = wgrad_tc_kernel<BN, CKP>;
+  const size_t smem = 1024 + (size_t)stages * STAGE + 256;
+  auto kfn = wgrad_tc_kernel<BN, CB>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -301,78 +306,69 @@ const char* launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, WgradPara
   count_launch();
   kfn<<<grid, kWgradThreads, smem, st>>>(tA, tB, p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return werrf("wgrad_tc_kernel<%d,%d> launch: %s", BN, CKP, cudaGetErrorString(e));
+  if (e != cudaSuccess) return werrf("wgrad_tc_kernel<%d,%d> launch: %s", BN, CB, cudaGetErrorString(e));
   return nullptr;
 }
 }  // namespace
 
-// dz_nchw: bf16 [n][Cout][H][Wp]; x_nchw: bf16 [ks][n][Cin][H][Wp] (copy s shifted by s - pad pixels); dwt_ws: fp32 [ks*ks][Cout][Cin] workspace;
-// dw_oihw: fp32 [Cout][Cin][ks][ks] result.
-const char* wgrad_run(const void* dz_nchw, const void* x_nchw, int n, int H, int W, int Wp, int Cout, int Cin, int ks,
-                      float* dwt_ws, float* dw_oihw, cudaStream_t st) {
+// dz: bf16 NHWC [n][H][W][Cout]; x: bf16 NHWC [n][H][W][cin_pad] (channels >= Cin are zero); dwt_ws: fp32
+// [ks*ks][Cout][Cin] workspace (unused for ks == 1: the accumulation target is dw itself); dw: fp32 [Cout][Cin][ks][ks].
+const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Cout, int Cin, int cin_pad, int ks,
+                      float* dwt_ws, float* dw, cudaStream_t st) {
   if (n <= 0) return nullptr;
-  const int ckp = W > 32 ? 64 : (W > 16 ? 32 : 16);
-  if (Wp % 8 != 0) return "wgrad: padded row length must be a multiple of 8 elements";
-  // N tile: the smallest supported width that covers Cin (16/32/64) or 128-wide tiles
-  int BN = Cin <= 16 ? 16 : (Cin <= 32 ? 32 : (Cin <= 64 ? 64 : 128));
+  if (Cout % 8 || cin_pad % 8) return "wgrad: channel counts must be multiples of 8 (16-byte NHWC rows)";
+  const int CB = cin_pad >= 64 ? 64 : (cin_pad >= 32 ? 32 : 16);
+  if (cin_pad < 16 || (cin_pad < 64 && cin_pad != CB)) return werrf("wgrad: unsupported padded input channel count %d", cin_pad);
+  const int BN = cin_pad >= 256 ? 256 : (cin_pad >= 128 ? 128 : CB);
   WgradParams p;
-  p.n = n; p.H = H; p.wchunks = (W + ckp - 1) / ckp;
-  p.ks = ks; p.pad = (ks - 1) / 2; p.Cout = Cout; p.Cin = Cin;
-  p.co_tiles = (Cout + 127) / 128; p.ci_tiles = (Cin + BN - 1) / BN; p.taps = ks * ks;
-  p.rows_total = n * H;
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  p.n = n; p.H = H; p.W = W;
+  // K block = 64-pixel patch w_t x h_t x n_t; w_t and h_t divide W and H so that no patch straddles an image edge
+  int w_t = 16;
+  while (w_t > 1 && W % w_t) w_t >>= 1;
+  int h_t = kWgradKP / w_t;
+  while (h_t > 1 && H % h_t) h_t >>= 1;
+  p.w_t = w_t; p.h_t = h_t; p.n_t = kWgradKP / (w_t * h_t);
+  p.tiles_w = W / w_t; p.tiles_h = H / h_t; p.tiles_n = (n + p.n_t - 1) / p.n_t;
+  p.pixel_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.ks = ks; p.pad = (ks - 1) / 2; p.Cout = Cout; p.Cin = Cin; p.row_stride = Cin;
+  p.co_tiles = (Cout + 127) / 128; p.ci_tiles = (cin_pad + BN - 1) / BN; p.taps = ks * ks;
+  const int sms = sm_count_cached();
   const int base_units = p.taps * p.co_tiles * p.ci_tiles;
   int ksplit = (2 * sms + base_units - 1) / base_units;        // aim at >= 2 units per SM
-  if (ksplit > p.rows_total) ksplit = p.rows_total;
+  if (ksplit > p.pixel_tiles) ksplit = p.pixel_tiles;
   if (ksplit < 1) ksplit = 1;
-  p.rows_per_split = (p.rows_total + ksplit - 1) / ksplit;
-  ksplit = (p.rows_total + p.rows_per_split - 1) / p.rows_per_split;
+  p.tiles_per_split = (p.pixel_tiles + ksplit - 1) / ksplit;
+  ksplit = (p.pixel_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.total_units = base_units * ksplit;
-  p.dwt = dwt_ws;
-  p.dbg = nullptr;
-  p.skip = getenv("VA_WGRAD_SKIP") ? atoi(getenv("VA_WGRAD_SKIP")) : 0;
-  static int* dbg_buf = nullptr;
-  const bool debug = getenv("VA_WGRAD_DEBUG") != nullptr;
-  if (debug) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 64);
-    cudaMemsetAsync(dbg_buf, 0, 64, st);
-    p.dbg = dbg_buf;
-  }
+  float* target = ks == 1 ? dw : dwt_ws;
+  p.dwt = target;
   p.div_taps = FastDiv::make((uint32_t)p.taps);
   p.div_ci = FastDiv::make((uint32_t)p.ci_tiles);
   p.div_co = FastDiv::make((uint32_t)p.co_tiles);
-  p.div_h = FastDiv::make((uint32_t)H);
-  cudaError_t ce = cudaMemsetAsync(dwt_ws, 0, (size_t)p.taps * Cout * Cin * sizeof(float), st);
+  p.div_tw = FastDiv::make((uint32_t)p.tiles_w);
+  p.div_th = FastDiv::make((uint32_t)p.tiles_h);
+  p.plain_store = ksplit == 1 ? 1 : 0;
+  cudaError_t ce = cudaSuccess;
+  if (!p.plain_store) ce = cudaMemsetAsync(target, 0, (size_t)p.taps * Cout * Cin * sizeof(float), st);
   if (ce != cudaSuccess) return werrf("wgrad memset: %s", cudaGetErrorString(ce));
   CUtensorMap tA, tB;
-  if (const char* e = encode_nchw(&tA, dz_nchw, n, Cout, H, Wp, ckp, 128)) return e;
-  if (const char* e = encode_nchw(&tB, x_nchw, ks * n, Cin, H, Wp, ckp, BN)) return e;
+  if (const char* e = encode_nhwc(&tA, dz, n, H, W, Cout, 64, p.w_t, p.h_t, p.n_t)) return e;
+  if (const char* e = encode_nhwc(&tB, x, n, H, W, cin_pad, CB, p.w_t, p.h_t, p.n_t)) return e;
   const int grid = p.total_units < sms ? p.total_units : sms;
   const char* err = nullptr;
-#define VA_W(bn, ck) if (BN == bn && ckp == ck) err = launch_wgrad<bn, ck>(tA, tB, p, grid, st); else
-  VA_W(16, 64) VA_W(32, 64) VA_W(64, 64) VA_W(128, 64) VA_W(64, 32) VA_W(128, 32) VA_W(64, 16) VA_W(128, 16)
-  VA_W(16, 32) VA_W(32, 32) VA_W(16, 16) VA_W(32, 16)
-  err = werrf("wgrad: no kernel for BN=%d CKP=%d", BN, ckp);
+#define VA_W(bn, cb) if (BN == bn && CB == cb) err = launch_wgrad<bn, cb>(tA, tB, p, grid, st); else
+  VA_W(256, 64) VA_W(128, 64) VA_W(64, 64) VA_W(32, 32) VA_W(16, 16)
+  err = werrf("wgrad: no kernel for BN=%d CB=%d", BN, CB);
 #undef VA_W
   if (err) return err;
-  if (debug) {
-    int h[8] = {0};
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[va wgrad debug] BN=%d ckp=%d units=%d rows/split=%d wchunks=%d grid=%d | stalled=%d tag=%d block=%d parity=%d thread=%d\n",
-            BN, ckp, p.total_units, p.rows_per_split, p.wchunks, grid, h[0], h[1], h[2], h[3], h[4]);
+  if (ks != 1) {
+    const size_t plane = (size_t)Cout * Cin;
+    unsigned blocks = (unsigned)std::min<size_t>((plane + 255) / 256, 148 * 8);
+    count_launch();
+    wgrad_to_oihw_kernel<<<blocks, 256, 0, st>>>(dwt_ws, dw, Cout, Cin, ks);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return werrf("wgrad_to_oihw: %s", cudaGetErrorString(ce));
   }
-  const size_t total = (size_t)Cout * Cin * ks * ks;
-  unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
-  count_launch();
-  wgrad_to_oihw_kernel<<<blocks, 256, 0, st>>>(dwt_ws, dw_oihw, Cout, Cin, ks);
-  ce = cudaGetLastError();
-  if (ce != cudaSuccess) return werrf("wgrad_to_oihw: %s", cudaGetErrorString(ce));
   return nullptr;
 }
 
