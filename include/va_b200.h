@@ -137,7 +137,8 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
  * (Dropout after FC1..FC3, :141-152).  Activations / activation gradients are bf16 NHWC, parameter gradients fp32
  * in the reference's own layouts (OIHW, [out][in]) so that they line up with the fp32 master parameters.
  *   va_maxpool2x2_nhwc   : MaxPool2d(2,2) forward (training keeps the un-pooled activation for the backward pass)
- *   va_relu_pool_bwd     : dZ = un-pool(dout) * (Y > 0); pooled=0: dout is already the gradient of Y
+ *   va_relu_pool_bwd     : dZ = un-pool(dout) * (Y > 0); pooled=0: dout is already the gradient of Y; with db != NULL
+ *                          the bias gradient db[c] = sum dZ[.., c] is produced by the same pass
  *   va_bias_grad         : db[c] = sum_rows dZ[row][c]
  *   va_dropout           : y = x * scale where mask (u8) != 0 else 0 (forward and backward are the same map)
  *   va_conv2d_dgrad      : dX = conv3x3(dZ, rot180(W) with channel roles swapped)  -- tcgen05 layer kernel
@@ -151,7 +152,7 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
  *                          e.g. 1/world_size after a gradient all-reduce)
  * --------------------------------------------------------------------------------------------------------- */
 va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, va_stream_t stream);
-va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ,
+va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ, float* db,
                            va_stream_t stream);
 va_status va_bias_grad(const void* dZ, long long rows, int C, float* db, va_stream_t stream);
 va_status va_dropout(const void* x, const uint8_t* mask, long long total, float scale, int is_f32, void* y,

@@ -40,6 +40,30 @@ def test_relu_pool_bwd_bit_exact(pooled):
     out.backward(dout)
     dz = T.relu_pool_bwd(_nhwc(dout), _nhwc(y.detach()), pooled=pooled)
     assert torch.equal(dz.float(), z.grad.permute(0, 2, 3, 1))
+    # fused bias gradient (8-channel path: C = 32 -> 4 channel groups) gives the same dz and the column sums
+    db = torch.empty(32, dtype=torch.float32, device="cuda")
+    dz2 = T.relu_pool_bwd(_nhwc(dout), _nhwc(y.detach()), pooled=pooled, bias_grad_out=db)
+    assert torch.equal(dz2, dz)
+    assert torch.allclose(db, z.grad.sum((0, 2, 3)), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(3, 14, 14, 512), (2, 28, 28, 192), (5, 1, 1, 4096)], ids=str)
+@pytest.mark.parametrize("pooled", [True, False])
+def test_relu_pool_bwd_fused_bias_shapes(shape, pooled):
+    """Fused path (C/8 divides 256), the two-pass fallback (C = 192) and the FC shape (C = 4096)."""
+    from video_analytics_b200 import train_ops as T
+    n, H, W, C = shape
+    if pooled and H == 1:
+        pytest.skip("no pooling on FC activations")
+    g = torch.Generator().manual_seed(12)
+    y = torch.relu(torch.randn(n, H, W, C, generator=g)).cuda().bfloat16()
+    dout = torch.randn((n, H // 2, W // 2, C) if pooled else (n, H, W, C), generator=g).cuda().bfloat16()
+    dz = T.relu_pool_bwd(dout, y, pooled=pooled)
+    db = torch.full((C,), 7.0, dtype=torch.float32, device="cuda")          # must be overwritten, not accumulated into
+    dz2 = T.relu_pool_bwd(dout, y, pooled=pooled, bias_grad_out=db)
+    assert torch.equal(dz, dz2)
+    ref = dz.float().sum((0, 1, 2))
+    assert torch.allclose(db, ref, rtol=1e-4, atol=1e-3 * float(ref.abs().max()))
 
 
 def test_bias_grad():

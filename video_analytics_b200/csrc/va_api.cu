@@ -394,18 +394,17 @@ va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y,
   VA_CUDA(va::launch_maxpool_fwd(x, y, n, H, W, C, static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }
-va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ,
+va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ, float* db,
                            va_stream_t stream) {
   if (!dout || !Y || !dZ) return fail(VA_ERR_INVALID, "va_relu_pool_bwd: NULL argument");
   if (C % 2 || (pooled && ((H | W) & 1))) return fail(VA_ERR_INVALID, "va_relu_pool_bwd: bad shape");
   if (va_status s = require_sm100()) return s;
-  VA_CUDA(va::launch_relu_pool_bwd(dout, Y, dZ, n, H, W, C, pooled, static_cast<cudaStream_t>(stream)));
+  VA_CUDA(va::launch_relu_pool_bwd(dout, Y, dZ, db, n, H, W, C, pooled, static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }
 va_status va_bias_grad(const void* dZ, long long rows, int C, float* db, va_stream_t stream) {
   if (!dZ || !db) return fail(VA_ERR_INVALID, "va_bias_grad: NULL argument");
   if (va_status s = require_sm100()) return s;
-  VA_CUDA(cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), static_cast<cudaStream_t>(stream)));
   VA_CUDA(va::launch_bias_grad(dZ, db, rows, C, static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }

@@ -36,7 +36,8 @@ cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad,
 
 // ---- training-step kernels (va_train_kernels.cu, va_wgrad_tc.cu)
 cudaError_t launch_maxpool_fwd(const void* x, void* y, int n, int H, int W, int C, cudaStream_t st);
-cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, int n, int H, int W, int C, int pooled, cudaStream_t st);
+cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, float* db, int n, int H, int W, int C, int pooled,
+                                 cudaStream_t st);
 cudaError_t launch_bias_grad(const void* dZ, float* db, long long rows, int C, cudaStream_t st);
 cudaError_t launch_dropout(const void* x, const uint8_t* mask, void* y, long long total, float scale, int is_f32, cudaStream_t st);
 cudaError_t launch_nhwc_to_nchw_bf16(const void* x, void* y, int n, int H, int W, int Wp, int C, int Cs, int nshift,

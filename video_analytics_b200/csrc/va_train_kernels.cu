@@ -74,6 +74,83 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const __nv_bfloat162* __r
   dZ[g] = __floats2bfloat162_rn(y.x > 0.f ? d.x : 0.f, y.y > 0.f ? d.y : 0.f);
 }
 
+// Fused variant for the conv stack: 8 channels (16 B) per thread, a thread keeps ONE channel group and strides over
+// windows / pixels, so the bias gradient db[c] = sum dZ[.., c] falls out of registers (block reduce + one atomic per
+// channel per block) instead of a second pass over dZ.  Needs C % 8 == 0 and (C / 8) dividing the block size.
+__device__ __forceinline__ void bf8_to_f(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+template <bool POOLED>
+__global__ void __launch_bounds__(256) relu_pool_bwd_bias_kernel(const uint4* __restrict__ dP, const uint4* __restrict__ Y,
+                                                                 uint4* __restrict__ dZ, float* __restrict__ db, int n, int H,
+                                                                 int W, int C8) {
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8, lanes = 256 / C8;
+  const int Ho = POOLED ? H >> 1 : H, Wo = POOLED ? W >> 1 : W;
+  const long long total = (long long)n * Ho * Wo;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (long long t = (long long)blockIdx.x * lanes + pl; t < total; t += (long long)gridDim.x * lanes) {
+    const uint4 gp4 = __ldg(dP + t * C8 + cg);
+    if (POOLED) {
+      const int wo = (int)(t % Wo);
+      const long long t2 = t / Wo;
+      const int ho = (int)(t2 % Ho), img = (int)(t2 / Ho);
+      const long long i00 = (((long long)img * H + 2 * ho) * W + 2 * wo) * C8 + cg;
+      const long long idx[4] = {i00, i00 + C8, i00 + (long long)W * C8, i00 + (long long)W * C8 + C8};
+      float gp[8], v[4][8];
+      bf8_to_f(gp4, gp);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bf8_to_f(__ldg(Y + idx[k]), v[k]);
+      uint32_t o[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[k][j] = 0u;
+      const uint16_t* g16 = reinterpret_cast<const uint16_t*>(&gp4);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        int a = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (v[k][c] > v[a][c]) a = k;
+        if (v[a][c] > 0.f) {
+          acc[c] += gp[c];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k == a) o[k][c >> 1] |= (uint32_t)g16[c] << ((c & 1) * 16);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dZ[idx[k]] = make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    } else {
+      float y[8], g[8];
+      bf8_to_f(__ldg(Y + t * C8 + cg), y);
+      bf8_to_f(gp4, g);
+      const uint16_t* g16 = reinterpret_cast<const uint16_t*>(&gp4);
+      uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (y[c] > 0.f) { acc[c] += g[c]; o[c >> 1] |= (uint32_t)g16[c] << ((c & 1) * 16); }
+      dZ[t * C8 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __shared__ float red[256 * 8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float sum = 0.f;
+      for (int l = 0; l < lanes; ++l) sum += red[(l * C8 + cg) * 8 + i];
+      atomicAdd(db + cg * 8 + i, sum);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ bias gradient
 // db[c] = sum over rows of dZ[row][c]; block = 64 channels x 4 row lanes, grid.y slices the rows; fp32 atomics.
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ dZ, float* __restrict__ db,
@@ -145,12 +222,30 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 __global__ void __launch_bounds__(256) sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                            float* __restrict__ buf, long long n, float lr, float momentum,
                                                            int first_step, float grad_scale) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float gi = g[i] * grad_scale;
-  const float b = first_step ? gi : fmaf(momentum, buf[i], gi);
-  buf[i] = b;
-  p[i] = fmaf(-lr, b, p[i]);
+  // four elements per thread (16-byte accesses: the arenas are 256-byte aligned); scalar tail
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 gv = *reinterpret_cast<const float4*>(g + i4);
+    float4 pv = *reinterpret_cast<float4*>(p + i4);
+    float4 bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(buf + i4);
+    const float ge[4] = {gv.x * grad_scale, gv.y * grad_scale, gv.z * grad_scale, gv.w * grad_scale};
+    float be[4] = {bv.x, bv.y, bv.z, bv.w};
+    float pe[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      be[k] = first_step ? ge[k] : fmaf(momentum, be[k], ge[k]);
+      pe[k] = fmaf(-lr, be[k], pe[k]);
+    }
+    *reinterpret_cast<float4*>(buf + i4) = make_float4(be[0], be[1], be[2], be[3]);
+    *reinterpret_cast<float4*>(p + i4) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+  } else {
+    for (long long i = i4; i < n; ++i) {
+      const float gi = g[i] * grad_scale;
+      const float b = first_step ? gi : fmaf(momentum, buf[i], gi);
+      buf[i] = b;
+      p[i] = fmaf(-lr, b, p[i]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ logit layer + CE
@@ -268,7 +363,29 @@ cudaError_t launch_maxpool_fwd(const void* x, void* y, int n, int H, int W, int 
   maxpool_fwd_kernel<<<nblk(total), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n, H, W, C / 8);
   return cudaGetLastError();
 }
-cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, int n, int H, int W, int C, int pooled, cudaStream_t st) {
+cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, float* db, int n, int H, int W, int C, int pooled,
+                                 cudaStream_t st) {
+  if (db != nullptr) {
+    const long long rows = (long long)n * H * W;
+    if (C % 8 == 0 && 256 % (C / 8) == 0 && rows > 0) {      // fused ReLU/pool backward + bias gradient
+      cudaError_t e = cudaMemsetAsync(db, 0, (size_t)C * 4, st);
+      if (e != cudaSuccess) return e;
+      const int C8 = C / 8, lanes = 256 / C8;
+      const long long units = pooled ? rows / 4 : rows;
+      const unsigned blocks = (unsigned)std::min<long long>((units + lanes - 1) / lanes, 148 * 8);
+      count_launch();
+      if (pooled)
+        relu_pool_bwd_bias_kernel<true><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(dP), static_cast<const uint4*>(Y),
+                                                                 static_cast<uint4*>(dZ), db, n, H, W, C8);
+      else
+        relu_pool_bwd_bias_kernel<false><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(dP), static_cast<const uint4*>(Y),
+                                                                  static_cast<uint4*>(dZ), db, n, H, W, C8);
+      return cudaGetLastError();
+    }
+    cudaError_t e = launch_relu_pool_bwd(dP, Y, dZ, nullptr, n, H, W, C, pooled, st);
+    if (e != cudaSuccess) return e;
+    return launch_bias_grad(dZ, db, rows, C, st);
+  }
   count_launch();
   if (pooled) {
     const long long total = (long long)n * (H / 2) * (W / 2) * (C / 2);
@@ -317,7 +434,7 @@ cudaError_t launch_sgd_momentum(float* p, const float* g, float* buf, long long 
                                 float grad_scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   count_launch();
-  sgd_momentum_kernel<<<nblk(n), 256, 0, st>>>(p, g, buf, n, lr, momentum, first_step, grad_scale);
+  sgd_momentum_kernel<<<nblk((n + 3) / 4), 256, 0, st>>>(p, g, buf, n, lr, momentum, first_step, grad_scale);
   return cudaGetLastError();
 }
 cudaError_t launch_ce_train(const float* x, const float* w4, const float* b4, const int64_t* labels, int n, int D, int C,

@@ -13,8 +13,11 @@
 // pass and no padded rows.  (A first version transposed both tensors to NCHW to get K-major operands; the pixel shift
 // then fell on the contiguous dimension, where TMA cannot start a box at a 2-byte offset, and three pre-shifted copies
 // of X were needed.  The transposes alone cost more than the GEMM.)
-// Work unit = (tap, ci tile, co tile, K split), tap fastest so that the CTAs running together stream the same pixels;
-// the fp32 TMEM accumulator of a unit is added to dW with red.global.add.f32 (split-K).  Warp-specialised like the
+// Work unit = (tap group, ci tile, co tile, K split), tap group fastest so that the CTAs running together stream the
+// same pixels.  A unit accumulates T taps at once (T accumulators of BN columns in TMEM): the dZ tile of a K block is
+// loaded ONCE and multiplied with T shifted X boxes -- T = 9 for the first layer (BN = 16/32: the kernel is otherwise
+// bound by re-reading dZ nine times), T = 3 (one filter column) for BN = 64/128, T = 1 for BN = 256 (TMEM is 512
+// columns).  The fp32 accumulators of a unit are added to dW with red.global.add.f32 (split-K).  Warp-specialised like the
 // forward kernel: TMA producer warp, MMA warp, 4 epilogue warps, mbarrier full/empty rings, 2 TMEM accumulator stages.
 // Reference being replaced: loss.backward() for Conv2d/Linear weights (Sheet03/spatialModel.py:180).
 #include "va_internal.h"
@@ -33,8 +36,8 @@ struct WgradParams {
   int w_t, h_t, n_t;          // pixel patch of a K block: w_t * h_t * n_t == kWgradKP
   int tiles_w, tiles_h, tiles_n, pixel_tiles;
   int ks, pad, Cout, Cin;     // Cin = real input channels (epilogue bound); the B tensor may carry padded channels
-  int co_tiles, ci_tiles, taps;
-  int total_units, tiles_per_split;
+  int co_tiles, ci_tiles, taps, tap_groups;
+  int total_units, ksplit;
   int num_stages;
   int row_stride;             // elements between output rows (Cin)
   int plain_store;            // one K split: every output element is written exactly once -> st.global, no memset
@@ -72,17 +75,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) { return
 
 constexpr int kWgradThreads = 192;
 
-// BN = N tile (input channels), CB = channels per B block = TMA box width (64, or the padded 16/32 of the first layer)
-template <int BN, int CB>
+// K split i covers pixel tiles [i*PT/ksplit, (i+1)*PT/ksplit): sizes differ by at most one tile
+__device__ __forceinline__ int split_begin(const WgradParams& p, int split) {
+  return (int)(((long long)split * p.pixel_tiles) / p.ksplit);
+}
+
+// BN = N tile (input channels), CB = channels per B block = TMA box width (64, or the padded 16/32 of the first layer),
+// T = filter taps accumulated per unit (tap' = group*T + j)
+template <int BN, int CB, int T>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
   static_assert(BN % CB == 0, "BN must be whole B blocks");
   constexpr int NB = BN / CB;
   constexpr int ROWB_B = CB * 2;
   constexpr uint32_t A_BLOCK = kWgradKP * 128, B_BLOCK = kWgradKP * ROWB_B;      // 8 KB, 8/4/2 KB: all multiples of 1024
-  constexpr uint32_t A_BYTES = 2 * A_BLOCK, B_BYTES = NB * B_BLOCK;
-  constexpr uint32_t STAGE = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t A_BYTES = 2 * A_BLOCK, B_BYTES = NB * B_BLOCK;    // B_BYTES per tap
+  constexpr uint32_t STAGE = A_BYTES + T * B_BYTES;
+  constexpr int NACC = (2 * T * BN <= 512) ? 2 : 1;                   // accumulator sets: double-buffered when TMEM allows
+  constexpr uint32_t ACC_COLS = T * BN;
+  constexpr uint32_t TMEM_NEED = NACC * ACC_COLS;
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static_assert(TMEM_NEED <= 512, "accumulators exceed TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,9 +120,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](int unit, int& tap, int& ci_t, int& co_t, int& split) {
+  auto decode = [&](int unit, int& tap, int& ci_t, int& co_t, int& split) {      // tap = first tap' of the unit's group
     uint32_t q, t;
-    p.div_taps.divmod((uint32_t)unit, q, t); tap = (int)t;
+    p.div_taps.divmod((uint32_t)unit, q, t); tap = (int)t * T;
     p.div_ci.divmod(q, q, t); ci_t = (int)t;
     p.div_co.divmod(q, q, t); co_t = (int)t;
     split = (int)q;
@@ -120,9 +133,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       int tap, ci_t, co_t, split;
       decode(unit, tap, ci_t, co_t, split);
-      const int s = tap / p.ks, r = tap - s * p.ks;        // tap' = s*ks + r (the forward kernel's order)
-      const int pt0 = split * p.tiles_per_split;
-      const int pt1 = min(p.pixel_tiles, pt0 + p.tiles_per_split);
+      const int pt0 = split_begin(p, split), pt1 = split_begin(p, split + 1);
       for (int pt = pt0; pt < pt1; ++pt) {
         uint32_t q, tw, th, tn;
         p.div_tw.divmod((uint32_t)pt, q, tw);
@@ -131,13 +142,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
         if (elect_one()) {
           uint8_t* a_dst = smem + (size_t)stage * STAGE;
-          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE);
           tma_load_4d(a_dst, &tmA, &full_bar[stage], co_t * 128, w0, h0, n0);
           tma_load_4d(a_dst + A_BLOCK, &tmA, &full_bar[stage], co_t * 128 + 64, w0, h0, n0);
 #pragma unroll
-          for (int b = 0; b < NB; ++b)
-            tma_load_4d(a_dst + A_BYTES + b * B_BLOCK, &tmB, &full_bar[stage], ci_t * BN + b * CB, w0 + s - p.pad,
-                        h0 + r - p.pad, n0);
+          for (int j = 0; j < T; ++j) {
+            const int s = (tap + j) / p.ks, r = (tap + j) - s * p.ks;      // tap' = s*ks + r (the forward kernel's order)
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+              tma_load_4d(a_dst + A_BYTES + j * B_BYTES + b * B_BLOCK, &tmB, &full_bar[stage], ci_t * BN + b * CB,
+                          w0 + s - p.pad, h0 + r - p.pad, n0);
+          }
         }
         __syncwarp();
         if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
@@ -151,11 +166,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       int tap, ci_t, co_t, split;
       decode(unit, tap, ci_t, co_t, split);
-      const int pt0 = split * p.tiles_per_split;
-      const int pt1 = min(p.pixel_tiles, pt0 + p.tiles_per_split);
+      const int pt0 = split_begin(p, split), pt1 = split_begin(p, split + 1);
       mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_u + as * BN;
+      const uint32_t d_tmem = tmem_u + as * ACC_COLS;
       uint32_t acc = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(&full_bar[stage], phase, 300 + stage);
@@ -165,8 +179,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, B_BLOCK);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of B per step
-            umma_bf16(d_tmem, da0 + ((k * 16 * 128) >> 4), db0 + ((k * 16 * ROWB_B) >> 4), idesc, k ? 1u : acc);
+          for (int j = 0; j < T; ++j)
+#pragma unroll
+            for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of B per step
+              umma_bf16(d_tmem + j * BN, da0 + ((k * 16 * 128) >> 4), db0 + ((j * B_BYTES + k * 16 * ROWB_B) >> 4), idesc,
+                        k ? 1u : acc);
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -175,8 +192,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (elect_one()) umma_commit(&tfull_bar[as]);
       __syncwarp();
-      as ^= 1;
-      if (as == 0) as_phase ^= 1;
+      if (++as == NACC) { as = 0; as_phase ^= 1; }
     }
   } else {
     // ===================================================== epilogue: TMEM -> fp32 atomics into dW
@@ -189,30 +205,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[as], as_phase, 400 + as);
       tc_fence_after();
       const int co = co_t * 128 + m;
-      float* dst = p.dwt + ((size_t)tap * p.Cout + co) * p.row_stride + ci_t * BN;
 #pragma unroll 1
-      for (int c16 = 0; c16 < BN / 16; ++c16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c16 * 16, v);
-        tmem_ld_wait();
-        if (co < p.Cout) {
-          if (p.plain_store) {
-            if (ci_t * BN + c16 * 16 + 16 <= p.Cin && (p.row_stride & 3) == 0) {
-              float4* d4 = reinterpret_cast<float4*>(dst + c16 * 16);
+      for (int j = 0; j < T; ++j) {
+        float* dst = p.dwt + ((size_t)(tap + j) * p.Cout + co) * p.row_stride + ci_t * BN;
+#pragma unroll 1
+        for (int c16 = 0; c16 < BN / 16; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS + j * BN + c16 * 16, v);
+          tmem_ld_wait();
+          if (co < p.Cout) {
+            if (p.plain_store) {
+              if (ci_t * BN + c16 * 16 + 16 <= p.Cin && (p.row_stride & 3) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst + c16 * 16);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                    __uint_as_float(v[4 * i + 3]));
+                for (int i = 0; i < 4; ++i)
+                  d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                      __uint_as_float(v[4 * i + 3]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (ci_t * BN + c16 * 16 + i < p.Cin) dst[c16 * 16 + i] = __uint_as_float(v[i]);
+              }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ci_t * BN + c16 * 16 + i < p.Cin) dst[c16 * 16 + i] = __uint_as_float(v[i]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int ci = ci_t * BN + c16 * 16 + i;
-              if (ci < p.Cin) atomicAdd(dst + c16 * 16 + i, __uint_as_float(v[i]));
+              for (int i = 0; i < 16; ++i) {
+                const int ci = ci_t * BN + c16 * 16 + i;
+                if (ci < p.Cin) atomicAdd(dst + c16 * 16 + i, __uint_as_float(v[i]));
+              }
             }
           }
         }
@@ -220,8 +239,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      as ^= 1;
-      if (as == 0) as_phase ^= 1;
+      if (++as == NACC) { as = 0; as_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -289,14 +307,14 @@ const char* encode_nhwc(CUtensorMap* m, const void* addr, int n, int H, int W, i
   return nullptr;
 }
 
-template <int BN, int CB>
+template <int BN, int CB, int T>
 const char* launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, WgradParams p, int grid, cudaStream_t st) {
-  constexpr uint32_t STAGE = 2 * kWgradKP * 128 + (BN / CB) * kWgradKP * CB * 2;
+  constexpr uint32_t STAGE = 2 * kWgradKP * 128 + T * (BN / CB) * kWgradKP * CB * 2;
   int stages = (int)((227 * 1024 - 1024 - 256) / STAGE);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
   const size_t smem = 1024 + (size_t)stages * STAGE + 256;
-  auto kfn = wgrad_tc_kernel<BN, CB>;
+  auto kfn = wgrad_tc_kernel<BN, CB, T>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -306,7 +324,7 @@ const char* launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, WgradPara
   count_launch();
   kfn<<<grid, kWgradThreads, smem, st>>>(tA, tB, p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return werrf("wgrad_tc_kernel<%d,%d> launch: %s", BN, CB, cudaGetErrorString(e));
+  if (e != cudaSuccess) return werrf("wgrad_tc_kernel<%d,%d,%d> launch: %s", BN, CB, T, cudaGetErrorString(e));
   return nullptr;
 }
 }  // namespace
@@ -332,17 +350,32 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   p.pixel_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   p.ks = ks; p.pad = (ks - 1) / 2; p.Cout = Cout; p.Cin = Cin; p.row_stride = Cin;
   p.co_tiles = (Cout + 127) / 128; p.ci_tiles = (cin_pad + BN - 1) / BN; p.taps = ks * ks;
+  // taps per unit: all 9 for the first layer, one filter column for the 64/128-wide N tiles, 1 when TMEM holds only one
+  const int T = ks == 1 ? 1 : (BN <= 32 ? 9 : (BN <= 64 ? 3 : 1));
+  p.tap_groups = p.taps / T;
   const int sms = sm_count_cached();
-  const int base_units = p.taps * p.co_tiles * p.ci_tiles;
-  int ksplit = (2 * sms + base_units - 1) / base_units;        // aim at >= 2 units per SM
-  if (ksplit > p.pixel_tiles) ksplit = p.pixel_tiles;
-  if (ksplit < 1) ksplit = 1;
-  p.tiles_per_split = (p.pixel_tiles + ksplit - 1) / ksplit;
-  ksplit = (p.pixel_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  const int base_units = p.tap_groups * p.co_tiles * p.ci_tiles;
+  // K splits: 2..8 units per SM, picked for the fullest last wave (units are dealt round-robin to one CTA per SM, so
+  // 2.07 waves cost 3); fewer splits win ties (less atomic traffic)
+  int ksplit = 1;
+  {
+    double best = -1.0;
+    const int k_lo = std::max(1, (2 * sms + base_units - 1) / base_units);
+    const int k_hi = std::max(k_lo, (8 * sms) / base_units);
+    for (int k = k_lo; k <= k_hi && k <= p.pixel_tiles; ++k) {
+      const int units = base_units * k;
+      const int waves = (units + sms - 1) / sms;
+      const double eff = (double)units / ((double)waves * sms);
+      if (eff > best + 0.01) { best = eff; ksplit = k; }
+    }
+    if (ksplit > p.pixel_tiles) ksplit = p.pixel_tiles;
+    if (base_units >= 2 * sms) ksplit = 1;       // enough independent output tiles (the FC layers): no split-K
+  }
+  p.ksplit = ksplit;
   p.total_units = base_units * ksplit;
   float* target = ks == 1 ? dw : dwt_ws;
   p.dwt = target;
-  p.div_taps = FastDiv::make((uint32_t)p.taps);
+  p.div_taps = FastDiv::make((uint32_t)p.tap_groups);
   p.div_ci = FastDiv::make((uint32_t)p.ci_tiles);
   p.div_co = FastDiv::make((uint32_t)p.co_tiles);
   p.div_tw = FastDiv::make((uint32_t)p.tiles_w);
@@ -356,9 +389,10 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   if (const char* e = encode_nhwc(&tB, x, n, H, W, cin_pad, CB, p.w_t, p.h_t, p.n_t)) return e;
   const int grid = p.total_units < sms ? p.total_units : sms;
   const char* err = nullptr;
-#define VA_W(bn, cb) if (BN == bn && CB == cb) err = launch_wgrad<bn, cb>(tA, tB, p, grid, st); else
-  VA_W(256, 64) VA_W(128, 64) VA_W(64, 64) VA_W(32, 32) VA_W(16, 16)
-  err = werrf("wgrad: no kernel for BN=%d CB=%d", BN, CB);
+#define VA_W(bn, cb, t) if (BN == bn && CB == cb && T == t) err = launch_wgrad<bn, cb, t>(tA, tB, p, grid, st); else
+  VA_W(256, 64, 1) VA_W(128, 64, 3) VA_W(64, 64, 3) VA_W(32, 32, 9) VA_W(16, 16, 9)
+  VA_W(128, 64, 1) VA_W(64, 64, 1) VA_W(32, 32, 1) VA_W(16, 16, 1)
+  err = werrf("wgrad: no kernel for BN=%d CB=%d T=%d", BN, CB, T);
 #undef VA_W
   if (err) return err;
   if (ks != 1) {

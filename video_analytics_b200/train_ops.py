@@ -24,15 +24,18 @@ def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def relu_pool_bwd(dout: torch.Tensor, y: torch.Tensor, *, pooled: bool) -> torch.Tensor:
+def relu_pool_bwd(dout: torch.Tensor, y: torch.Tensor, *, pooled: bool, bias_grad_out=None) -> torch.Tensor:
     """Gradient w.r.t. the pre-activation z of y = relu(z) [n,H,W,C], given the gradient of pool(y) (pooled=True,
-    dout [n,H/2,W/2,C]) or of y itself (pooled=False)."""
-    _need_cuda(dout, y)
+    dout [n,H/2,W/2,C]) or of y itself (pooled=False).  bias_grad_out: fp32 [C] tensor that receives
+    sum over pixels of dz (the layer's bias gradient) from the same pass."""
+    _need_cuda(dout, y, bias_grad_out)
     assert dout.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
     n, H, W, Cc = y.shape
+    if bias_grad_out is not None:
+        assert bias_grad_out.dtype == torch.float32 and bias_grad_out.numel() == Cc
     dz = torch.empty_like(y)
-    check(_lib.load().va_relu_pool_bwd(ptr(dout), ptr(y), n, H, W, Cc, int(pooled), ptr(dz), stream_ptr()),
-          "va_relu_pool_bwd")
+    check(_lib.load().va_relu_pool_bwd(ptr(dout), ptr(y), n, H, W, Cc, int(pooled), ptr(dz), ptr(bias_grad_out),
+                                       stream_ptr()), "va_relu_pool_bwd")
     return dz
 
 

@@ -157,18 +157,18 @@ class StreamTrainer:
         dz = T.relu_bwd_f32_to_bf16(g, h3)
         T.linear_wgrad(dz, d2, out=G[30]); T.bias_grad(dz, out=G[31])
         g = T.dropout(T.linear_dgrad(dz, W[30]), masks[1], DROPOUT_P)
-        dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h2.view(n, 1, 1, -1), pooled=False).view(n, -1)
-        T.linear_wgrad(dz, d1, out=G[28]); T.bias_grad(dz, out=G[29])
+        dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h2.view(n, 1, 1, -1), pooled=False, bias_grad_out=G[29]).view(n, -1)
+        T.linear_wgrad(dz, d1, out=G[28])
         g = T.dropout(T.linear_dgrad(dz, W[28]), masks[0], DROPOUT_P)
-        dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h1.view(n, 1, 1, -1), pooled=False).view(n, -1)
-        T.linear_wgrad(dz, flat, out=G[26]); T.bias_grad(dz, out=G[27])
+        dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h1.view(n, 1, 1, -1), pooled=False, bias_grad_out=G[27]).view(n, -1)
+        T.linear_wgrad(dz, flat, out=G[26])
         g = T.linear_dgrad(dz, W[26])                                        # [n, ch*hw] in NCHW flatten order
         g = T.transpose_bf16(g.view(n, ch, hw)).view(n, x.shape[1], x.shape[2], ch)
         for i in range(12, -1, -1):
             xin, y = saved[i]
-            dz = T.relu_pool_bwd(g, y, pooled=POOL_AFTER[i])
+            dz = T.relu_pool_bwd(g, y, pooled=POOL_AFTER[i], bias_grad_out=G[2 * i + 1])
             cin = W[2 * i].shape[1]
-            T.conv2d_wgrad(dz, xin, cin, out=G[2 * i]); T.bias_grad(dz, out=G[2 * i + 1])
+            T.conv2d_wgrad(dz, xin, cin, out=G[2 * i])
             if i > 0:
                 g = T.conv2d_dgrad(dz, W[2 * i])
             saved[i] = None
