@@ -113,10 +113,11 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_bias_kernel(const uint4* __
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         int a = 0;
+        float best = v[0][c];                 // running maximum kept in a register: no dynamically indexed array
 #pragma unroll
         for (int k = 1; k < 4; ++k)
-          if (v[k][c] > v[a][c]) a = k;
-        if (v[a][c] > 0.f) {
+          if (v[k][c] > best) { best = v[k][c]; a = k; }
+        if (best > 0.f) {
           acc[c] += gp[c];
 #pragma unroll
           for (int k = 0; k < 4; ++k)

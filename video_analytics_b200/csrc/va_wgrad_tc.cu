@@ -159,7 +159,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == kMmaWarp) {
-    constexpr uint32_t idesc = make_idesc_bf16_mn(128, BN);
+    // The T taps' B boxes are consecutive blocks B_BLOCK apart -- the MN-major layout's LBO -- so ONE MMA covers
+    // several taps: N = NT*BN columns, tap j of the group landing in accumulator columns [j*BN, (j+1)*BN).
+    constexpr int NT = (T * BN <= 256) ? T : (256 / BN);          // taps per MMA (N <= 256)
+    constexpr int NG = (T + NT - 1) / NT;                          // MMAs per K step
+    constexpr int NT_LAST = T - (NG - 1) * NT;
+    constexpr uint32_t idesc = make_idesc_bf16_mn(128, NT * BN);
+    constexpr uint32_t idesc_last = make_idesc_bf16_mn(128, NT_LAST * BN);
     const uint32_t smem_base_u32 = smem_u32(smem);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
@@ -179,11 +185,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, B_BLOCK);
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < T; ++j)
+          for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of each B block per step
 #pragma unroll
-            for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of B per step
-              umma_bf16(d_tmem + j * BN, da0 + ((k * 16 * 128) >> 4), db0 + ((j * B_BYTES + k * 16 * ROWB_B) >> 4), idesc,
-                        k ? 1u : acc);
+            for (int gI = 0; gI < NG; ++gI)
+              umma_bf16(d_tmem + gI * NT * BN, da0 + ((k * 16 * 128) >> 4),
+                        db0 + ((gI * NT * B_BYTES + k * 16 * ROWB_B) >> 4), gI == NG - 1 ? idesc_last : idesc, k ? 1u : acc);
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -351,7 +357,7 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   p.ks = ks; p.pad = (ks - 1) / 2; p.Cout = Cout; p.Cin = Cin; p.row_stride = Cin;
   p.co_tiles = (Cout + 127) / 128; p.ci_tiles = (cin_pad + BN - 1) / BN; p.taps = ks * ks;
   // taps per unit: all 9 for the first layer, one filter column for the 64/128-wide N tiles, 1 when TMEM holds only one
-  const int T = ks == 1 ? 1 : (BN <= 32 ? 9 : (BN <= 64 ? 3 : 1));
+  const int T = ks == 1 ? 1 : (BN <= 32 ? 9 : (BN <= 128 ? 3 : 1));
   p.tap_groups = p.taps / T;
   const int sms = sm_count_cached();
   const int base_units = p.tap_groups * p.co_tiles * p.ci_tiles;
