@@ -57,6 +57,6 @@ tot = collections.OrderedDict()
 for name, shape, a, b in spans:
     ms = a.elapsed_time(b)
     tot[name] = tot.get(name, 0.0) + ms
-    if name in ("conv2d_wgrad", "conv2d_dgrad", "conv2d_nhwc", "linear_wgrad", "linear_dgrad", "linear"):
+    if name in ("conv2d_wgrad", "conv2d_dgrad", "conv2d_nhwc", "linear_wgrad", "linear_dgrad", "linear", "relu_pool_bwd", "maxpool2x2"):
         print(f"  {name:16s} {str(shape):28s} {ms:8.3f} ms")
 print({k: round(v, 2) for k, v in tot.items()}, "sum", round(sum(tot.values()), 2))

@@ -373,7 +373,9 @@ cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, float*
       if (e != cudaSuccess) return e;
       const int C8 = C / 8, lanes = 256 / C8;
       const long long units = pooled ? rows / 4 : rows;
-      const unsigned blocks = (unsigned)std::min<long long>((units + lanes - 1) / lanes, 148 * 8);
+      // >= 16 windows per thread: every block ends with C same-address atomics, which dominate on the small layers
+      const long long want = (units + lanes * 16 - 1) / (lanes * 16);
+      const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(want, 148 * 8));
       count_launch();
       if (pooled)
         relu_pool_bwd_bias_kernel<true><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(dP), static_cast<const uint4*>(Y),
