@@ -14,7 +14,9 @@ Layout of the step on the device:
     (drawn by torch's generator, or supplied by the caller so the oracle can share them);
   * backward: ReLU/pool routing kernel -> weight-gradient GEMM (tcgen05, split-K fp32 atomics) + bias-gradient
     reduction -> data-gradient through the layer kernel with rotated/transposed filters; gradients between layers bf16;
-  * multi-GPU: ONE NCCL all-reduce (sum) over the gradient arena, its 1/world scale folded into the update kernel;
+  * multi-GPU: NCCL all-reduce (sum) over the flat gradient arena in two slices -- the classifier's 476 MB as soon as
+    they exist (first in the backward pass, hidden under the conv-stack backward), the conv stack's 59 MB at the end --
+    with the 1/world scale folded into the update kernel;
   * update: ONE fused SGD-momentum launch over the whole arena.
 
 There is no torch autograd and no torch compute op on this path; torch owns memory, streams and the process group.
@@ -120,10 +122,12 @@ class StreamTrainer:
 
     # ---- the step
     def forward_backward(self, x_nhwc: torch.Tensor, labels: torch.Tensor, masks: Optional[Sequence[torch.Tensor]] = None,
-                         keep: Optional[dict] = None):
+                         keep: Optional[dict] = None, on_classifier_grads=None):
         """Fills the gradient arena; returns (loss [1] fp32 tensor, featureVectors [n,D] fp32, logits [n,C] fp32).
         keep: optional dict that receives the saved forward activations (tests check the backward chain against a
-        reference backward taken over exactly these activations)."""
+        reference backward taken over exactly these activations).  on_classifier_grads: called (no arguments) as soon
+        as every classifier gradient is in the arena -- they are produced FIRST in the backward pass and are 88 % of the
+        bytes, so their all-reduce can run under the whole conv-stack backward."""
         assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.dim() == 4 and x_nhwc.shape[3] == self.c_pad, x_nhwc.shape
         n = x_nhwc.shape[0]
         W = [p.data for p in self.params]
@@ -162,6 +166,8 @@ class StreamTrainer:
         g = T.dropout(T.linear_dgrad(dz, W[28]), masks[0], DROPOUT_P)
         dz = T.relu_pool_bwd(g.view(n, 1, 1, -1), h1.view(n, 1, 1, -1), pooled=False, bias_grad_out=G[27]).view(n, -1)
         T.linear_wgrad(dz, flat, out=G[26])
+        if on_classifier_grads is not None:
+            on_classifier_grads()
         g = T.linear_dgrad(dz, W[26])                                        # [n, ch*hw] in NCHW flatten order
         g = T.transpose_bf16(g.view(n, ch, hw)).view(n, x.shape[1], x.shape[2], ch)
         for i in range(12, -1, -1):
@@ -174,12 +180,20 @@ class StreamTrainer:
             saved[i] = None
         return ce["loss"], d3, ce["logits"]
 
-    def apply_update(self):
-        """Gradient all-reduce (when a process group is given) + the fused SGD-momentum update over the arena."""
+    def _allreduce_async(self, lo: int, hi: int):
+        import torch.distributed as dist
+        return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def apply_update(self, pending=()):
+        """Gradient all-reduce (when a process group is given) + the fused SGD-momentum update over the arena.
+        pending: work handles of slices whose all-reduce is already in flight."""
         scale = 1.0
         if self.group is not None:
             import torch.distributed as dist
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            if not pending:
+                pending = [self._allreduce_async(0, self.flat_grad.numel())]
+            for w in pending:
+                w.wait()                       # makes the current stream wait for the collective
             scale = 1.0 / dist.get_world_size(self.group)
         lr, momentum = self.hyper()
         T.sgd_momentum_(self.flat_param, self.flat_grad, self.flat_buf, lr=lr, momentum=momentum,
@@ -189,8 +203,18 @@ class StreamTrainer:
         self.steps_done += 1
 
     def step(self, x_nhwc: torch.Tensor, labels: torch.Tensor, masks=None):
-        loss, feat, logits = self.forward_backward(x_nhwc, labels, masks)
-        self.apply_update()
+        """Forward + backward + (overlapped) gradient all-reduce + update.  The arena is reduced in two slices: the
+        classifier's gradients as soon as they exist (under the conv-stack backward), the conv stack's at the end."""
+        pending = []
+        split = self.offsets[26]               # first classifier tensor (state_dict order: 13 conv pairs, then 4 FC pairs)
+        hook = None
+        if self.group is not None:
+            def hook():
+                pending.append(self._allreduce_async(split, self.flat_grad.numel()))
+        loss, feat, logits = self.forward_backward(x_nhwc, labels, masks, on_classifier_grads=hook)
+        if self.group is not None:
+            pending.append(self._allreduce_async(0, split))
+        self.apply_update(pending)
         return loss, feat, logits
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
