@@ -248,3 +248,22 @@ def test_fp32_mode_vs_oracle(kind, world):
     decidable = (srt[:, 0] - srt[:, 1]) > 2 * float((logits.cpu() - ol).abs().max())
     assert bool((pred.cpu().long() == opred)[decidable].all())
     net.close()
+
+
+def test_result_independent_of_chunk_size():
+    """The internal chunking (max_batch) must not change a single bit: same K order in every layer for any batch."""
+    from video_analytics_b200 import ops
+    from video_analytics_b200.spatialModel import build_spatial_torch_model
+    sd = build_spatial_torch_model(101, 256, seed=2).state_dict()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 224, 224, 16, generator=g).cuda().bfloat16()
+    x[..., 3:] = 0
+    outs = []
+    for mb in (5, 16, 64):
+        net = ops.StreamNet(ops.STREAM_SPATIAL, 3, 101, 256, max_batch=mb)
+        net.load_state_dict(sd)
+        outs.append([t.clone() for t in net.forward(x)])
+        net.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)

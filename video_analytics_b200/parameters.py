@@ -43,7 +43,7 @@ STREAM_WEIGHT_SPATIAL = 1.0   # late-fusion weights for the class-score average 
 STREAM_WEIGHT_TEMPORAL = 1.0
 FLOW_NORM_MEAN = NORM_MEANS_TF[0]   # 1-channel flow images see only mean[0]/std[0] (2018 torchvision zip semantics)
 FLOW_NORM_STD = NORM_STDS_TF[0]
-GPU_MAX_BATCH = 125           # snippets per internal chunk of the network workspace (2 chunks per 250-snippet video)
+GPU_MAX_BATCH = 250           # snippets per internal chunk of the network workspace (one 250-snippet video)
 
 __all__ = list(_REFERENCE_TABLE) + ["N_TEST_SNIPPETS", "N_TEST_CROPS", "STREAM_WEIGHT_SPATIAL", "STREAM_WEIGHT_TEMPORAL",
                                    "FLOW_NORM_MEAN", "FLOW_NORM_STD", "GPU_MAX_BATCH"]
