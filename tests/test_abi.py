@@ -59,3 +59,35 @@ def test_sass_is_blackwell_native(built_lib):
     for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass     # no legacy mma.sync path
+
+
+def test_training_primitives_reject_bad_arguments_without_touching_the_gpu(built_lib):
+    """Argument validation of the K5 entry points happens before any CUDA call (status 1 = VA_ERR_INVALID)."""
+    from video_analytics_b200 import _lib
+    lib = _lib.load()
+    assert lib.va_wgrad(None, None, 1, 4, 4, 64, 64, 64, 3, None, None) != 0
+    assert b"NULL" in lib.va_last_error()
+    assert lib.va_conv2d_dgrad(None, 1, 4, 4, 64, None, 64, None, None) != 0
+    assert lib.va_relu_pool_bwd(None, None, 1, 4, 4, 64, 1, None, None, None) != 0
+    assert lib.va_sgd_momentum(None, None, None, 10, 0.1, 0.9, 1, 1.0, None) != 0
+    assert lib.va_ce_train(None, None, None, None, 1, 256, 101, None, None, None, None, None, None, None) != 0
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.va_wgrad(p, p, 1, 4, 4, 64, 64, 64, 5, p, None) != 0           # ks must be 1 or 3
+    assert b"ks" in lib.va_last_error()
+    assert lib.va_conv2d_dgrad(p, 1, 4, 4, 48, p, 64, p, None) != 0             # channels must be multiples of 64
+    assert lib.va_maxpool2x2_nhwc(p, 1, 5, 4, 64, p, None) != 0                 # odd height
+
+
+def test_training_has_no_cpu_fallback(built_lib):
+    import torch
+    from video_analytics_b200 import train_ops as T
+    from video_analytics_b200._lib import VAError
+    with pytest.raises(VAError):
+        T.maxpool2x2(torch.zeros(1, 4, 4, 8, dtype=torch.bfloat16))
+    with pytest.raises(VAError):
+        T.conv2d_wgrad(torch.zeros(1, 4, 4, 64, dtype=torch.bfloat16), torch.zeros(1, 4, 4, 64, dtype=torch.bfloat16), 64)
+    if not torch.cuda.is_available():
+        from video_analytics_b200.training import StreamTrainer
+        with pytest.raises(VAError):
+            StreamTrainer(torch.nn.Linear(2, 2))

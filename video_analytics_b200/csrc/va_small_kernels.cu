@@ -315,6 +315,14 @@ __global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     out[g] = __float2bfloat16_rn(w[o * n_in + src]);
   }
 }
+// chan == 0 (no re-ordering): plain fp32 -> bf16 cast, four elements per thread
+__global__ void __launch_bounds__(256) cast_f32_bf16_vec4_kernel(const float4* __restrict__ w, uint2* __restrict__ out, size_t total4) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total4; g += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(w + g);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    out[g] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
+}
 __global__ void transpose_f32_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int cols) {
   const int total = rows * cols;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
@@ -334,6 +342,10 @@ cudaError_t launch_pack_fc_w(const float* w, void* out, int n_out, int n_in, int
   const size_t total = (size_t)n_out * n_in;
   unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
   count_launch();
+  if (chan == 0 && (total & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    cast_f32_bf16_vec4_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(w), reinterpret_cast<uint2*>(out), total / 4);
+    return cudaGetLastError();
+  }
   pack_fc_w_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), n_out, n_in, chan, hw);
   return cudaGetLastError();
 }
