@@ -143,8 +143,11 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
  *   va_dropout           : y = x * scale where mask (u8) != 0 else 0 (forward and backward are the same map)
  *   va_conv2d_dgrad      : dX = conv3x3(dZ, rot180(W) with channel roles swapped)  -- tcgen05 layer kernel
  *   va_linear_dgrad      : dX = dY . W                                            -- tcgen05 layer kernel
- *   va_wgrad             : dW[co][ci][r][s] = sum_pixels dZ[p][co] X[p + (r,s)][ci] -- tcgen05 weight-gradient GEMM
- *                          (ks=1, H=1, W=batch gives the fully-connected dW = dY^T . X)
+ *   va_wgrad             : dW[co][ci][r][s] = sum_pixels dZ[p][co] X[p + (r,s)][ci] -- tcgen05 weight-gradient GEMM that
+ *                          reads dZ [n][H][W][cout] and X [n][H][W][cin_pad] (bf16 NHWC) as MN-major operands; dW is
+ *                          fp32 [cout][cin][ks][ks] with cin <= cin_pad the real input channels (channels >= cin of X
+ *                          must be zero).  cout % 8 == 0; cin_pad is 16, 32 or >= 64 (% 8 == 0); ks is 3 (pad 1) or 1.
+ *                          ks=1, H=W=1, n=batch gives the fully-connected dW = dY^T . X
  *   va_ce_train          : fp32 logit layer forward + mean cross-entropy + its backward (dlogits, dW4, db4, dx)
  *   va_transpose_bf16    : [n][A][B] -> [n][B][A] (NHWC <-> the reference's NCHW flatten order in front of FC1)
  *   va_relu_bwd_f32_to_bf16, va_f32_to_bf16 : glue between the fp32 descriptor layer and the bf16 stack
