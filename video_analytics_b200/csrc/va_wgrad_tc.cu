@@ -41,6 +41,7 @@ struct WgradParams {
   int num_stages;
   int row_stride;             // elements between output rows (Cin)
   int plain_store;            // one K split: every output element is written exactly once -> st.global, no memset
+  int vr_rows, vr_shift;      // VR variant: rows of the (h_t+2)-row B box, rows between vertically adjacent taps (= w_t)
   float* dwt;                 // fp32 [taps][Cout][Cin], pre-zeroed
   FastDiv div_taps, div_ci, div_co, div_tw, div_th;
 };
@@ -53,6 +54,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+// 16-byte vector reduction: one L2 request adds four consecutive floats (sm_90+).  The split-K epilogue issues 128 x BN
+// reductions per unit from 128 different rows; with scalar REDs they, not the MMAs, bounded the 256-wide layers at
+// batch 64 (ncu source view: 60 % of the stall samples on the RED instructions).
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // MN-major operand descriptor: rows of ROWB bytes (one pixel each) written by TMA with the matching swizzle; 8-row
@@ -81,8 +89,11 @@ __device__ __forceinline__ int split_begin(const WgradParams& p, int split) {
 }
 
 // BN = N tile (input channels), CB = channels per B block = TMA box width (64, or the padded 16/32 of the first layer),
-// T = filter taps accumulated per unit (tap' = group*T + j)
-template <int BN, int CB, int T>
+// T = filter taps accumulated per unit (tap' = group*T + j).
+// VR ("vertical reuse", T == 3, one image per K block, w_t a multiple of 8): the three taps r = 0..2 of a filter column
+// read ONE B box of h_t + 2 rows at row offsets r*w_t (whole 8-row swizzle atoms) instead of three shifted boxes --
+// 36 instead of 64 KB per K block at BN = 128, and the 64/128-wide layers are bound by L2 -> SM bytes.
+template <int BN, int CB, int T, bool VR>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
   static_assert(BN % CB == 0, "BN must be whole B blocks");
@@ -90,7 +101,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int ROWB_B = CB * 2;
   constexpr uint32_t A_BLOCK = kWgradKP * 128, B_BLOCK = kWgradKP * ROWB_B;      // 8 KB, 8/4/2 KB: all multiples of 1024
   constexpr uint32_t A_BYTES = 2 * A_BLOCK, B_BYTES = NB * B_BLOCK;    // B_BYTES per tap
-  constexpr uint32_t STAGE = A_BYTES + T * B_BYTES;
+  static_assert(!VR || (T == 3 && CB == 64), "vertical reuse: one filter column, 64-channel blocks");
+  const uint32_t b_block = VR ? (uint32_t)p.vr_rows * ROWB_B : B_BLOCK;            // bytes of one 64-channel B block
+  const uint32_t STAGE = VR ? A_BYTES + NB * b_block : A_BYTES + T * B_BYTES;
   constexpr int NACC = (2 * T * BN <= 512) ? 2 : 1;                   // accumulator sets: double-buffered when TMEM allows
   constexpr uint32_t ACC_COLS = T * BN;
   constexpr uint32_t TMEM_NEED = NACC * ACC_COLS;
@@ -145,13 +158,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_arrive_expect_tx(&full_bar[stage], STAGE);
           tma_load_4d(a_dst, &tmA, &full_bar[stage], co_t * 128, w0, h0, n0);
           tma_load_4d(a_dst + A_BLOCK, &tmA, &full_bar[stage], co_t * 128 + 64, w0, h0, n0);
-#pragma unroll
-          for (int j = 0; j < T; ++j) {
-            const int s = (tap + j) / p.ks, r = (tap + j) - s * p.ks;      // tap' = s*ks + r (the forward kernel's order)
+          if (VR) {
+            const int s = tap / p.ks;                                        // the group is filter column s
 #pragma unroll
             for (int b = 0; b < NB; ++b)
-              tma_load_4d(a_dst + A_BYTES + j * B_BYTES + b * B_BLOCK, &tmB, &full_bar[stage], ci_t * BN + b * CB,
-                          w0 + s - p.pad, h0 + r - p.pad, n0);
+              tma_load_4d(a_dst + A_BYTES + b * b_block, &tmB, &full_bar[stage], ci_t * BN + b * CB, w0 + s - p.pad,
+                          h0 - p.pad, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+              const int s = (tap + j) / p.ks, r = (tap + j) - s * p.ks;      // tap' = s*ks + r (the forward kernel's order)
+#pragma unroll
+              for (int b = 0; b < NB; ++b)
+                tma_load_4d(a_dst + A_BYTES + j * B_BYTES + b * B_BLOCK, &tmB, &full_bar[stage], ci_t * BN + b * CB,
+                            w0 + s - p.pad, h0 + r - p.pad, n0);
+            }
           }
         }
         __syncwarp();
@@ -182,14 +203,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t a_addr = smem_base_u32 + stage * STAGE;
         const uint64_t da0 = make_smem_desc_mn<128>(a_addr, A_BLOCK);
-        const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, B_BLOCK);
         if (elect_one()) {
+          if (VR && NB == 1) {
+            // blocks of the three taps overlap: tap r starts vr_shift rows after tap r-1 -> one N = 3*BN MMA, LBO = shift
+            const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, (uint32_t)p.vr_shift * ROWB_B);
 #pragma unroll
-          for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of each B block per step
+            for (int k = 0; k < kWgradKP / 16; ++k)
+              umma_bf16(d_tmem, da0 + ((k * 16 * 128) >> 4), db0 + ((k * 16 * ROWB_B) >> 4), make_idesc_bf16_mn(128, 3 * BN),
+                        k ? 1u : acc);
+          } else if (VR) {
+            const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, b_block);
+            const uint32_t shift16 = ((uint32_t)p.vr_shift * ROWB_B) >> 4;
 #pragma unroll
-            for (int gI = 0; gI < NG; ++gI)
-              umma_bf16(d_tmem + gI * NT * BN, da0 + ((k * 16 * 128) >> 4),
-                        db0 + ((gI * NT * B_BYTES + k * 16 * ROWB_B) >> 4), gI == NG - 1 ? idesc_last : idesc, k ? 1u : acc);
+            for (int k = 0; k < kWgradKP / 16; ++k)
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+                umma_bf16(d_tmem + r * BN, da0 + ((k * 16 * 128) >> 4), db0 + r * shift16 + ((k * 16 * ROWB_B) >> 4),
+                          make_idesc_bf16_mn(128, BN), k ? 1u : acc);
+          } else {
+            const uint64_t db0 = make_smem_desc_mn<ROWB_B>(a_addr + A_BYTES, B_BLOCK);
+#pragma unroll
+            for (int k = 0; k < kWgradKP / 16; ++k)     // 16 pixels = 16 rows: 2 KB of A, 16*ROWB_B of each B block per step
+#pragma unroll
+              for (int gI = 0; gI < NG; ++gI)
+                umma_bf16(d_tmem + gI * NT * BN, da0 + ((k * 16 * 128) >> 4),
+                          db0 + ((gI * NT * B_BYTES + k * 16 * ROWB_B) >> 4), gI == NG - 1 ? idesc_last : idesc, k ? 1u : acc);
+          }
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -232,6 +271,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int i = 0; i < 16; ++i)
                   if (ci_t * BN + c16 * 16 + i < p.Cin) dst[c16 * 16 + i] = __uint_as_float(v[i]);
               }
+            } else if (ci_t * BN + c16 * 16 + 16 <= p.Cin && (p.row_stride & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                red_add_v4(dst + c16 * 16 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -313,14 +357,15 @@ const char* encode_nhwc(CUtensorMap* m, const void* addr, int n, int H, int W, i
   return nullptr;
 }
 
-template <int BN, int CB, int T>
+template <int BN, int CB, int T, bool VR>
 const char* launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, WgradParams p, int grid, cudaStream_t st) {
-  constexpr uint32_t STAGE = 2 * kWgradKP * 128 + T * (BN / CB) * kWgradKP * CB * 2;
+  const uint32_t STAGE = VR ? 2 * kWgradKP * 128 + (BN / CB) * p.vr_rows * CB * 2
+                            : 2 * kWgradKP * 128 + T * (BN / CB) * kWgradKP * CB * 2;
   int stages = (int)((227 * 1024 - 1024 - 256) / STAGE);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
   const size_t smem = 1024 + (size_t)stages * STAGE + 256;
-  auto kfn = wgrad_tc_kernel<BN, CB, T>;
+  auto kfn = wgrad_tc_kernel<BN, CB, T, VR>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -330,7 +375,7 @@ const char* launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, WgradPara
   count_launch();
   kfn<<<grid, kWgradThreads, smem, st>>>(tA, tB, p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return werrf("wgrad_tc_kernel<%d,%d,%d> launch: %s", BN, CB, T, cudaGetErrorString(e));
+  if (e != cudaSuccess) return werrf("wgrad_tc_kernel<%d,%d,%d,%d> launch: %s", BN, CB, T, (int)VR, cudaGetErrorString(e));
   return nullptr;
 }
 }  // namespace
@@ -392,12 +437,16 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   if (ce != cudaSuccess) return werrf("wgrad memset: %s", cudaGetErrorString(ce));
   CUtensorMap tA, tB;
   if (const char* e = encode_nhwc(&tA, dz, n, H, W, Cout, 64, p.w_t, p.h_t, p.n_t)) return e;
-  if (const char* e = encode_nhwc(&tB, x, n, H, W, cin_pad, CB, p.w_t, p.h_t, p.n_t)) return e;
+  // vertical reuse needs one image per K block and tap offsets of whole 8-row swizzle atoms
+  const bool vr = T == 3 && CB == 64 && p.n_t == 1 && (p.w_t % 8) == 0 && getenv("VA_WGRAD_NO_VR") == nullptr;
+  p.vr_rows = (p.h_t + 2) * p.w_t; p.vr_shift = p.w_t;
+  if (const char* e = encode_nhwc(&tB, x, n, H, W, cin_pad, CB, p.w_t, vr ? p.h_t + 2 : p.h_t, p.n_t)) return e;
   const int grid = p.total_units < sms ? p.total_units : sms;
   const char* err = nullptr;
-#define VA_W(bn, cb, t) if (BN == bn && CB == cb && T == t) err = launch_wgrad<bn, cb, t>(tA, tB, p, grid, st); else
-  VA_W(256, 64, 1) VA_W(128, 64, 3) VA_W(64, 64, 3) VA_W(32, 32, 9) VA_W(16, 16, 9)
-  VA_W(128, 64, 1) VA_W(64, 64, 1) VA_W(32, 32, 1) VA_W(16, 16, 1)
+#define VA_W(bn, cb, t, v) if (BN == bn && CB == cb && T == t && vr == v) err = launch_wgrad<bn, cb, t, v>(tA, tB, p, grid, st); else
+  VA_W(256, 64, 1, false) VA_W(128, 64, 3, false) VA_W(64, 64, 3, false) VA_W(32, 32, 9, false) VA_W(16, 16, 9, false)
+  VA_W(128, 64, 3, true) VA_W(64, 64, 3, true)
+  VA_W(128, 64, 1, false) VA_W(64, 64, 1, false) VA_W(32, 32, 1, false) VA_W(16, 16, 1, false)
   err = werrf("wgrad: no kernel for BN=%d CB=%d T=%d", BN, CB, T);
 #undef VA_W
   if (err) return err;
