@@ -5,6 +5,7 @@ import io
 import random
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import synth, two_stream as ts
@@ -167,3 +168,37 @@ def test_train_step_vs_golden(golden):
         assert abs(float(fv.abs().mean()) - st["fv_abs_mean"]) < 1e-3 * st["fv_abs_mean"]
         assert abs(float(model.features[0].weight.abs().mean()) - st["w0_abs_mean"]) < 1e-4 * st["w0_abs_mean"]
         assert abs(float(model.classifier[9].weight.abs().mean()) - st["w_last_abs_mean"]) < 1e-4 * st["w_last_abs_mean"]
+
+
+def test_jpeg_restatement_vs_pillow():
+    """(f)#2 oracle pin: oracle/jpeg_baseline.py restates Pillow's libjpeg-turbo decode path (what the reference's
+    Image.open does to the files cv2.imwrite wrote, spatialModel.py:76-79, utils.py:116-120) -- identical bytes."""
+    import io
+    import cv2
+    from PIL import Image
+    from oracle import jpeg_baseline as J
+    rng = np.random.default_rng(0)
+
+    def synth(h, w, c):
+        yy, xx = np.mgrid[0:h, 0:w]
+        chans = [(xx * 0.7 + yy * 0.3) % 256, (xx * 0.2 + yy * 0.9) % 256, 128 + 60 * np.sin(xx / 17) + 40 * np.cos(yy / 11)][:c]
+        img = (np.stack(chans, -1) + rng.integers(-25, 25, (h, w, c))).clip(0, 255).astype(np.uint8)
+        return img if c == 3 else img[..., 0]
+
+    files = []
+    for (h, w, c) in [(240, 320, 3), (256, 340, 1), (37, 53, 3), (100, 17, 1), (33, 2, 3), (1, 1, 3)]:
+        img = synth(h, w, c)
+        files.append(cv2.imencode(".jpg", img)[1].tobytes())                      # the reference's writer
+        b = io.BytesIO()
+        Image.fromarray(img).save(b, "JPEG", quality=60, subsampling=0)           # 4:4:4 (colour) / other tables
+        files.append(b.getvalue())
+    files.append(cv2.imencode(".jpg", synth(64, 83, 3), [cv2.IMWRITE_JPEG_RST_INTERVAL, 3])[1].tobytes())
+    files.append(cv2.imencode(".jpg", synth(64, 83, 1), [cv2.IMWRITE_JPEG_RST_INTERVAL, 5, cv2.IMWRITE_JPEG_OPTIMIZE, 1])[1].tobytes())
+    for f in files:
+        ref = np.asarray(Image.open(io.BytesIO(f)))
+        mine = J.decode(f)
+        assert mine.shape == ref.shape and np.array_equal(mine, ref)
+    b = io.BytesIO()
+    Image.fromarray(synth(32, 32, 3)).save(b, "JPEG", progressive=True)
+    with pytest.raises(J.JpegUnsupported):
+        J.decode(b.getvalue())
