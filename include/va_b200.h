@@ -174,6 +174,38 @@ va_status va_sgd_momentum(float* param, const float* grad, float* momentum_buf, 
 va_status va_transpose_bf16(const void* x, int n, int A, int B, void* y, va_stream_t stream);
 va_status va_f32_to_bf16(const float* x, long long n, void* y, va_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Baseline-JPEG decode into the image store.  Replaces Image.open(...) of
+ * SpatialDataset / TemporalDataset.__getitem__ (reference spatialModel.py:76-79, temporalModel.py:85-88) for the files
+ * cv2.imwrite writes (utils.py:116-120): 8-bit baseline sequential Huffman JPEG, one component or YCbCr 4:2:0 / 4:4:4.
+ * Pixels are bit-identical to Pillow's (libjpeg-turbo: islow IDCT, fancy h2v2 upsampling, 16-bit fixed-point YCbCr->RGB).
+ * The host parses the headers (video_analytics_b200/jpeg.py) and passes, per image, where the entropy-coded segment
+ * starts and which tables it uses; the whole files are in `bitstreams` (device).  Output: [H][W] (1 component) or
+ * [H][W][3] RGB u8 at out + out_offset -- e.g. image id * image_bytes of a va_preprocess store.
+ *   qtables: HOST uint16 [n_qtables][64] in NATURAL (row-major) order.
+ *   htables: HOST derived Huffman tables (jpeg_make_d_derived_tbl): maxcode[l] = largest code of length l or -1,
+ *            valoffset[l] = index of the first symbol of length l minus its code.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct va_jpeg_image {
+  unsigned long long scan_offset;    /* first entropy-coded byte, relative to `bitstreams` */
+  unsigned long long out_offset;     /* byte offset of the decoded image in `out` */
+  unsigned int scan_bytes;           /* bytes from scan_offset to the end of the file */
+  unsigned int restart_interval;     /* MCUs between RSTn markers (DRI), 0 = none */
+  unsigned short width, height;
+  unsigned char n_comp;              /* 1 or 3 */
+  unsigned char sampling;            /* 0 = one component, 1 = 4:4:4, 2 = 4:2:0 */
+  unsigned char qt[3], dc[3], ac[3]; /* table indices per component */
+  unsigned char pad[9];
+} va_jpeg_image;                     /* 48 bytes */
+typedef struct va_jpeg_huff {
+  int maxcode[18];
+  int valoffset[17];
+  unsigned char huffval[256];
+  int pad;
+} va_jpeg_huff;                      /* 400 bytes */
+va_status va_jpeg_decode(const uint8_t* bitstreams, const va_jpeg_image* images, int n_images, const uint16_t* qtables,
+                         int n_qtables, const va_jpeg_huff* htables, int n_htables, uint8_t* out, va_stream_t stream);
+
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,

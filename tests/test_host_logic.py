@@ -213,3 +213,39 @@ def test_fastdiv_magic_numbers():
         for x in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1] + [rng.randrange(0, 1 << 31) for _ in range(200)]:
             q = x if d == 1 else ((x * mul) >> 32) >> shr
             assert q == x // d, (d, x)
+
+
+def test_jpeg_header_parser_and_huffman_tables_match_oracle():
+    """Host side of the JPEG row: the product's marker walk / canonical-table derivation vs the oracle's restatement of
+    libjpeg (jdmarker.c / jpeg_make_d_derived_tbl) on files from cv2 and Pillow."""
+    import io
+    import cv2
+    import numpy as np
+    from PIL import Image
+    from oracle import jpeg_baseline as J
+    from video_analytics_b200 import jpeg
+    rng = np.random.default_rng(2)
+    files = [cv2.imencode(".jpg", rng.integers(0, 256, (40, 56, 3)).astype(np.uint8))[1].tobytes(),
+             cv2.imencode(".jpg", rng.integers(0, 256, (33, 21)).astype(np.uint8), [cv2.IMWRITE_JPEG_OPTIMIZE, 1,
+                                                                                      cv2.IMWRITE_JPEG_RST_INTERVAL, 2])[1].tobytes()]
+    b = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, (24, 24, 3)).astype(np.uint8)).save(b, "JPEG", quality=30, subsampling=0)
+    files.append(b.getvalue())
+    for f in files:
+        mine, ref = jpeg.parse_header(f), J.parse_header(f)
+        assert (mine.height, mine.width, mine.n_comp) == (ref.height, ref.width, len(ref.comps))
+        assert mine.scan_offset == ref.scan_offset and mine.restart_interval == ref.restart_interval
+        for c, comp in enumerate(ref.comps):
+            assert np.array_equal(np.frombuffer(mine.qtables[c], dtype=np.uint16), ref.qt[comp.tq])
+            for cls, tid, raw in ((0, comp.td, mine.htables[c][0]), (1, comp.ta, mine.htables[c][1])):
+                t = jpeg._derive_huffman(raw[:16], raw[16:])
+                maxcode, valoffset = J.derive_table(*ref.huff[(cls, tid)])
+                assert np.array_equal(t["maxcode"][1:17], maxcode[1:17])
+                used = [l for l in range(1, 17) if maxcode[l] >= 0]
+                assert all(int(t["valoffset"][l]) == int(valoffset[l]) for l in used)
+                assert np.array_equal(t["huffval"][:len(ref.huff[(cls, tid)][1])], ref.huff[(cls, tid)][1])
+    batch = jpeg.JpegBatch(files, [0, 10000, 20000])
+    assert batch.images["sampling"].tolist() == [2, 0, 1] and batch.qtables.shape[1] == 64
+    assert int(batch.images["scan_offset"][1]) == len(files[0]) + jpeg.parse_header(files[1]).scan_offset
+    with pytest.raises(jpeg.JpegFormatError):
+        jpeg.parse_header(b"\x89PNG....")

@@ -504,6 +504,18 @@ va_status va_f32_to_bf16(const float* x, long long n, void* y, va_stream_t strea
   return VA_OK;
 }
 
+va_status va_jpeg_decode(const uint8_t* bitstreams, const va_jpeg_image* images, int n_images, const uint16_t* qtables,
+                         int n_qtables, const va_jpeg_huff* htables, int n_htables, uint8_t* out, va_stream_t stream) {
+  if (n_images == 0) return VA_OK;
+  if (!bitstreams || !images || !qtables || !htables || !out) return fail(VA_ERR_INVALID, "va_jpeg_decode: NULL argument");
+  if (n_images < 0 || n_qtables <= 0 || n_htables <= 0) return fail(VA_ERR_INVALID, "va_jpeg_decode: bad counts");
+  if (va_status s = require_sm100()) return s;
+  const char* e = va::jpeg_decode_run(bitstreams, images, n_images, qtables, n_qtables, htables, n_htables, out,
+                                      static_cast<cudaStream_t>(stream));
+  if (e) return fail(VA_ERR_INVALID, "va_jpeg_decode: %s", e);
+  return VA_OK;
+}
+
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c, uint32_t seed,
                         uint32_t first_id, va_stream_t stream) {
   if (!images) return fail(VA_ERR_INVALID, "va_synth_fill: NULL");

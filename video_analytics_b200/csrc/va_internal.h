@@ -53,6 +53,11 @@ cudaError_t launch_pack_fc_w_t(const float* w, void* out, int n_out, int n_in, c
 const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Cout, int Cin, int cin_pad, int ks,
                       float* dwt_ws, float* dw, cudaStream_t st);
 
+// ---- JPEG decode (va_jpeg.cu)
+const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_host, int n_images,
+                            const unsigned short* qtables_host, int n_q, const void* htables_host, int n_h,
+                            unsigned char* out, cudaStream_t st);
+
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
 struct ConvLayerDesc {
   const void* x;        // bf16 NHWC [n][H][W][cin_pad]

@@ -1,0 +1,425 @@
+// Baseline-JPEG decode on the GPU, bit-exact with the reference's loader.
+//
+// The reference decodes every frame / flow image with Pillow's Image.open (Sheet03/spatialModel.py:76-79,
+// temporalModel.py:85-88) on files written by cv2.imwrite (utils.py:116-120): 8-bit baseline sequential JPEG, YCbCr 4:2:0
+// (frames) or one component (flow images), Huffman coded.  Pillow's libjpeg-turbo default path is reproduced step by
+// step so that the pixels entering K1 are the reference's pixels:
+//   jpeg_huffman_kernel   jdhuff.c decode_mcu -- canonical codes (maxcode / valoffset), RECEIVE/EXTEND, DC prediction,
+//                         ZRL / EOB, 0xFF00 unstuffing, restart markers.  The bit stream of an image is inherently serial:
+//                         one THREAD per image (a batch has 10^3..10^4 images), non-zero coefficients scattered into a
+//                         zero-filled int16 workspace.
+//   jpeg_idct_kernel      dequantise + jidctint.c jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2) + range limit: one thread
+//                         per 8x8 block.  One-component images are written straight into the image store.
+//   jpeg_color_kernel     jdsample.c h2v2_fancy_upsample (triangle filter, biases 8/7, replicated context rows; plain
+//                         replication when the chroma plane is <= 2 samples wide) + jdcolor.c ycc_rgb_convert
+//                         (16-bit fixed point): one thread per output pixel, interleaved RGB out.
+// Header parsing (markers, DQT/DHT/SOF0/SOS/DRI) is host work (video_analytics_b200/jpeg.py).
+#include "va_internal.h"
+
+#include <stdio.h>
+
+#include <vector>
+
+namespace va {
+
+struct JpegImage {            // mirrors va_jpeg_image (include/va_b200.h) field for field
+  unsigned long long scan_offset;    // first entropy-coded byte, relative to `bitstreams`
+  unsigned long long out_offset;     // byte offset of the decoded image [H][W][n_comp] in `out`
+  unsigned int scan_bytes;           // bytes from scan_offset to the end of the file
+  unsigned int restart_interval;     // MCUs between RSTn markers, 0 = none
+  unsigned short width, height;
+  unsigned char n_comp;              // 1 or 3
+  unsigned char sampling;            // 0 = one component, 1 = 4:4:4, 2 = 4:2:0
+  unsigned char qt[3], dc[3], ac[3]; // table indices per component
+  unsigned char pad[9];
+};
+static_assert(sizeof(JpegImage) == 48, "JpegImage layout");
+
+struct JpegHuff {             // derived table (jpeg_make_d_derived_tbl)
+  int maxcode[18];            // largest code of length l (-1 if none); [17] = sentinel
+  int valoffset[17];          // huffval index = code + valoffset[l]
+  unsigned char huffval[256];
+  int pad;
+};
+static_assert(sizeof(JpegHuff) == 400, "JpegHuff layout");
+
+struct JpegGeom {             // per image, computed on the host side of va_jpeg_decode
+  unsigned long long coef_block0;    // first block of this image in the coefficient workspace
+  unsigned long long plane_offset;   // byte offset of this image's component planes (colour images only)
+  int mcux, mcuy;                    // MCUs per row / column
+  int bw[3], bh[3];                  // blocks per row / column of each component plane
+};
+
+__constant__ unsigned char c_natural[80] = {
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55,
+    62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};      // + 16 safety entries (libjpeg)
+
+// ------------------------------------------------------------------------------------------------ entropy decoding
+struct BitReader {
+  const unsigned char* p;
+  const unsigned char* end;
+  unsigned long long buf;
+  int nbits;
+  bool marker;
+
+  __device__ __forceinline__ void fill() {
+    while (nbits <= 56) {
+      unsigned int c = 0;
+      if (!marker && p < end) {
+        c = __ldg(p);
+        if (c == 0xFF) {
+          const unsigned int c2 = (p + 1 < end) ? __ldg(p + 1) : 0xD9u;
+          if (c2 == 0) p += 2;
+          else { c = 0; marker = true; }          // a marker: feed zero bits from here on (jpeg_fill_bit_buffer)
+        } else {
+          ++p;
+        }
+      }
+      buf = (buf << 8) | c;
+      nbits += 8;
+    }
+  }
+  __device__ __forceinline__ unsigned int peek16() {
+    if (nbits < 16) fill();
+    return (unsigned int)(buf >> (nbits - 16)) & 0xFFFFu;
+  }
+  __device__ __forceinline__ unsigned int get(int n) {
+    if (n == 0) return 0;
+    if (nbits < n) fill();
+    nbits -= n;
+    return (unsigned int)(buf >> nbits) & ((1u << n) - 1u);
+  }
+  __device__ __forceinline__ int decode(const JpegHuff* __restrict__ t) {
+    const unsigned int look = peek16();
+    int l = 1;
+    int code = (int)(look >> 15);
+    while (l < 17 && code > __ldg(&t->maxcode[l])) {
+      ++l;
+      code = (int)(look >> (16 - l));
+    }
+    if (l > 16) { nbits -= 16; return 0; }        // corrupt data: libjpeg warns and returns 0
+    nbits -= l;
+    return (int)__ldg(&t->huffval[(code + __ldg(&t->valoffset[l])) & 255]);
+  }
+  __device__ __forceinline__ void restart() {     // process_restart: drop the partial byte, skip RSTn
+    nbits = 0; buf = 0; marker = false;
+    while (p + 1 < end && !(__ldg(p) == 0xFF && __ldg(p + 1) >= 0xD0 && __ldg(p + 1) <= 0xD7)) ++p;
+    p += 2;
+  }
+};
+
+__device__ __forceinline__ int jpeg_extend(unsigned int v, int s) {
+  return (int)v < (1 << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v;
+}
+
+__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* __restrict__ bitstreams,
+                                                          const JpegImage* __restrict__ images,
+                                                          const JpegGeom* __restrict__ geom,
+                                                          const JpegHuff* __restrict__ htab, int n_images,
+                                                          short* __restrict__ coef) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n_images) return;
+  const JpegImage im = images[img];
+  const JpegGeom g = geom[img];
+  BitReader br;
+  br.p = bitstreams + im.scan_offset;
+  br.end = br.p + im.scan_bytes;
+  br.buf = 0; br.nbits = 0; br.marker = false;
+  int pred[3] = {0, 0, 0};
+  // blocks of component c inside one MCU: (hs x vs)
+  const int hs0 = im.sampling == 2 ? 2 : 1, vs0 = hs0;
+  unsigned long long plane0[3];
+  plane0[0] = g.coef_block0;
+  plane0[1] = plane0[0] + (unsigned long long)g.bw[0] * g.bh[0];
+  plane0[2] = plane0[1] + (unsigned long long)g.bw[1] * g.bh[1];
+  unsigned int todo = im.restart_interval;
+  for (int my = 0; my < g.mcuy; ++my) {
+    for (int mx = 0; mx < g.mcux; ++mx) {
+      if (im.restart_interval) {
+        if (todo == 0) {
+          br.restart();
+          pred[0] = pred[1] = pred[2] = 0;
+          todo = im.restart_interval;
+        }
+        --todo;
+      }
+      for (int c = 0; c < im.n_comp; ++c) {
+        const int hs = c == 0 ? hs0 : 1, vs = c == 0 ? vs0 : 1;
+        const JpegHuff* dct = htab + im.dc[c];
+        const JpegHuff* act = htab + im.ac[c];
+        for (int by = 0; by < vs; ++by) {
+          for (int bx = 0; bx < hs; ++bx) {
+            short* blk = coef + (plane0[c] + (unsigned long long)(my * vs + by) * g.bw[c] + (mx * hs + bx)) * 64;
+            int s = br.decode(dct);
+            if (s) pred[c] += jpeg_extend(br.get(s), s);
+            blk[0] = (short)pred[c];
+            int k = 1;
+            while (k < 64) {
+              const int rs = br.decode(act);
+              const int r = rs >> 4;
+              s = rs & 15;
+              if (s) {
+                k += r;
+                blk[c_natural[k < 80 ? k : 79]] = (short)jpeg_extend(br.get(s), s);
+                ++k;
+              } else if (r == 15) {
+                k += 16;
+              } else {
+                break;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ IDCT
+#define JF_0_298631336 2446
+#define JF_0_390180644 3196
+#define JF_0_541196100 4433
+#define JF_0_765366865 6270
+#define JF_0_899976223 7373
+#define JF_1_175875602 9633
+#define JF_1_501321110 12299
+#define JF_1_847759065 15137
+#define JF_1_961570560 16069
+#define JF_2_053119869 16819
+#define JF_2_562915447 20995
+#define JF_3_072711026 25172
+
+// one 1-D pass of jpeg_idct_islow on d[0..7] (stride 1 in registers); SHIFT = descale amount
+template <int SHIFT>
+__device__ __forceinline__ void idct8(int (&d)[8]) {
+  int z2 = d[2], z3 = d[6];
+  int z1 = (z2 + z3) * JF_0_541196100;
+  const int tmp2 = z1 + z3 * (-JF_1_847759065);
+  const int tmp3 = z1 + z2 * JF_0_765366865;
+  const int tmp0 = (d[0] + d[4]) << 13;
+  const int tmp1 = (d[0] - d[4]) << 13;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  int t0 = d[7], t1 = d[5], t2 = d[3], t3 = d[1];
+  z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2;
+  int z4 = t1 + t3;
+  const int z5 = (z3 + z4) * JF_1_175875602;
+  t0 *= JF_0_298631336; t1 *= JF_2_053119869; t2 *= JF_3_072711026; t3 *= JF_1_501321110;
+  z1 *= -JF_0_899976223; z2 *= -JF_2_562915447;
+  z3 = z3 * (-JF_1_961570560) + z5;
+  z4 = z4 * (-JF_0_390180644) + z5;
+  t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
+  constexpr int R = 1 << (SHIFT - 1);
+  d[0] = (tmp10 + t3 + R) >> SHIFT; d[7] = (tmp10 - t3 + R) >> SHIFT;
+  d[1] = (tmp11 + t2 + R) >> SHIFT; d[6] = (tmp11 - t2 + R) >> SHIFT;
+  d[2] = (tmp12 + t1 + R) >> SHIFT; d[5] = (tmp12 - t1 + R) >> SHIFT;
+  d[3] = (tmp13 + t0 + R) >> SHIFT; d[4] = (tmp13 - t0 + R) >> SHIFT;
+}
+
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(const short* __restrict__ coef, const JpegImage* __restrict__ images,
+                                                        const JpegGeom* __restrict__ geom,
+                                                        const unsigned short* __restrict__ qtab, int n_images,
+                                                        unsigned long long total_blocks, unsigned char* __restrict__ planes,
+                                                        unsigned char* __restrict__ out) {
+  const unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= total_blocks) return;
+  // image of this block: last image whose first block <= b
+  int lo = 0, hi = n_images - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (geom[mid].coef_block0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const JpegImage im = images[lo];
+  const JpegGeom g = geom[lo];
+  unsigned long long local = b - g.coef_block0;
+  int c = 0;
+  while (c < 2 && local >= (unsigned long long)g.bw[c] * g.bh[c]) { local -= (unsigned long long)g.bw[c] * g.bh[c]; ++c; }
+  const int by = (int)(local / g.bw[c]), bx = (int)(local % g.bw[c]);
+  const unsigned short* q = qtab + im.qt[c] * 64;
+  const uint4* src = reinterpret_cast<const uint4*>(coef + b * 64);
+  int ws[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const uint4 v = __ldg(src + r);
+    const short* s = reinterpret_cast<const short*>(&v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ws[r][k] = (int)s[k] * (int)__ldg(q + r * 8 + k);     // DEQUANTIZE
+  }
+  // pass 1: columns
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int col[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) col[r] = ws[r][k];
+    idct8<13 - 2>(col);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ws[r][k] = col[r];
+  }
+  // pass 2: rows, range limit, store
+  unsigned char* dst;
+  int stride, wlim, hlim;
+  if (im.n_comp == 1) {
+    dst = out + im.out_offset;
+    stride = im.width; wlim = im.width; hlim = im.height;
+  } else {
+    unsigned long long off = g.plane_offset;
+    for (int k = 0; k < c; ++k) off += (unsigned long long)g.bw[k] * g.bh[k] * 64;
+    dst = planes + off;
+    stride = g.bw[c] * 8; wlim = stride; hlim = g.bh[c] * 8;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    idct8<13 + 2 + 3>(ws[r]);
+    const int y = by * 8 + r;
+    if (y < hlim) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int x = bx * 8 + k;
+        int v = ((ws[r][k] + 512) & 1023) - 512;          // range_limit[x & RANGE_MASK] ...
+        v = min(max(v + 128, 0), 255);                    // ... == clamp(x + CENTERJSAMPLE) on that window
+        if (x < wlim) dst[(size_t)y * stride + x] = (unsigned char)v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsample + colour
+__device__ __forceinline__ int fancy_h2v2(const unsigned char* __restrict__ p, int stride, int dw, int dh, int y, int x) {
+  const int i = y >> 1, j = x >> 1;
+  if (dw <= 2) return p[(size_t)i * stride + j];                            // h2v2_upsample (replication)
+  const int far_i = (y & 1) ? min(i + 1, dh - 1) : max(i - 1, 0);
+  const unsigned char* r0 = p + (size_t)i * stride;
+  const unsigned char* r1 = p + (size_t)far_i * stride;
+  const int cur = 3 * r0[j] + r1[j];
+  if (x & 1) {
+    const int jn = min(j + 1, dw - 1);
+    return (cur * 3 + (3 * r0[jn] + r1[jn]) + 7) >> 4;
+  }
+  const int jl = max(j - 1, 0);
+  return (cur * 3 + (3 * r0[jl] + r1[jl]) + 8) >> 4;
+}
+
+__global__ void __launch_bounds__(256) jpeg_color_kernel(const int* __restrict__ color_ids, const JpegImage* __restrict__ images,
+                                                         const JpegGeom* __restrict__ geom,
+                                                         const unsigned char* __restrict__ planes,
+                                                         unsigned char* __restrict__ out) {
+  const int img = color_ids[blockIdx.y];
+  const JpegImage im = images[img];
+  const JpegGeom g = geom[img];
+  const int W = im.width, H = im.height;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= W * H) return;
+  const int y = pix / W, x = pix - y * W;
+  const unsigned char* py = planes + g.plane_offset;
+  const unsigned char* pcb = py + (size_t)g.bw[0] * g.bh[0] * 64;
+  const unsigned char* pcr = pcb + (size_t)g.bw[1] * g.bh[1] * 64;
+  const int yy = py[(size_t)y * (g.bw[0] * 8) + x];
+  int cb, cr;
+  if (im.sampling == 2) {
+    const int dw = (W + 1) >> 1, dh = (H + 1) >> 1;
+    cb = fancy_h2v2(pcb, g.bw[1] * 8, dw, dh, y, x);
+    cr = fancy_h2v2(pcr, g.bw[2] * 8, dw, dh, y, x);
+  } else {
+    cb = pcb[(size_t)y * (g.bw[1] * 8) + x];
+    cr = pcr[(size_t)y * (g.bw[2] * 8) + x];
+  }
+  // jdcolor.c build_ycc_rgb_table: FIX(x) = (int)(x * 65536 + 0.5), ONE_HALF = 32768, arithmetic right shifts
+  const int xb = cb - 128, xr = cr - 128;
+  const int r = yy + ((91881 * xr + 32768) >> 16);
+  const int gg = yy + ((-22554 * xb + 32768 + (-46802) * xr) >> 16);
+  const int bl = yy + ((116130 * xb + 32768) >> 16);
+  unsigned char* o = out + im.out_offset + ((size_t)y * W + x) * 3;
+  o[0] = (unsigned char)min(max(r, 0), 255);
+  o[1] = (unsigned char)min(max(gg, 0), 255);
+  o[2] = (unsigned char)min(max(bl, 0), 255);
+}
+
+// ------------------------------------------------------------------------------------------------ host entry
+namespace {
+thread_local char g_jerr[256];
+}
+
+const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_host, int n_images, const unsigned short* qtables_host,
+                            int n_q, const void* htables_host, int n_h, unsigned char* out, cudaStream_t st) {
+  if (n_images <= 0) return nullptr;
+  const JpegImage* im = static_cast<const JpegImage*>(images_host);
+  std::vector<JpegGeom> geom((size_t)n_images);
+  std::vector<int> color_ids;
+  unsigned long long blocks = 0, plane_bytes = 0;
+  int max_pix = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const JpegImage& m = im[i];
+    JpegGeom& g = geom[(size_t)i];
+    if (m.width == 0 || m.height == 0) { snprintf(g_jerr, sizeof(g_jerr), "image %d has zero size", i); return g_jerr; }
+    if (!((m.n_comp == 1 && m.sampling == 0) || (m.n_comp == 3 && (m.sampling == 1 || m.sampling == 2)))) {
+      snprintf(g_jerr, sizeof(g_jerr), "image %d: unsupported component layout (n_comp %d, sampling %d)", i, m.n_comp, m.sampling);
+      return g_jerr;
+    }
+    for (int c = 0; c < m.n_comp; ++c)
+      if (m.qt[c] >= n_q || m.dc[c] >= n_h || m.ac[c] >= n_h) {
+        snprintf(g_jerr, sizeof(g_jerr), "image %d: table index out of range", i);
+        return g_jerr;
+      }
+    const int mcu = m.sampling == 2 ? 16 : 8;
+    g.mcux = (m.width + mcu - 1) / mcu;
+    g.mcuy = (m.height + mcu - 1) / mcu;
+    const int f = m.sampling == 2 ? 2 : 1;
+    g.bw[0] = g.mcux * f; g.bh[0] = g.mcuy * f;
+    g.bw[1] = g.bw[2] = m.n_comp == 3 ? g.mcux : 0;
+    g.bh[1] = g.bh[2] = m.n_comp == 3 ? g.mcuy : 0;
+    g.coef_block0 = blocks;
+    g.plane_offset = plane_bytes;
+    const unsigned long long nb = (unsigned long long)g.bw[0] * g.bh[0] + 2ull * g.bw[1] * g.bh[1];
+    blocks += nb;
+    if (m.n_comp == 3) {
+      plane_bytes += nb * 64;
+      color_ids.push_back(i);
+      if ((int)m.width * (int)m.height > max_pix) max_pix = (int)m.width * (int)m.height;
+    }
+  }
+  if (color_ids.size() > 65535) return "more than 65535 colour images in one call";
+  short* d_coef = nullptr;
+  unsigned char* d_planes = nullptr;
+  JpegImage* d_im = nullptr;
+  JpegGeom* d_geom = nullptr;
+  JpegHuff* d_h = nullptr;
+  unsigned short* d_q = nullptr;
+  int* d_cid = nullptr;
+  cudaError_t e = cudaSuccess;
+#define JCK(x) if ((e = (x)) != cudaSuccess) { snprintf(g_jerr, sizeof(g_jerr), "%s: %s", #x, cudaGetErrorString(e)); return g_jerr; }
+  JCK(cudaMallocAsync(&d_coef, blocks * 64 * sizeof(short), st));
+  JCK(cudaMemsetAsync(d_coef, 0, blocks * 64 * sizeof(short), st));
+  if (plane_bytes) JCK(cudaMallocAsync(&d_planes, plane_bytes, st));
+  JCK(cudaMallocAsync(&d_im, sizeof(JpegImage) * n_images, st));
+  JCK(cudaMallocAsync(&d_geom, sizeof(JpegGeom) * n_images, st));
+  JCK(cudaMallocAsync(&d_h, sizeof(JpegHuff) * n_h, st));
+  JCK(cudaMallocAsync(&d_q, 128 * n_q, st));
+  JCK(cudaMemcpyAsync(d_im, im, sizeof(JpegImage) * n_images, cudaMemcpyHostToDevice, st));
+  JCK(cudaMemcpyAsync(d_geom, geom.data(), sizeof(JpegGeom) * n_images, cudaMemcpyHostToDevice, st));
+  JCK(cudaMemcpyAsync(d_h, htables_host, sizeof(JpegHuff) * n_h, cudaMemcpyHostToDevice, st));
+  JCK(cudaMemcpyAsync(d_q, qtables_host, 128 * n_q, cudaMemcpyHostToDevice, st));
+  if (!color_ids.empty()) {
+    JCK(cudaMallocAsync(&d_cid, sizeof(int) * color_ids.size(), st));
+    JCK(cudaMemcpyAsync(d_cid, color_ids.data(), sizeof(int) * color_ids.size(), cudaMemcpyHostToDevice, st));
+  }
+  // (copies from pageable host memory return once the source has been staged, so the host vectors may go out of scope)
+  count_launch();
+  jpeg_huffman_kernel<<<(n_images + 31) / 32, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, n_images, d_coef);
+  JCK(cudaGetLastError());
+  count_launch();
+  jpeg_idct_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, st>>>(d_coef, d_im, d_geom, d_q, n_images, blocks, d_planes, out);
+  JCK(cudaGetLastError());
+  if (!color_ids.empty()) {
+    count_launch();
+    jpeg_color_kernel<<<dim3((max_pix + 255) / 256, (unsigned)color_ids.size()), 256, 0, st>>>(d_cid, d_im, d_geom, d_planes, out);
+    JCK(cudaGetLastError());
+  }
+  cudaFreeAsync(d_coef, st);
+  if (d_planes) cudaFreeAsync(d_planes, st);
+  cudaFreeAsync(d_im, st); cudaFreeAsync(d_geom, st); cudaFreeAsync(d_h, st); cudaFreeAsync(d_q, st);
+  if (d_cid) cudaFreeAsync(d_cid, st);
+#undef JCK
+  return nullptr;
+}
+
+}  // namespace va
