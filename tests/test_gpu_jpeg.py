@@ -100,3 +100,41 @@ def test_batch_of_flow_images_and_errors():
         jpeg.decode_into(files[:1], torch.empty(10, dtype=torch.uint8, device="cuda"), [0])     # does not fit
     with pytest.raises(VAError):
         jpeg.decode_into(files[:1], torch.empty(256 * 340, dtype=torch.uint8), [0])              # CPU tensor: no fallback
+
+
+def test_many_files_with_their_own_huffman_tables():
+    """Optimised-Huffman files carry private tables; decode_into splits the batch (<= 8 tables per kernel call)."""
+    import cv2
+    from PIL import Image
+    from video_analytics_b200 import jpeg
+    rng = np.random.default_rng(4)
+    files = [cv2.imencode(".jpg", _synth(rng, 40 + 3 * k, 56 + k, 3 if k % 2 else 1), [cv2.IMWRITE_JPEG_OPTIMIZE, 1,
+                                                                                      cv2.IMWRITE_JPEG_QUALITY, 50 + 4 * k])[1].tobytes()
+             for k in range(9)]
+    for f, o in zip(files, jpeg.decode(files)):
+        assert np.array_equal(o.cpu().numpy(), np.asarray(Image.open(io.BytesIO(f))))
+
+
+def test_store_from_jpeg_files_runs_the_protocol():
+    """Frames and flow images written the reference's way -> DeviceStore.from_jpeg_files -> the 25x10 evaluation: the
+    store holds Pillow's pixels, so the index tables / K1 / networks see what the reference's loader would feed."""
+    import cv2
+    from PIL import Image
+    from oracle import synth
+    from video_analytics_b200.store import DeviceStore, make_layout
+    lay = make_layout(1)
+    rgb, flow = synth.build_store_numpy(lay)
+    rgb = rgb.reshape(-1, *lay.rgb_shape)
+    flow = flow.reshape(-1, lay.flow_shape[0], lay.flow_shape[1])
+    rgb_files = [cv2.imencode(".jpg", f[..., ::-1])[1].tobytes() for f in rgb]          # cv2 takes BGR
+    flow_files = [cv2.imencode(".jpg", f)[1].tobytes() for f in flow]
+    store = DeviceStore.from_jpeg_files(lay, rgb_files, flow_files)
+    torch.cuda.synchronize()
+    got_rgb = store.rgb.cpu().numpy().reshape(rgb.shape)
+    got_flow = store.flow.cpu().numpy().reshape(flow.shape)
+    for k in (0, len(rgb_files) // 2, len(rgb_files) - 1):
+        assert np.array_equal(got_rgb[k], np.asarray(Image.open(io.BytesIO(rgb_files[k]))))
+    for k in (0, len(flow_files) // 3, len(flow_files) - 1):
+        assert np.array_equal(got_flow[k], np.asarray(Image.open(io.BytesIO(flow_files[k]))))
+    with pytest.raises(ValueError):
+        DeviceStore.from_jpeg_files(lay, flow_files[:1], [])                            # wrong size for the RGB store

@@ -56,6 +56,20 @@ __constant__ unsigned char c_natural[80] = {
     62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};      // + 16 safety entries (libjpeg)
 
 // ------------------------------------------------------------------------------------------------ entropy decoding
+// One thread decodes one image; a warp therefore runs 32 independent serial decoders, and what matters is (a) the
+// dependent-instruction latency per symbol and (b) that the lanes stay converged.  Both are served by a BRANCH-FREE code
+// length search: canonical codes of length l occupy the 16-bit-left-aligned interval below bound[l] = (maxcode[l]+1) <<
+// (16-l) (unused lengths inherit the previous bound), so  l = 1 + #{ l' : look >= bound[l'] }  -- 16 independent
+// shared-memory reads and compares instead of a data-dependent loop over global memory.
+constexpr int kJpegMaxTables = 8;            // Huffman tables kept in shared memory per block
+
+struct HuffSmem {
+  unsigned int bound[kJpegMaxTables][17];    // [t][l], l = 1..16; [0] unused
+  int valoffset[kJpegMaxTables][17];
+  unsigned char huffval[kJpegMaxTables][256];
+  unsigned char natural[80];
+};
+
 struct BitReader {
   const unsigned char* p;
   const unsigned char* end;
@@ -63,7 +77,7 @@ struct BitReader {
   int nbits;
   bool marker;
 
-  __device__ __forceinline__ void fill() {
+  __device__ __forceinline__ void fill_slow() {            // byte-wise: 0xFF00 unstuffing, stop at markers
     while (nbits <= 56) {
       unsigned int c = 0;
       if (!marker && p < end) {
@@ -80,27 +94,34 @@ struct BitReader {
       nbits += 8;
     }
   }
-  __device__ __forceinline__ unsigned int peek16() {
-    if (nbits < 16) fill();
-    return (unsigned int)(buf >> (nbits - 16)) & 0xFFFFu;
+  // keep at least 32 valid bits: four independent byte loads, inserted at once unless one of them is 0xFF
+  __device__ __forceinline__ void refill() {
+    if (nbits >= 32) return;
+    if (!marker && p + 4 <= end) {
+      const unsigned int b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+      if (b0 != 0xFF && b1 != 0xFF && b2 != 0xFF && b3 != 0xFF) {
+        buf = (buf << 32) | (unsigned long long)((b0 << 24) | (b1 << 16) | (b2 << 8) | b3);
+        nbits += 32;
+        p += 4;
+        return;
+      }
+    }
+    fill_slow();
   }
-  __device__ __forceinline__ unsigned int get(int n) {
-    if (n == 0) return 0;
-    if (nbits < n) fill();
+  __device__ __forceinline__ unsigned int get(int n) {     // n <= 16; caller keeps nbits >= 32 via refill()
     nbits -= n;
     return (unsigned int)(buf >> nbits) & ((1u << n) - 1u);
   }
-  __device__ __forceinline__ int decode(const JpegHuff* __restrict__ t) {
-    const unsigned int look = peek16();
+  __device__ __forceinline__ int decode(const HuffSmem& h, int t) {
+    refill();
+    const unsigned int look = (unsigned int)(buf >> (nbits - 16)) & 0xFFFFu;
     int l = 1;
-    int code = (int)(look >> 15);
-    while (l < 17 && code > __ldg(&t->maxcode[l])) {
-      ++l;
-      code = (int)(look >> (16 - l));
-    }
+#pragma unroll
+    for (int k = 1; k <= 16; ++k) l += (look >= h.bound[t][k]) ? 1 : 0;
     if (l > 16) { nbits -= 16; return 0; }        // corrupt data: libjpeg warns and returns 0
     nbits -= l;
-    return (int)__ldg(&t->huffval[(code + __ldg(&t->valoffset[l])) & 255]);
+    const int code = (int)(look >> (16 - l));
+    return (int)h.huffval[t][(code + h.valoffset[t][l]) & 255];
   }
   __device__ __forceinline__ void restart() {     // process_restart: drop the partial byte, skip RSTn
     nbits = 0; buf = 0; marker = false;
@@ -116,8 +137,26 @@ __device__ __forceinline__ int jpeg_extend(unsigned int v, int s) {
 __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* __restrict__ bitstreams,
                                                           const JpegImage* __restrict__ images,
                                                           const JpegGeom* __restrict__ geom,
-                                                          const JpegHuff* __restrict__ htab, int n_images,
+                                                          const JpegHuff* __restrict__ htab, int n_tables, int n_images,
                                                           short* __restrict__ coef) {
+  __shared__ HuffSmem h;
+  for (int idx = threadIdx.x; idx < n_tables * 17; idx += blockDim.x) {
+    const int t = idx / 17, l = idx % 17;
+    h.valoffset[t][l] = htab[t].valoffset[l];
+  }
+  for (int idx = threadIdx.x; idx < n_tables * 256; idx += blockDim.x) h.huffval[idx >> 8][idx & 255] = htab[idx >> 8].huffval[idx & 255];
+  for (int idx = threadIdx.x; idx < 80; idx += blockDim.x) h.natural[idx] = c_natural[idx];
+  if (threadIdx.x < n_tables) {
+    const int t = threadIdx.x;
+    unsigned int prev = 0;
+    h.bound[t][0] = 0;
+    for (int l = 1; l <= 16; ++l) {
+      const int mc = htab[t].maxcode[l];
+      if (mc >= 0) prev = (unsigned int)(mc + 1) << (16 - l);
+      h.bound[t][l] = prev;
+    }
+  }
+  __syncthreads();
   const int img = blockIdx.x * blockDim.x + threadIdx.x;
   if (img >= n_images) return;
   const JpegImage im = images[img];
@@ -146,22 +185,22 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* _
       }
       for (int c = 0; c < im.n_comp; ++c) {
         const int hs = c == 0 ? hs0 : 1, vs = c == 0 ? vs0 : 1;
-        const JpegHuff* dct = htab + im.dc[c];
-        const JpegHuff* act = htab + im.ac[c];
+        const int dct = im.dc[c], act = im.ac[c];
         for (int by = 0; by < vs; ++by) {
           for (int bx = 0; bx < hs; ++bx) {
             short* blk = coef + (plane0[c] + (unsigned long long)(my * vs + by) * g.bw[c] + (mx * hs + bx)) * 64;
-            int s = br.decode(dct);
-            if (s) pred[c] += jpeg_extend(br.get(s), s);
+            int s = br.decode(h, dct);
+            if (s) { br.refill(); pred[c] += jpeg_extend(br.get(s), s); }
             blk[0] = (short)pred[c];
             int k = 1;
             while (k < 64) {
-              const int rs = br.decode(act);
+              const int rs = br.decode(h, act);
               const int r = rs >> 4;
               s = rs & 15;
               if (s) {
                 k += r;
-                blk[c_natural[k < 80 ? k : 79]] = (short)jpeg_extend(br.get(s), s);
+                br.refill();
+                blk[h.natural[k < 80 ? k : 79]] = (short)jpeg_extend(br.get(s), s);
                 ++k;
               } else if (r == 15) {
                 k += 16;
@@ -378,6 +417,10 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
     }
   }
   if (color_ids.size() > 65535) return "more than 65535 colour images in one call";
+  if (n_h > kJpegMaxTables) {
+    snprintf(g_jerr, sizeof(g_jerr), "%d distinct Huffman tables in one call (at most %d; decode in smaller batches)", n_h, kJpegMaxTables);
+    return g_jerr;
+  }
   short* d_coef = nullptr;
   unsigned char* d_planes = nullptr;
   JpegImage* d_im = nullptr;
@@ -404,7 +447,7 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
   }
   // (copies from pageable host memory return once the source has been staged, so the host vectors may go out of scope)
   count_launch();
-  jpeg_huffman_kernel<<<(n_images + 31) / 32, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, n_images, d_coef);
+  jpeg_huffman_kernel<<<(n_images + 31) / 32, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, n_h, n_images, d_coef);
   JCK(cudaGetLastError());
   count_launch();
   jpeg_idct_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, st>>>(d_coef, d_im, d_geom, d_q, n_images, blocks, d_planes, out);

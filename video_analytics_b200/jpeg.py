@@ -29,6 +29,9 @@ HUFF_DTYPE = np.dtype([("maxcode", "<i4", (18,)), ("valoffset", "<i4", (17,)), (
 assert IMAGE_DTYPE.itemsize == 48 and HUFF_DTYPE.itemsize == 400
 
 
+MAX_HUFF_TABLES_PER_CALL = 8     # kJpegMaxTables of csrc/va_jpeg.cu: tables live in shared memory
+
+
 class JpegFormatError(VAError):
     """The file is not an 8-bit baseline sequential Huffman JPEG with 1 component or YCbCr 4:2:0 / 4:4:4."""
 
@@ -58,15 +61,20 @@ class ParsedJpeg:
                  "scan_offset")
 
 
+_HEADER_CACHE: Dict[tuple, tuple] = {}
+_LAST_HEADER: List[Optional[tuple]] = [None]
+
+
 def parse_header(data: bytes) -> ParsedJpeg:
-    """Walk the marker segments up to the first scan."""
+    """Walk the marker segments up to the first scan.  Files of one encoder / size / quality share every table, so the
+    table work is memoised on the raw DQT / DHT / SOF / SOS segments (a loader parses the same header thousands of times)."""
     if len(data) < 4 or data[0] != 0xFF or data[1] != 0xD8:
         raise JpegFormatError("not a JPEG file (no SOI marker)")
-    out = ParsedJpeg()
-    out.restart_interval = 0
-    qt: Dict[int, bytes] = {}
-    ht: Dict[Tuple[int, int], bytes] = {}
-    comps: List[Tuple[int, int, int, int]] = []
+    last = _LAST_HEADER[0]
+    if last is not None and data.startswith(last[0]):       # same bytes up to the scan as the previous file: same header
+        return last[1]
+    segs = []
+    restart_interval = 0
     i, n = 2, len(data)
     while i + 4 <= n:
         if data[i] != 0xFF:
@@ -78,7 +86,35 @@ def parse_header(data: bytes) -> ParsedJpeg:
         if m == 0x01 or 0xD0 <= m <= 0xD8:
             continue
         L = (data[i] << 8) | data[i + 1]
-        seg = data[i + 2:i + L]
+        if m in (0xDB, 0xC4, 0xC0, 0xC1, 0xDA):
+            segs.append((m, bytes(data[i + 2:i + L])))
+        elif m in (0xC2, 0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
+            raise JpegFormatError("SOF%d: progressive / lossless / arithmetic JPEGs are not what cv2.imwrite writes" % (m - 0xC0))
+        elif m == 0xDD:
+            restart_interval = (data[i + 2] << 8) | data[i + 3]
+        if m == 0xDA:
+            key = tuple(segs)
+            hit = _HEADER_CACHE.get(key)
+            if hit is None:
+                hit = _interpret_segments(segs)
+                if len(_HEADER_CACHE) < 4096:
+                    _HEADER_CACHE[key] = hit
+            out = ParsedJpeg()
+            out.width, out.height, out.n_comp, out.sampling, out.qtables, out.htables = hit
+            out.restart_interval = restart_interval
+            out.scan_offset = i + L
+            _LAST_HEADER[0] = (bytes(data[:out.scan_offset]), out)
+            return out
+        i += L
+    raise JpegFormatError("no scan (SOS) found")
+
+
+def _interpret_segments(segs) -> tuple:
+    qt: Dict[int, bytes] = {}
+    ht: Dict[Tuple[int, int], bytes] = {}
+    comps: List[Tuple[int, int, int, int]] = []
+    width = height = 0
+    for m, seg in segs:
         if m == 0xDB:
             j = 0
             while j < len(seg):
@@ -100,12 +136,8 @@ def parse_header(data: bytes) -> ParsedJpeg:
         elif m in (0xC0, 0xC1):
             if seg[0] != 8:
                 raise JpegFormatError("sample precision %d (8 expected)" % seg[0])
-            out.height, out.width = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4]
+            height, width = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4]
             comps = [(seg[6 + 3 * k], seg[7 + 3 * k] >> 4, seg[7 + 3 * k] & 15, seg[8 + 3 * k]) for k in range(seg[5])]
-        elif m in (0xC2, 0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
-            raise JpegFormatError("SOF%d: progressive / lossless / arithmetic JPEGs are not what cv2.imwrite writes" % (m - 0xC0))
-        elif m == 0xDD:
-            out.restart_interval = (seg[0] << 8) | seg[1]
         elif m == 0xDA:
             if not comps:
                 raise JpegFormatError("SOS before SOF")
@@ -114,21 +146,19 @@ def parse_header(data: bytes) -> ParsedJpeg:
             sel = {seg[1 + 2 * k]: seg[2 + 2 * k] for k in range(seg[0])}
             samp = [(c[1], c[2]) for c in comps]
             if len(comps) == 1:
-                out.n_comp, out.sampling = 1, 0
+                n_comp, sampling = 1, 0
             elif len(comps) == 3 and samp == [(2, 2), (1, 1), (1, 1)]:
-                out.n_comp, out.sampling = 3, 2
+                n_comp, sampling = 3, 2
             elif len(comps) == 3 and samp == [(1, 1), (1, 1), (1, 1)]:
-                out.n_comp, out.sampling = 3, 1
+                n_comp, sampling = 3, 1
             else:
                 raise JpegFormatError("component layout %r is not supported (1 component, 4:4:4 or 4:2:0)" % (samp,))
             try:
-                out.qtables = [qt[c[3]] for c in comps]
-                out.htables = [(ht[(0, sel[c[0]] >> 4)], ht[(1, sel[c[0]] & 15)]) for c in comps]
+                qtables = [qt[c[3]] for c in comps]
+                htables = [(ht[(0, sel[c[0]] >> 4)], ht[(1, sel[c[0]] & 15)]) for c in comps]
             except KeyError as e:
                 raise JpegFormatError("missing table %r" % (e.args[0],)) from None
-            out.scan_offset = i + L
-            return out
-        i += L
+            return width, height, n_comp, sampling, qtables, htables
     raise JpegFormatError("no scan (SOS) found")
 
 
@@ -138,60 +168,105 @@ class JpegBatch:
     def __init__(self, files: Sequence[bytes], out_offsets: Sequence[int]):
         assert len(files) == len(out_offsets)
         self.n = len(files)
-        self.images = np.zeros(self.n, dtype=IMAGE_DTYPE)
         q_index: Dict[bytes, int] = {}
         h_index: Dict[bytes, int] = {}
         h_tabs: List[np.ndarray] = []
+        table_rows: Dict[int, tuple] = {}          # id(header cache entry) -> per-component table indices
+        rows = []
         pos = 0
         self.sizes = []
-        for k, (f, off) in enumerate(zip(files, out_offsets)):
+        for f, off in zip(files, out_offsets):
             hd = parse_header(f)
-            im = self.images[k]
-            im["scan_offset"] = pos + hd.scan_offset
-            im["scan_bytes"] = len(f) - hd.scan_offset
-            im["out_offset"] = off
-            im["restart_interval"] = hd.restart_interval
-            im["width"], im["height"], im["n_comp"], im["sampling"] = hd.width, hd.height, hd.n_comp, hd.sampling
-            for c in range(hd.n_comp):
-                im["qt"][c] = q_index.setdefault(hd.qtables[c], len(q_index))
-                for which, raw in (("dc", hd.htables[c][0]), ("ac", hd.htables[c][1])):
-                    if raw not in h_index:
-                        h_index[raw] = len(h_tabs)
-                        h_tabs.append(_derive_huffman(raw[:16], raw[16:]))
-                    im[which][c] = h_index[raw]
-            if len(q_index) > 255 or len(h_tabs) > 255:
-                raise JpegFormatError("more than 255 distinct tables in one batch; decode in smaller batches")
+            key = (id(hd.qtables), id(hd.htables))
+            idx = table_rows.get(key)
+            if idx is None:
+                qi, di, ai = [0, 0, 0], [0, 0, 0], [0, 0, 0]
+                for c in range(hd.n_comp):
+                    qi[c] = q_index.setdefault(hd.qtables[c], len(q_index))
+                    for dst, raw in ((di, hd.htables[c][0]), (ai, hd.htables[c][1])):
+                        if raw not in h_index:
+                            h_index[raw] = len(h_tabs)
+                            h_tabs.append(_derive_huffman(raw[:16], raw[16:]))
+                        dst[c] = h_index[raw]
+                if len(q_index) > 255 or len(h_tabs) > MAX_HUFF_TABLES_PER_CALL:
+                    raise JpegFormatError("too many distinct tables in one batch (decode_into splits batches for you)")
+                idx = table_rows[key] = (hd.qtables, hd.htables, tuple(qi), tuple(di), tuple(ai))   # keeps the ids alive
+            rows.append((pos + hd.scan_offset, off, len(f) - hd.scan_offset, hd.restart_interval, hd.width, hd.height,
+                         hd.n_comp, hd.sampling, idx[2], idx[3], idx[4]))
             self.sizes.append((hd.height, hd.width, hd.n_comp))
             pos += len(f)
         self.total_bytes = pos
+        self.images = np.zeros(self.n, dtype=IMAGE_DTYPE)
+        if rows:
+            cols = list(zip(*rows))
+            for name, col in zip(("scan_offset", "out_offset", "scan_bytes", "restart_interval", "width", "height", "n_comp",
+                                  "sampling", "qt", "dc", "ac"), cols):
+                self.images[name] = np.asarray(col)
         self.qtables = np.frombuffer(b"".join(q_index.keys()), dtype=np.uint16).reshape(-1, 64).copy()
         self.htables = np.stack(h_tabs) if h_tabs else np.zeros(0, dtype=HUFF_DTYPE)
 
 
+class JpegFileSet:
+    """A set of files staged for decoding: bytes concatenated in pinned host memory, headers parsed, tables pooled --
+    split into groups of at most 8 distinct Huffman tables (files with optimised tables carry their own).  Reusable:
+    a loader stages a video's files once and decodes them into any store slot."""
+
+    def __init__(self, files: Sequence[bytes]):
+        self.n = len(files)
+        self.groups: List[Tuple[int, int, JpegBatch]] = []          # (first file, end file, batch)
+        distinct, start = set(), 0
+        for k, f in enumerate(files):
+            hd = parse_header(f)
+            mine = {t for pair in hd.htables for t in pair}
+            if len(distinct | mine) > MAX_HUFF_TABLES_PER_CALL and k > start:
+                self.groups.append((start, k, JpegBatch(files[start:k], [0] * (k - start))))
+                distinct, start = set(), k
+            distinct |= mine
+        if self.n > start:
+            self.groups.append((start, self.n, JpegBatch(files[start:], [0] * (self.n - start))))
+        self.sizes = [s for _, _, b in self.groups for s in b.sizes]
+        total = sum(len(f) for f in files)
+        self.host = torch.empty(total + 16, dtype=torch.uint8).pin_memory()
+        hv = self.host.numpy()
+        pos = 0
+        self.group_bytes = []
+        for a, b_, batch in self.groups:
+            g0 = pos
+            for f in files[a:b_]:
+                hv[pos:pos + len(f)] = np.frombuffer(f, dtype=np.uint8)
+                pos += len(f)
+            self.group_bytes.append((g0, pos))
+        hv[pos:] = 0
+
+    def decode_into(self, out: torch.Tensor, out_offsets: Sequence[int]) -> None:
+        """Image k goes to byte offset out_offsets[k] of the flat uint8 device tensor `out` as [H][W] (one component) or
+        [H][W][3] RGB.  Asynchronous on the current CUDA stream."""
+        if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise VAError("jpeg decode: `out` must be a contiguous uint8 CUDA tensor (no CPU decode fallback)")
+        if len(out_offsets) != self.n:
+            raise VAError("jpeg decode: %d offsets for %d files" % (len(out_offsets), self.n))
+        for (h, w, c), off in zip(self.sizes, out_offsets):
+            if off < 0 or off + h * w * c > out.numel():
+                raise VAError("jpeg decode: image of %dx%dx%d at offset %d does not fit in `out`" % (h, w, c, off))
+        lib = _lib.load()
+        cur = torch.cuda.current_stream()
+        for (a, b_, batch), (g0, g1) in zip(self.groups, self.group_bytes):
+            dev = self.host[g0:g1 + 16].to(out.device, non_blocking=True)
+            batch.images["out_offset"] = np.asarray(out_offsets[a:b_], dtype=np.uint64)
+            images, q, h = batch.images, batch.qtables, batch.htables
+            check(lib.va_jpeg_decode(ptr(dev), images.ctypes.data_as(C.c_void_p), batch.n, q.ctypes.data_as(C.c_void_p),
+                                     q.shape[0], h.ctypes.data_as(C.c_void_p), h.shape[0], ptr(out), stream_ptr()),
+                  "va_jpeg_decode")
+            dev.record_stream(cur)
+
+
 def decode_into(files: Sequence[bytes], out: torch.Tensor, out_offsets: Sequence[int]) -> None:
-    """Decode `files` into the flat uint8 device tensor `out`, image k at byte offset out_offsets[k] as [H][W] (one
-    component) or [H][W][3] RGB.  Asynchronous on the current CUDA stream (the file bytes are staged through pinned memory)."""
+    """Decode `files` into the flat uint8 device tensor `out`, image k at byte offset out_offsets[k]."""
     if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
         raise VAError("jpeg.decode_into: `out` must be a contiguous uint8 CUDA tensor (no CPU decode fallback)")
     if len(files) == 0:
         return
-    batch = JpegBatch(files, out_offsets)
-    for (h, w, c), off in zip(batch.sizes, out_offsets):
-        if off < 0 or off + h * w * c > out.numel():
-            raise VAError("jpeg.decode_into: image of %dx%dx%d at offset %d does not fit in `out`" % (h, w, c, off))
-    host = torch.empty(batch.total_bytes + 16, dtype=torch.uint8).pin_memory()
-    hv = host.numpy()
-    pos = 0
-    for f in files:
-        hv[pos:pos + len(f)] = np.frombuffer(f, dtype=np.uint8)
-        pos += len(f)
-    hv[pos:] = 0
-    dev = host.to(out.device, non_blocking=True)
-    images, q, h = np.ascontiguousarray(batch.images), np.ascontiguousarray(batch.qtables), np.ascontiguousarray(batch.htables)
-    check(_lib.load().va_jpeg_decode(ptr(dev), images.ctypes.data_as(C.c_void_p), batch.n, q.ctypes.data_as(C.c_void_p),
-                                     q.shape[0], h.ctypes.data_as(C.c_void_p), h.shape[0], ptr(out), stream_ptr()),
-          "va_jpeg_decode")
-    dev.record_stream(torch.cuda.current_stream())
+    JpegFileSet(files).decode_into(out, out_offsets)
 
 
 def decode(files: Sequence[bytes], device: Optional[torch.device] = None) -> List[torch.Tensor]:

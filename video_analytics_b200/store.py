@@ -98,6 +98,32 @@ class DeviceStore:
             ops.synth_fill(self.flow, layout.flow_shape, layout.n_flow_images, seed=layout.seed + 1)
 
     @classmethod
+    def from_jpeg_files(cls, layout: StoreLayout, rgb_files, flow_files, device=None):
+        """Build the store from the reference's on-disk format: `rgb_files[k]` / `flow_files[k]` are the bytes of the JPEG
+        of image id k (frames "<i>.jpg" written by cv2.imwrite, utils.py:116-120; flow_x_/flow_y_ images).  Decoded on the
+        GPU by jpeg.decode_into -- the pixels are Pillow's (Image.open, spatialModel.py:76-79), bit for bit."""
+        import torch
+        from . import jpeg
+
+        self = cls.__new__(cls)
+        self.layout = layout
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        nb_rgb = layout.rgb_shape[0] * layout.rgb_shape[1] * layout.rgb_shape[2]
+        nb_flow = layout.flow_shape[0] * layout.flow_shape[1] * layout.flow_shape[2]
+        self.rgb = torch.empty(max(1, len(rgb_files)) * nb_rgb, dtype=torch.uint8, device=dev)
+        self.flow = torch.empty(max(1, len(flow_files)) * nb_flow, dtype=torch.uint8, device=dev)
+        for files, buf, nb, shape in ((rgb_files, self.rgb, nb_rgb, layout.rgb_shape), (flow_files, self.flow, nb_flow, layout.flow_shape)):
+            if len(files) == 0:
+                continue
+            fs = jpeg.JpegFileSet(files)
+            want = (shape[0], shape[1], shape[2]) if shape[2] != 1 else (shape[0], shape[1], 1)
+            bad = [k for k, sz in enumerate(fs.sizes) if tuple(sz) != want]
+            if bad:
+                raise ValueError("image %d is %r, the store layout expects %r" % (bad[0], fs.sizes[bad[0]], want))
+            fs.decode_into(buf, [k * nb for k in range(len(files))])
+        return self
+
+    @classmethod
     def from_host(cls, layout: StoreLayout, rgb_u8, flow_u8, device=None):
         """Upload host-decoded frames (numpy u8) instead of generating them."""
         import torch
