@@ -134,6 +134,61 @@ def cpu_reference_pass(n_spatial, n_temporal, batch=10, threads=None):
     return time.perf_counter() - t0, torch.get_num_threads()
 
 
+def jpeg_decode_measurement(store, layout, dev, n_rgb=50, n_flow=1000):
+    """the images ONE evaluation step touches (2 videos: 50 frames + 1000 flow images), written the
+    reference's way (cv2.imwrite -> baseline JPEG), decoded into the store by the CUDA decoder: H2D of the compressed
+    files + Huffman / IDCT / colour kernels, timed with CUDA events; Pillow (the reference's loader) on the host cores
+    beside it.  Synthetic frames are hash noise: ~67 KB per file, close to the worst case for entropy decoding."""
+    import concurrent.futures as cf
+    import io
+    import numpy as np
+    import torch
+    try:
+        import cv2
+        from PIL import Image
+    except Exception as e:                      # encoder / reference decoder missing: nothing to measure against
+        return {"unavailable": repr(e)}
+    from video_analytics_b200 import jpeg
+    rgb = store.rgb[:n_rgb * int(np.prod(layout.rgb_shape))].cpu().numpy().reshape(n_rgb, *layout.rgb_shape)
+    nf = layout.flow_shape[0] * layout.flow_shape[1]
+    have = min(n_flow, store.flow.numel() // nf)
+    flow = store.flow[:have * nf].cpu().numpy().reshape(have, layout.flow_shape[0], layout.flow_shape[1])
+    files_rgb = [cv2.imencode(".jpg", f[..., ::-1])[1].tobytes() for f in rgb]
+    files_flow = [cv2.imencode(".jpg", flow[k % have])[1].tobytes() for k in range(n_flow)]
+    out_rgb = torch.empty(n_rgb * rgb[0].size, dtype=torch.uint8, device=dev)
+    out_flow = torch.empty(n_flow * nf, dtype=torch.uint8, device=dev)
+    sets = [(jpeg.JpegFileSet(files_rgb), out_rgb, [k * rgb[0].size for k in range(n_rgb)]),
+            (jpeg.JpegFileSet(files_flow), out_flow, [k * nf for k in range(n_flow)])]
+
+    def run():
+        for fs_, out_, offs_ in sets:
+            fs_.decode_into(out_, offs_)
+    run(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    ok = bool(np.array_equal(out_flow[:nf].cpu().numpy().reshape(flow[0].shape), np.asarray(Image.open(io.BytesIO(files_flow[0])))) and
+              np.array_equal(out_rgb[:rgb[0].size].cpu().numpy().reshape(rgb[0].shape), np.asarray(Image.open(io.BytesIO(files_rgb[0])))))
+    threads = os.cpu_count() or 1
+    allf = files_rgb + files_flow
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda f: np.asarray(Image.open(io.BytesIO(f))).shape, allf[:64]))
+        t0 = time.perf_counter()
+        list(ex.map(lambda f: np.asarray(Image.open(io.BytesIO(f))).shape, allf))
+        cpu_s = time.perf_counter() - t0
+    n = n_rgb + n_flow
+    out_bytes = out_rgb.numel() + out_flow.numel()
+    return {"images_per_call": n, "ms_per_call": ms, "images_per_s": n / (ms * 1e-3), "decoded_GB_per_s": out_bytes / (ms * 1e-3) / 1e9,
+            "compressed_bytes_per_call": sum(len(f) for f in allf), "bit_exact_vs_pillow": ok,
+            "bound": "latency of the serial entropy decode (one thread per image): ms_per_call barely depends on the image count",
+            "cpu_baseline": {"images_per_s": n / cpu_s, "cores": threads, "kind": "reference",
+                             "sample": "PIL.Image.open + np.asarray of the same files on a %d-thread pool" % threads}}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -362,6 +417,7 @@ def main():
             aux.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": nbytes})
         del fd, fs, fout
+        jpeg_line = jpeg_decode_measurement(store, layout, dev)
 
     if rank == 0:
         peaks = read_peaks()
@@ -389,6 +445,7 @@ def main():
                          "flops_per_launch": t_f.value / max(1, t_l.value),
                          "share_of_step": t_ms.value / total_ms if total_ms > 0 else None},
             "aux_rooflines": aux,
+            "jpeg_decode": jpeg_line,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
