@@ -6,8 +6,8 @@
 // step so that the pixels entering K1 are the reference's pixels:
 //   jpeg_huffman_kernel   jdhuff.c decode_mcu -- canonical codes (maxcode / valoffset), RECEIVE/EXTEND, DC prediction,
 //                         ZRL / EOB, 0xFF00 unstuffing, restart markers.  The bit stream of an image is inherently serial:
-//                         one THREAD per image (a batch has 10^3..10^4 images), non-zero coefficients scattered into a
-//                         zero-filled int16 workspace.
+//                         one THREAD per image (a batch has 10^3..10^4 images; 1..32 images per warp depending on the
+//                         batch size), non-zero coefficients scattered into a zero-filled int16 workspace.
 //   jpeg_idct_kernel      dequantise + jidctint.c jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2) + range limit: one thread
 //                         per 8x8 block.  One-component images are written straight into the image store.
 //   jpeg_color_kernel     jdsample.c h2v2_fancy_upsample (triangle filter, biases 8/7, replicated context rows; plain
@@ -17,6 +17,7 @@
 #include "va_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* _
                                                           const JpegImage* __restrict__ images,
                                                           const JpegGeom* __restrict__ geom,
                                                           const JpegHuff* __restrict__ htab, int n_tables, int n_images,
-                                                          short* __restrict__ coef) {
+                                                          int lane_stride, short* __restrict__ coef) {
   __shared__ HuffSmem h;
   for (int idx = threadIdx.x; idx < n_tables * 17; idx += blockDim.x) {
     const int t = idx / 17, l = idx % 17;
@@ -157,7 +158,9 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* _
     }
   }
   __syncthreads();
-  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  // lane_stride = 32 / images per warp: with fewer images per warp the decoders of a warp diverge less (1 = none)
+  if (threadIdx.x % lane_stride) return;
+  const int img = blockIdx.x * (blockDim.x / lane_stride) + threadIdx.x / lane_stride;
   if (img >= n_images) return;
   const JpegImage im = images[img];
   const JpegGeom g = geom[img];
@@ -447,7 +450,18 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
   }
   // (copies from pageable host memory return once the source has been staged, so the host vectors may go out of scope)
   count_launch();
-  jpeg_huffman_kernel<<<(n_images + 31) / 32, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, n_h, n_images, d_coef);
+  // Images per warp: decoders sharing a warp diverge (every symbol costs the union of the lanes' paths: 500 frames take
+  // 55 ms at 32 per warp, 23 ms at one per warp), but one image per warp oversubscribes the machine beyond ~16 warps
+  // per SM (10 000 flow images: 115 ms vs 54 ms at 4 per warp).  Pick the smallest power of two that keeps the warp
+  // count under 16 per SM.
+  int per_warp = 1;
+  while (per_warp < 32 && (n_images + per_warp - 1) / per_warp > 148 * 16) per_warp *= 2;
+  if (const char* env = getenv("VA_JPEG_IMAGES_PER_WARP")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 32 && (32 % v) == 0) per_warp = v;
+  }
+  jpeg_huffman_kernel<<<(n_images + per_warp - 1) / per_warp, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, n_h, n_images,
+                                                                           32 / per_warp, d_coef);
   JCK(cudaGetLastError());
   count_launch();
   jpeg_idct_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, st>>>(d_coef, d_im, d_geom, d_q, n_images, blocks, d_planes, out);
