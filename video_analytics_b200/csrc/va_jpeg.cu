@@ -18,6 +18,7 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -135,29 +136,10 @@ __device__ __forceinline__ int jpeg_extend(unsigned int v, int s) {
   return (int)v < (1 << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v;
 }
 
-__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* __restrict__ bitstreams,
-                                                          const JpegImage* __restrict__ images,
-                                                          const JpegGeom* __restrict__ geom,
-                                                          const JpegHuff* __restrict__ htab, int n_tables, int n_images,
-                                                          int lane_stride, short* __restrict__ coef) {
-  __shared__ HuffSmem h;
-  for (int idx = threadIdx.x; idx < n_tables * 17; idx += blockDim.x) {
-    const int t = idx / 17, l = idx % 17;
-    h.valoffset[t][l] = htab[t].valoffset[l];
-  }
-  for (int idx = threadIdx.x; idx < n_tables * 256; idx += blockDim.x) h.huffval[idx >> 8][idx & 255] = htab[idx >> 8].huffval[idx & 255];
-  for (int idx = threadIdx.x; idx < 80; idx += blockDim.x) h.natural[idx] = c_natural[idx];
-  if (threadIdx.x < n_tables) {
-    const int t = threadIdx.x;
-    unsigned int prev = 0;
-    h.bound[t][0] = 0;
-    for (int l = 1; l <= 16; ++l) {
-      const int mc = htab[t].maxcode[l];
-      if (mc >= 0) prev = (unsigned int)(mc + 1) << (16 - l);
-      h.bound[t][l] = prev;
-    }
-  }
-  __syncthreads();
+__device__ __forceinline__ void huffman_decode_images(const unsigned char* __restrict__ bitstreams,
+                                                      const JpegImage* __restrict__ images,
+                                                      const JpegGeom* __restrict__ geom, const HuffSmem& h, int n_images,
+                                                      int lane_stride, short* __restrict__ coef) {
   // lane_stride = 32 / images per warp: with fewer images per warp the decoders of a warp diverge less (1 = none)
   if (threadIdx.x % lane_stride) return;
   const int img = blockIdx.x * (blockDim.x / lane_stride) + threadIdx.x / lane_stride;
@@ -216,6 +198,59 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* _
       }
     }
   }
+}
+
+// Decoding tables in the layout the decoder reads (bound / valoffset / symbols / zigzag), built once per call in global
+// memory.  USE_SMEM = false (VA_JPEG_SMEM_TABLES=0) reads them through L1 instead of copying them to shared memory: 15-20 %
+// slower alone.  It was written to let decoder blocks co-reside with the persistent layer kernels on a side stream, but
+// those take 227 KB + the 1 KB system reservation of the SM's 228 KB, so NO other block fits next to them whatever it
+// needs: a decode issued ahead on a side stream runs in the gaps between layer launches (measured: bench e2e_jpeg).
+__global__ void jpeg_tables_kernel(const JpegHuff* __restrict__ htab, int n_tables, HuffSmem* __restrict__ out) {
+  for (int idx = threadIdx.x; idx < n_tables * 17; idx += blockDim.x) out->valoffset[idx / 17][idx % 17] = htab[idx / 17].valoffset[idx % 17];
+  for (int idx = threadIdx.x; idx < n_tables * 256; idx += blockDim.x) out->huffval[idx >> 8][idx & 255] = htab[idx >> 8].huffval[idx & 255];
+  for (int idx = threadIdx.x; idx < 80; idx += blockDim.x) out->natural[idx] = c_natural[idx];
+  if (threadIdx.x < n_tables) {
+    const int t = threadIdx.x;
+    unsigned int prev = 0;
+    out->bound[t][0] = 0;
+    for (int l = 1; l <= 16; ++l) {
+      const int mc = htab[t].maxcode[l];
+      if (mc >= 0) prev = (unsigned int)(mc + 1) << (16 - l);
+      out->bound[t][l] = prev;
+    }
+  }
+}
+
+template <bool USE_SMEM>
+__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* __restrict__ bitstreams,
+                                                          const JpegImage* __restrict__ images,
+                                                          const JpegGeom* __restrict__ geom,
+                                                          const JpegHuff* __restrict__ htab,
+                                                          const HuffSmem* __restrict__ gtab, int n_tables, int n_images,
+                                                          int lane_stride, short* __restrict__ coef) {
+  if (!USE_SMEM) {
+    huffman_decode_images(bitstreams, images, geom, *gtab, n_images, lane_stride, coef);
+    return;
+  }
+  __shared__ HuffSmem h;
+  for (int idx = threadIdx.x; idx < n_tables * 17; idx += blockDim.x) {
+    const int t = idx / 17, l = idx % 17;
+    h.valoffset[t][l] = htab[t].valoffset[l];
+  }
+  for (int idx = threadIdx.x; idx < n_tables * 256; idx += blockDim.x) h.huffval[idx >> 8][idx & 255] = htab[idx >> 8].huffval[idx & 255];
+  for (int idx = threadIdx.x; idx < 80; idx += blockDim.x) h.natural[idx] = c_natural[idx];
+  if (threadIdx.x < n_tables) {
+    const int t = threadIdx.x;
+    unsigned int prev = 0;
+    h.bound[t][0] = 0;
+    for (int l = 1; l <= 16; ++l) {
+      const int mc = htab[t].maxcode[l];
+      if (mc >= 0) prev = (unsigned int)(mc + 1) << (16 - l);
+      h.bound[t][l] = prev;
+    }
+  }
+  __syncthreads();
+  huffman_decode_images(bitstreams, images, geom, h, n_images, lane_stride, coef);
 }
 
 // ------------------------------------------------------------------------------------------------ IDCT
@@ -379,6 +414,31 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const int* __restrict__
 // ------------------------------------------------------------------------------------------------ host entry
 namespace {
 thread_local char g_jerr[256];
+
+// Ring of pinned host buffers for the per-call descriptor upload; a slot is reused once its copy has completed.
+struct PinnedSlot {
+  unsigned char* host = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t done = nullptr;
+};
+PinnedSlot* pinned_slot(size_t bytes) {
+  constexpr int kSlots = 8;
+  static thread_local PinnedSlot ring[kSlots];
+  static thread_local int next = 0;
+  PinnedSlot& s = ring[next];
+  next = (next + 1) % kSlots;
+  if (s.done == nullptr && cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (s.host != nullptr && cudaEventSynchronize(s.done) != cudaSuccess) return nullptr;      // normally long complete
+  if (s.bytes < bytes) {
+    if (s.host) cudaFreeHost(s.host);
+    s.host = nullptr;
+    s.bytes = 0;
+    const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+    if (cudaMallocHost(&s.host, want) != cudaSuccess) return nullptr;
+    s.bytes = want;
+  }
+  return &s;
+}
 }
 
 const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_host, int n_images, const unsigned short* qtables_host,
@@ -436,19 +496,30 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
   JCK(cudaMallocAsync(&d_coef, blocks * 64 * sizeof(short), st));
   JCK(cudaMemsetAsync(d_coef, 0, blocks * 64 * sizeof(short), st));
   if (plane_bytes) JCK(cudaMallocAsync(&d_planes, plane_bytes, st));
-  JCK(cudaMallocAsync(&d_im, sizeof(JpegImage) * n_images, st));
-  JCK(cudaMallocAsync(&d_geom, sizeof(JpegGeom) * n_images, st));
-  JCK(cudaMallocAsync(&d_h, sizeof(JpegHuff) * n_h, st));
-  JCK(cudaMallocAsync(&d_q, 128 * n_q, st));
-  JCK(cudaMemcpyAsync(d_im, im, sizeof(JpegImage) * n_images, cudaMemcpyHostToDevice, st));
-  JCK(cudaMemcpyAsync(d_geom, geom.data(), sizeof(JpegGeom) * n_images, cudaMemcpyHostToDevice, st));
-  JCK(cudaMemcpyAsync(d_h, htables_host, sizeof(JpegHuff) * n_h, cudaMemcpyHostToDevice, st));
-  JCK(cudaMemcpyAsync(d_q, qtables_host, 128 * n_q, cudaMemcpyHostToDevice, st));
-  if (!color_ids.empty()) {
-    JCK(cudaMallocAsync(&d_cid, sizeof(int) * color_ids.size(), st));
-    JCK(cudaMemcpyAsync(d_cid, color_ids.data(), sizeof(int) * color_ids.size(), cudaMemcpyHostToDevice, st));
-  }
-  // (copies from pageable host memory return once the source has been staged, so the host vectors may go out of scope)
+  // Descriptors go up in ONE copy from a pinned staging slot.  From pageable memory every cudaMemcpyAsync first
+  // synchronises the stream: a loader that decodes ahead on a side stream would block the host -- and with it the
+  // launches of the main stream -- until the previous decode has finished.
+  const size_t sz_im = sizeof(JpegImage) * n_images, sz_geom = sizeof(JpegGeom) * n_images, sz_h = sizeof(JpegHuff) * n_h;
+  const size_t sz_q = 128 * (size_t)n_q, sz_cid = sizeof(int) * color_ids.size();
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t o_im = 0, o_geom = al(sz_im), o_h = o_geom + al(sz_geom), o_q = o_h + al(sz_h), o_cid = o_q + al(sz_q);
+  const size_t total = o_cid + al(sz_cid);
+  PinnedSlot* slot = pinned_slot(total);
+  if (!slot) return "pinned staging allocation failed";
+  memcpy(slot->host + o_im, im, sz_im);
+  memcpy(slot->host + o_geom, geom.data(), sz_geom);
+  memcpy(slot->host + o_h, htables_host, sz_h);
+  memcpy(slot->host + o_q, qtables_host, sz_q);
+  if (sz_cid) memcpy(slot->host + o_cid, color_ids.data(), sz_cid);
+  unsigned char* d_desc = nullptr;
+  JCK(cudaMallocAsync(&d_desc, total, st));
+  JCK(cudaMemcpyAsync(d_desc, slot->host, total, cudaMemcpyHostToDevice, st));
+  JCK(cudaEventRecord(slot->done, st));
+  d_im = reinterpret_cast<JpegImage*>(d_desc + o_im);
+  d_geom = reinterpret_cast<JpegGeom*>(d_desc + o_geom);
+  d_h = reinterpret_cast<JpegHuff*>(d_desc + o_h);
+  d_q = reinterpret_cast<unsigned short*>(d_desc + o_q);
+  d_cid = sz_cid ? reinterpret_cast<int*>(d_desc + o_cid) : nullptr;
   count_launch();
   // Images per warp: decoders sharing a warp diverge (every symbol costs the union of the lanes' paths: 500 frames take
   // 55 ms at 32 per warp, 23 ms at one per warp), but one image per warp oversubscribes the machine beyond ~16 warps
@@ -460,8 +531,18 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
     const int v = atoi(env);
     if (v >= 1 && v <= 32 && (32 % v) == 0) per_warp = v;
   }
-  jpeg_huffman_kernel<<<(n_images + per_warp - 1) / per_warp, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, n_h, n_images,
-                                                                           32 / per_warp, d_coef);
+  const char* smem_env = getenv("VA_JPEG_SMEM_TABLES");
+  const bool use_smem = !(smem_env != nullptr && smem_env[0] == '0');       // default: tables in shared memory
+  HuffSmem* d_tab = nullptr;
+  JCK(cudaMallocAsync(&d_tab, sizeof(HuffSmem), st));
+  jpeg_tables_kernel<<<1, 256, 0, st>>>(d_h, n_h, d_tab);
+  if (use_smem)
+    jpeg_huffman_kernel<true><<<(n_images + per_warp - 1) / per_warp, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, d_tab, n_h,
+                                                                                 n_images, 32 / per_warp, d_coef);
+  else
+    jpeg_huffman_kernel<false><<<(n_images + per_warp - 1) / per_warp, 32, 0, st>>>(bitstreams, d_im, d_geom, d_h, d_tab, n_h,
+                                                                                  n_images, 32 / per_warp, d_coef);
+  cudaFreeAsync(d_tab, st);
   JCK(cudaGetLastError());
   count_launch();
   jpeg_idct_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, st>>>(d_coef, d_im, d_geom, d_q, n_images, blocks, d_planes, out);
@@ -473,8 +554,7 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
   }
   cudaFreeAsync(d_coef, st);
   if (d_planes) cudaFreeAsync(d_planes, st);
-  cudaFreeAsync(d_im, st); cudaFreeAsync(d_geom, st); cudaFreeAsync(d_h, st); cudaFreeAsync(d_q, st);
-  if (d_cid) cudaFreeAsync(d_cid, st);
+  cudaFreeAsync(d_desc, st);
 #undef JCK
   return nullptr;
 }
