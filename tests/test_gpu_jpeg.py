@@ -138,3 +138,14 @@ def test_store_from_jpeg_files_runs_the_protocol():
         assert np.array_equal(got_flow[k], np.asarray(Image.open(io.BytesIO(flow_files[k]))))
     with pytest.raises(ValueError):
         DeviceStore.from_jpeg_files(lay, flow_files[:1], [])                            # wrong size for the RGB store
+
+
+@pytest.mark.parametrize("mode", ["serial", "parallel"])
+def test_both_entropy_decoders_on_all_files(mode, monkeypatch):
+    """The one-thread-per-image decoder and the block-per-image (self-synchronising chunks) decoder give Pillow's bytes."""
+    from PIL import Image
+    from video_analytics_b200 import jpeg
+    monkeypatch.setenv("VA_JPEG_PARALLEL", "0" if mode == "serial" else "1")
+    files = _files()
+    for f, o in zip(files, jpeg.decode(files)):
+        assert np.array_equal(o.cpu().numpy(), np.asarray(Image.open(io.BytesIO(f))))

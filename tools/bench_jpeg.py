@@ -19,6 +19,20 @@ store = DeviceStore(layout, torch.device("cuda"))
 rgb = store.rgb.cpu().numpy().reshape(-1, *layout.rgb_shape)
 flow = store.flow.cpu().numpy().reshape(-1, layout.flow_shape[0], layout.flow_shape[1])
 n_rgb, n_flow = int(sys.argv[1]) if len(sys.argv) > 1 else 50, int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+if len(sys.argv) > 3 and sys.argv[3] == "smooth":
+    # photo-like content (low-frequency structure + mild sensor noise): most blocks end with EOB, files are ~3x smaller
+    rng = np.random.default_rng(0)
+
+    def smooth(shape, k):
+        h, w = shape[0], shape[1]
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = [128 + 70 * np.sin(xx / (23.0 + k % 7) + k) * np.cos(yy / (31.0 + k % 5)), 120 + 60 * np.cos((xx + yy) / (41.0 + k % 3)),
+                110 + 50 * np.sin(yy / 19.0 + 0.3 * k)]
+        img = np.stack(base[:shape[2]] if len(shape) == 3 else base[:1], -1) + rng.normal(0, 3.0, (h, w, shape[2] if len(shape) == 3 else 1))
+        img = img.clip(0, 255).astype(np.uint8)
+        return img if len(shape) == 3 else img[..., 0]
+    rgb = np.stack([smooth(layout.rgb_shape, k) for k in range(16)])
+    flow = np.stack([smooth((layout.flow_shape[0], layout.flow_shape[1]), k) for k in range(32)])
 rgb_files = [cv2.imencode(".jpg", rgb[i % len(rgb)][..., ::-1])[1].tobytes() for i in range(n_rgb)]
 flow_files = [cv2.imencode(".jpg", flow[i % len(flow)])[1].tobytes() for i in range(n_flow)]
 print(f"{n_rgb} RGB files avg {np.mean([len(f) for f in rgb_files]):.0f} B, {n_flow} flow files avg {np.mean([len(f) for f in flow_files]):.0f} B")
