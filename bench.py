@@ -182,11 +182,47 @@ def jpeg_decode_measurement(store, layout, dev, n_rgb=50, n_flow=1000):
         cpu_s = time.perf_counter() - t0
     n = n_rgb + n_flow
     out_bytes = out_rgb.numel() + out_flow.numel()
+    # the same measurement on photo-like content (low-frequency structure + mild noise): files ~3x smaller, nearly every
+    # block ends with EOB -- the regime the block-per-image parallel entropy decoder is built for
+    rng = np.random.default_rng(0)
+
+    def photo_like(h, w, c, k):
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = [128 + 70 * np.sin(xx / (23.0 + k % 7) + k) * np.cos(yy / (31.0 + k % 5)), 120 + 60 * np.cos((xx + yy) / (41.0 + k % 3)),
+                110 + 50 * np.sin(yy / 19.0 + 0.3 * k)][:c]
+        img = (np.stack(base, -1) + rng.normal(0, 3.0, (h, w, c))).clip(0, 255).astype(np.uint8)
+        return img if c == 3 else img[..., 0]
+    p_rgb = [cv2.imencode(".jpg", photo_like(layout.rgb_shape[0], layout.rgb_shape[1], 3, k))[1].tobytes() for k in range(16)]
+    p_flow = [cv2.imencode(".jpg", photo_like(layout.flow_shape[0], layout.flow_shape[1], 1, k))[1].tobytes() for k in range(32)]
+    pf_rgb, pf_flow = [p_rgb[k % 16] for k in range(n_rgb)], [p_flow[k % 32] for k in range(n_flow)]
+    sets_p = [(jpeg.JpegFileSet(pf_rgb), out_rgb, sets[0][2]), (jpeg.JpegFileSet(pf_flow), out_flow, sets[1][2])]
+
+    def run_p():
+        for fs_, out_, offs_ in sets_p:
+            fs_.decode_into(out_, offs_)
+    run_p(); torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        run_p()
+    b.record(); torch.cuda.synchronize()
+    ms_p = a.elapsed_time(b) / reps
+    ok_p = bool(np.array_equal(out_flow[:nf].cpu().numpy().reshape(flow[0].shape), np.asarray(Image.open(io.BytesIO(pf_flow[0])))) and
+                np.array_equal(out_rgb[:rgb[0].size].cpu().numpy().reshape(rgb[0].shape), np.asarray(Image.open(io.BytesIO(pf_rgb[0])))))
+    with cf.ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(lambda f: np.asarray(Image.open(io.BytesIO(f))).shape, pf_rgb + pf_flow))
+        cpu_p = time.perf_counter() - t0
     return {"images_per_call": n, "ms_per_call": ms, "images_per_s": n / (ms * 1e-3), "decoded_GB_per_s": out_bytes / (ms * 1e-3) / 1e9,
             "compressed_bytes_per_call": sum(len(f) for f in allf), "bit_exact_vs_pillow": ok,
-            "bound": "latency of the serial entropy decode (one thread per image): ms_per_call barely depends on the image count",
+            "content": "frames of the synthetic store: hash noise, every coefficient non-zero, no EOB -- the worst case for entropy "
+                       "decoding and for chunk self-synchronisation",
+            "bound": "latency of the entropy decode",
             "cpu_baseline": {"images_per_s": n / cpu_s, "cores": threads, "kind": "reference",
-                             "sample": "PIL.Image.open + np.asarray of the same files on a %d-thread pool" % threads}}
+                             "sample": "PIL.Image.open + np.asarray of the same files on a %d-thread pool" % threads},
+            "photo_like": {"images_per_call": n, "ms_per_call": ms_p, "images_per_s": n / (ms_p * 1e-3),
+                           "decoded_GB_per_s": out_bytes / (ms_p * 1e-3) / 1e9,
+                           "compressed_bytes_per_call": sum(len(f) for f in pf_rgb + pf_flow), "bit_exact_vs_pillow": ok_p,
+                           "cpu_baseline": {"images_per_s": n / cpu_p, "cores": threads, "kind": "reference"}}}
 
 
 def run_reference(args, rank):
