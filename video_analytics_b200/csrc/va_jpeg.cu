@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const unsigned char* _
 //   4. a scan per component over the blocks in stream order turns the DC differences into DC values.
 // ~4 passes of work per image instead of 1, but spread over 256 threads: 206 images in ~1.5 ms instead of 22 ms.
 constexpr int kParThreads = 256;
-constexpr int kParMaxChunks = 1024;
+constexpr int kParMaxChunks = 512;      // 8 KB of records: small enough to co-reside with a layer kernel that leaves ~17 KB
 
 struct ChunkRec {
   unsigned int p;          // bit position of the first symbol that starts at or after the chunk end
