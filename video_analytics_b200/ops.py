@@ -60,7 +60,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, relu=True, o
 
 def preprocess(images: torch.Tensor, image_shape: Sequence[int], index_table: torch.Tensor, mean: Sequence[float],
                std: Sequence[float], *, c_pad: int = 16, reference_layout: bool = False, crop: int = CROP,
-               image_bytes: Optional[int] = None) -> torch.Tensor:
+               image_bytes: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K1.  images: u8 store (flat); image_shape (h, w, c); index_table int32 [n, planes, 4]
     = (image id, crop top, crop left, flip).  Returns bf16 NHWC [n,crop,crop,c_pad], or with
     reference_layout=True the reference's fp32 NCHW tensor [n, planes*c, crop, crop] (bit-exact)."""
@@ -73,10 +73,14 @@ def preprocess(images: torch.Tensor, image_shape: Sequence[int], index_table: to
     assert len(mean) == nch and len(std) == nch, "one mean/std per stacked channel"
     if image_bytes is None:
         image_bytes = h * w * c
-    if reference_layout:
-        out = torch.empty((n, nch, crop, crop), dtype=torch.float32, device=images.device)
-    else:
-        out = torch.empty((n, crop, crop, c_pad), dtype=torch.bfloat16, device=images.device)
+    shape = (n, nch, crop, crop) if reference_layout else (n, crop, crop, c_pad)
+    dtype = torch.float32 if reference_layout else torch.bfloat16
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=images.device)
+    else:                                   # caller-owned buffer (e.g. reused across steps on a side stream)
+        _need_cuda(out)
+        assert out.dtype == dtype and out.numel() >= int(torch.Size(shape).numel()), (out.shape, shape)
+        out = out.view(-1)[:int(torch.Size(shape).numel())].view(shape)
     fm = (C.c_float * nch)(*mean)
     fs = (C.c_float * nch)(*std)
     check(_lib.load().va_preprocess(ptr(images), image_bytes, h, w, c, ptr(index_table), n, planes, crop, fm, fs, c_pad,
