@@ -249,3 +249,15 @@ def test_jpeg_header_parser_and_huffman_tables_match_oracle():
     assert int(batch.images["scan_offset"][1]) == len(files[0]) + jpeg.parse_header(files[1]).scan_offset
     with pytest.raises(jpeg.JpegFormatError):
         jpeg.parse_header(b"\x89PNG....")
+
+
+def test_training_flop_accounting_matches_survey():
+    """bench_train's algorithmic FLOPs: forward = SURVEY 8d figures minus the fp32 logit layer (2*256*101, not a
+    tensor-core call); backward = data gradient (all layers but conv1_1) + weight gradient."""
+    import bench_train as B
+    fs, bs = B.stream_flops(3)
+    ft, bt = B.stream_flops(20)
+    assert int(fs) + 2 * 256 * 101 == 30_934_485_504
+    assert int(ft) + 2 * 256 * 101 == 31_917_132_288
+    first_s, first_t = 2.0 * 224 * 224 * 64 * 9 * 3, 2.0 * 224 * 224 * 64 * 9 * 20
+    assert bs == 2 * fs - first_s and bt == 2 * ft - first_t
