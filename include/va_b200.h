@@ -136,7 +136,10 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
  * train() (reference spatialModel.py:178-181: CrossEntropyLoss, SGD(lr, momentum=0.9)) and the train-mode forward
  * (Dropout after FC1..FC3, :141-152).  Activations / activation gradients are bf16 NHWC, parameter gradients fp32
  * in the reference's own layouts (OIHW, [out][in]) so that they line up with the fp32 master parameters.
- *   va_maxpool2x2_nhwc   : MaxPool2d(2,2) forward (training keeps the un-pooled activation for the backward pass)
+ *   va_maxpool2x2_nhwc   : MaxPool2d(2,2) forward; with codes != NULL (uint32 [n][H/2][W/2][C/8]) it also records, in 4 bits
+ *                          per window and channel, which element takes the gradient (0..3, first maximum in scan order;
+ *                          4 = none: the maximum is not positive) -- 1/16 of the activation's bytes
+ *   va_pool_bwd_codes    : dZ (and db) of relu+pool from those codes, without the un-pooled activation
  *   va_relu_pool_bwd     : dZ = un-pool(dout) * (Y > 0); pooled=0: dout is already the gradient of Y; with db != NULL
  *                          the bias gradient db[c] = sum dZ[.., c] is produced by the same pass
  *   va_bias_grad         : db[c] = sum_rows dZ[row][c]
@@ -154,7 +157,9 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
  *   va_sgd_momentum      : buf = g (first step) | momentum*buf + g;  p -= lr*buf   (grad_scale multiplies g first,
  *                          e.g. 1/world_size after a gradient all-reduce)
  * --------------------------------------------------------------------------------------------------------- */
-va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, va_stream_t stream);
+va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, void* codes, va_stream_t stream);
+va_status va_pool_bwd_codes(const void* dout, const void* codes, int n, int H, int W, int C, void* dZ, float* db,
+                            va_stream_t stream);
 va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ, float* db,
                            va_stream_t stream);
 va_status va_bias_grad(const void* dZ, long long rows, int C, float* db, va_stream_t stream);

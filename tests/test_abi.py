@@ -76,7 +76,7 @@ def test_training_primitives_reject_bad_arguments_without_touching_the_gpu(built
     assert lib.va_wgrad(p, p, 1, 4, 4, 64, 64, 64, 5, p, None) != 0           # ks must be 1 or 3
     assert b"ks" in lib.va_last_error()
     assert lib.va_conv2d_dgrad(p, 1, 4, 4, 48, p, 64, p, None) != 0             # channels must be multiples of 64
-    assert lib.va_maxpool2x2_nhwc(p, 1, 5, 4, 64, p, None) != 0                 # odd height
+    assert lib.va_maxpool2x2_nhwc(p, 1, 5, 4, 64, p, None, None) != 0           # odd height
 
 
 def test_training_has_no_cpu_fallback(built_lib):

@@ -47,6 +47,27 @@ def test_relu_pool_bwd_bit_exact(pooled):
     assert torch.allclose(db, z.grad.sum((0, 2, 3)), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("C", [64, 128, 512])
+def test_pool_codes_route_like_the_activation(C):
+    """maxpool codes + pool_bwd_codes == relu_pool_bwd on the activation itself (bit-exact), incl. ties and dead windows."""
+    from video_analytics_b200 import train_ops as T
+    g = torch.Generator().manual_seed(21)
+    y = torch.relu(torch.randn(3, 12, 20, C, generator=g)).bfloat16()
+    y[0, :4, :4] = 0.75                       # ties: the first element of each window must win
+    y[1, 2:6, 2:8] = 0.0                      # windows with no positive element: no gradient
+    y = y.cuda()
+    p, codes = T.maxpool2x2(y, with_codes=True)
+    assert torch.equal(p, T.maxpool2x2(y))
+    dout = torch.randn(p.shape, generator=g).bfloat16().cuda()
+    db_ref = torch.empty(C, dtype=torch.float32, device="cuda")
+    db = torch.full((C,), 3.0, dtype=torch.float32, device="cuda")
+    ref = T.relu_pool_bwd(dout, y, pooled=True, bias_grad_out=db_ref)
+    got = T.pool_bwd_codes(dout, codes, bias_grad_out=db)
+    assert torch.equal(got, ref)
+    assert torch.allclose(db, db_ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(T.pool_bwd_codes(dout, codes), ref)           # without the bias gradient
+
+
 @pytest.mark.parametrize("shape", [(3, 14, 14, 512), (2, 28, 28, 192), (5, 1, 1, 4096)], ids=str)
 @pytest.mark.parametrize("pooled", [True, False])
 def test_relu_pool_bwd_fused_bias_shapes(shape, pooled):

@@ -48,7 +48,7 @@ print(f"{kind} n={n}: {e0.elapsed_time(e1) / 3:.2f} ms/step  -> {n * 3 / e0.elap
       f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
 for name in ("conv2d_nhwc", "linear"):
     wrap(ops, name)
-for name in ("maxpool2x2", "relu_pool_bwd", "bias_grad", "dropout", "conv2d_dgrad", "linear_dgrad", "conv2d_wgrad",
+for name in ("maxpool2x2", "relu_pool_bwd", "pool_bwd_codes", "bias_grad", "dropout", "conv2d_dgrad", "linear_dgrad", "conv2d_wgrad",
              "linear_wgrad", "ce_train", "relu_bwd_f32_to_bf16", "transpose_bf16", "sgd_momentum_"):
     wrap(T, name)
 trainer.step(x, labels)
@@ -57,6 +57,6 @@ tot = collections.OrderedDict()
 for name, shape, a, b in spans:
     ms = a.elapsed_time(b)
     tot[name] = tot.get(name, 0.0) + ms
-    if name in ("conv2d_wgrad", "conv2d_dgrad", "conv2d_nhwc", "linear_wgrad", "linear_dgrad", "linear", "relu_pool_bwd", "maxpool2x2"):
+    if name in ("conv2d_wgrad", "conv2d_dgrad", "conv2d_nhwc", "linear_wgrad", "linear_dgrad", "linear", "relu_pool_bwd", "pool_bwd_codes", "maxpool2x2"):
         print(f"  {name:16s} {str(shape):28s} {ms:8.3f} ms")
 print({k: round(v, 2) for k, v in tot.items()}, "sum", round(sum(tot.values()), 2))

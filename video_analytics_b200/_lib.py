@@ -35,7 +35,8 @@ SIGNATURES = {
     "va_consensus_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "va_pack_input_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "va_pack_input_nchw_split6": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "va_maxpool2x2_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "va_maxpool2x2_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "va_pool_bwd_codes": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "va_relu_pool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "va_bias_grad": (_i, [_vp, C.c_longlong, _i, _vp, _vp]),
     "va_dropout": (_i, [_vp, _vp, C.c_longlong, _f, _i, _vp, _vp]),

@@ -387,11 +387,19 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
 
 
 // ------------------------------------------------------------------------------------------------ training primitives
-va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, va_stream_t stream) {
+va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, void* codes, va_stream_t stream) {
   if (!x || !y) return fail(VA_ERR_INVALID, "va_maxpool2x2_nhwc: NULL argument");
   if ((H | W) & 1 || C % 8) return fail(VA_ERR_INVALID, "va_maxpool2x2_nhwc: H, W must be even and C a multiple of 8");
   if (va_status s = require_sm100()) return s;
-  VA_CUDA(va::launch_maxpool_fwd(x, y, n, H, W, C, static_cast<cudaStream_t>(stream)));
+  VA_CUDA(va::launch_maxpool_fwd(x, y, codes, n, H, W, C, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+va_status va_pool_bwd_codes(const void* dout, const void* codes, int n, int H, int W, int C, void* dZ, float* db,
+                            va_stream_t stream) {
+  if (!dout || !codes || !dZ) return fail(VA_ERR_INVALID, "va_pool_bwd_codes: NULL argument");
+  if ((H | W) & 1 || C % 8 || 256 % (C / 8)) return fail(VA_ERR_INVALID, "va_pool_bwd_codes: H, W must be even and C/8 must divide 256");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_pool_bwd_codes(dout, codes, dZ, db, n, H, W, C, static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }
 va_status va_relu_pool_bwd(const void* dout, const void* Y, int n, int H, int W, int C, int pooled, void* dZ, float* db,

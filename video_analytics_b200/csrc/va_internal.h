@@ -35,7 +35,8 @@ cudaError_t launch_nchw_to_nhwc_split6(const float* x, int n, int c, int hw, int
 cudaError_t launch_nchw_to_nhwc(const float* x, int n, int c, int hw, int c_pad, void* out, cudaStream_t st);
 
 // ---- training-step kernels (va_train_kernels.cu, va_wgrad_tc.cu)
-cudaError_t launch_maxpool_fwd(const void* x, void* y, int n, int H, int W, int C, cudaStream_t st);
+cudaError_t launch_maxpool_fwd(const void* x, void* y, void* codes, int n, int H, int W, int C, cudaStream_t st);
+cudaError_t launch_pool_bwd_codes(const void* dP, const void* codes, void* dZ, float* db, int n, int H, int W, int C, cudaStream_t st);
 cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, float* db, int n, int H, int W, int C, int pooled,
                                  cudaStream_t st);
 cudaError_t launch_bias_grad(const void* dZ, float* db, long long rows, int C, cudaStream_t st);

@@ -8,8 +8,12 @@ namespace va {
 
 // ------------------------------------------------------------------------------------------------ max-pool forward
 // NHWC bf16, 2x2 stride 2; 8 channels (16 B) per thread.
-__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int H,
-                                                          int W, int C8) {
+// codes (optional): one 4-bit code per (window, channel), 8 channels per uint32 -- the index 0..3 (scan order, first
+// maximum) of the window element that receives the gradient, or 4 when the maximum is not positive (ReLU kills it).
+// With the codes the backward pass needs neither a second look at the un-pooled activation nor the activation itself:
+// 1/16 of its bytes are kept instead.
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                          uint32_t* __restrict__ codes, int n, int H, int W, int C8) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)n * Ho * Wo * C8;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,6 +33,76 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const uint4* __restric
   o.x = mx(mx(a.x, b.x), mx(cc.x, d.x)); o.y = mx(mx(a.y, b.y), mx(cc.y, d.y));
   o.z = mx(mx(a.z, b.z), mx(cc.z, d.z)); o.w = mx(mx(a.w, b.w), mx(cc.w, d.w));
   y[g] = o;
+  if (codes != nullptr) {
+    const uint4 win[4] = {a, b, cc, d};
+    uint32_t code = 0;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      float best = 0.f;
+      int arg = 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t word = reinterpret_cast<const uint32_t*>(&win[k])[ch >> 1];
+        const float v = __uint_as_float((ch & 1) ? (word & 0xFFFF0000u) : (word << 16));     // bf16 -> fp32 is a shift
+        // first maximum in scan order, and only if positive: strict > against the running best (starts at 0)
+        if (k == 0 ? v > 0.f : v > best) { if (v > 0.f) { best = v; arg = k; } }
+      }
+      code |= (uint32_t)arg << (4 * ch);
+    }
+    codes[g] = code;
+  }
+}
+
+// Pool + ReLU backward from the codes of maxpool_fwd_kernel (+ bias gradient): reads dP and 4 bits per window-channel
+// instead of the whole un-pooled activation.
+__global__ void __launch_bounds__(256) pool_bwd_codes_bias_kernel(const uint4* __restrict__ dP, const uint32_t* __restrict__ codes,
+                                                                  uint4* __restrict__ dZ, float* __restrict__ db, int n, int H,
+                                                                  int W, int C8) {
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8, lanes = 256 / C8;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)n * Ho * Wo;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (long long t = (long long)blockIdx.x * lanes + pl; t < total; t += (long long)gridDim.x * lanes) {
+    const uint4 gp4 = __ldg(dP + t * C8 + cg);
+    const uint32_t code = __ldg(codes + t * C8 + cg);
+    const int wo = (int)(t % Wo);
+    const long long t2 = t / Wo;
+    const int ho = (int)(t2 % Ho), img = (int)(t2 / Ho);
+    const long long i00 = (((long long)img * H + 2 * ho) * W + 2 * wo) * C8 + cg;
+    const long long idx[4] = {i00, i00 + C8, i00 + (long long)W * C8, i00 + (long long)W * C8 + C8};
+    const uint16_t* g16 = reinterpret_cast<const uint16_t*>(&gp4);
+    uint32_t o[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[k][j] = 0u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t a = (code >> (4 * c)) & 15u;
+      const uint32_t bits = (uint32_t)g16[c] << ((c & 1) * 16);
+      if (a < 4) acc[c] += __uint_as_float((uint32_t)g16[c] << 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (a == (uint32_t)k) o[k][c >> 1] |= bits;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dZ[idx[k]] = make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
+  }
+  if (db == nullptr) return;
+  __shared__ float red[256 * 8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float sum = 0.f;
+      for (int l = 0; l < lanes; ++l) sum += red[(l * C8 + cg) * 8 + i];
+      atomicAdd(db + cg * 8 + i, sum);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ ReLU (+pool) backward
@@ -357,11 +431,28 @@ __global__ void pack_fc_w_t_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------ launchers
 static inline unsigned nblk(long long total) { return (unsigned)((total + 255) / 256); }
 
-cudaError_t launch_maxpool_fwd(const void* x, void* y, int n, int H, int W, int C, cudaStream_t st) {
+cudaError_t launch_maxpool_fwd(const void* x, void* y, void* codes, int n, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)n * (H / 2) * (W / 2) * (C / 8);
   if (total == 0) return cudaSuccess;
   count_launch();
-  maxpool_fwd_kernel<<<nblk(total), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n, H, W, C / 8);
+  maxpool_fwd_kernel<<<nblk(total), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
+                                                  static_cast<uint32_t*>(codes), n, H, W, C / 8);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_bwd_codes(const void* dP, const void* codes, void* dZ, float* db, int n, int H, int W, int C, cudaStream_t st) {
+  const long long units = (long long)n * (H / 2) * (W / 2);
+  if (units == 0) return cudaSuccess;
+  if (C % 8 != 0 || 256 % (C / 8) != 0) return cudaErrorInvalidValue;
+  if (db != nullptr) {
+    cudaError_t e = cudaMemsetAsync(db, 0, (size_t)C * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  const int C8 = C / 8, lanes = 256 / C8;
+  const long long want = (units + lanes * 16 - 1) / (lanes * 16);
+  const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(want, 148 * 8));
+  count_launch();
+  pool_bwd_codes_bias_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint4*>(dP), static_cast<const uint32_t*>(codes),
+                                                     static_cast<uint4*>(dZ), db, n, H, W, C8);
   return cudaGetLastError();
 }
 cudaError_t launch_relu_pool_bwd(const void* dP, const void* Y, void* dZ, float* db, int n, int H, int W, int C, int pooled,

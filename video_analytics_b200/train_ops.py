@@ -14,14 +14,29 @@ from ._lib import check, ptr, stream_ptr
 from .ops import _need_cuda
 
 
-def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
-    """bf16 NHWC [n,H,W,C] -> [n,H/2,W/2,C]  (MaxPool2d(2,2))."""
+def maxpool2x2(x: torch.Tensor, with_codes: bool = False):
+    """bf16 NHWC [n,H,W,C] -> [n,H/2,W/2,C]  (MaxPool2d(2,2)).  with_codes=True also returns the gradient-routing codes
+    (int32 [n,H/2,W/2,C/8], 4 bits per window and channel) that pool_bwd_codes consumes instead of the activation."""
     _need_cuda(x)
     assert x.dtype == torch.bfloat16
     n, H, W, Cc = x.shape
     y = torch.empty((n, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().va_maxpool2x2_nhwc(ptr(x), n, H, W, Cc, ptr(y), stream_ptr()), "va_maxpool2x2_nhwc")
-    return y
+    codes = torch.empty((n, H // 2, W // 2, Cc // 8), dtype=torch.int32, device=x.device) if with_codes else None
+    check(_lib.load().va_maxpool2x2_nhwc(ptr(x), n, H, W, Cc, ptr(y), ptr(codes), stream_ptr()), "va_maxpool2x2_nhwc")
+    return (y, codes) if with_codes else y
+
+
+def pool_bwd_codes(dout: torch.Tensor, codes: torch.Tensor, *, bias_grad_out=None) -> torch.Tensor:
+    """Gradient w.r.t. the pre-activation of relu -> maxpool from the pooled gradient dout [n,H/2,W/2,C] and the codes of
+    maxpool2x2(..., with_codes=True); same result as relu_pool_bwd(dout, y, pooled=True) without reading y."""
+    _need_cuda(dout, codes, bias_grad_out)
+    assert dout.dtype == torch.bfloat16 and codes.dtype == torch.int32
+    n, Ho, Wo, Cc = dout.shape
+    assert tuple(codes.shape) == (n, Ho, Wo, Cc // 8)
+    dz = torch.empty((n, 2 * Ho, 2 * Wo, Cc), dtype=torch.bfloat16, device=dout.device)
+    check(_lib.load().va_pool_bwd_codes(ptr(dout), ptr(codes), n, 2 * Ho, 2 * Wo, Cc, ptr(dz), ptr(bias_grad_out),
+                                        stream_ptr()), "va_pool_bwd_codes")
+    return dz
 
 
 def relu_pool_bwd(dout: torch.Tensor, y: torch.Tensor, *, pooled: bool, bias_grad_out=None) -> torch.Tensor:

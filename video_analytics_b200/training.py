@@ -138,12 +138,21 @@ class StreamTrainer:
         labels = labels.to(device=x_nhwc.device, dtype=torch.int64).contiguous()
 
         # ---------------- forward (train mode), activations kept
-        saved = []                                   # per conv: (input, un-pooled post-ReLU output)
+        # per conv: (input, post-ReLU output, pool codes).  A pooled layer keeps 4 bits per window and channel (which
+        # element takes the gradient) instead of its un-pooled output -- 1/16 of the bytes, and the backward pass does
+        # not read the activation again; the outputs of the pooled layers are 80 % of the activation volume.
+        saved = []
         x = x_nhwc
         for i in range(13):
             y = ops.conv2d_nhwc(x, W[2 * i], W[2 * i + 1], relu=True, pool=False)
-            saved.append((x, y))
-            x = T.maxpool2x2(y) if POOL_AFTER[i] else y
+            if POOL_AFTER[i]:
+                nxt, codes = T.maxpool2x2(y, with_codes=True)
+                saved.append((x, y if keep is not None else None, codes))
+                x = nxt
+            else:
+                saved.append((x, y, None))
+                x = y
+            del y
         hw, ch = x.shape[1] * x.shape[2], x.shape[3]
         flat = T.transpose_bf16(x.view(n, hw, ch)).view(n, ch * hw)          # the reference's NCHW flatten order
         h1 = ops.linear(flat, W[26], W[27], relu=True)
@@ -154,7 +163,7 @@ class StreamTrainer:
         d3 = T.dropout(h3, masks[2], DROPOUT_P)                              # featureVectors (reference :176)
         ce = T.ce_train(d3, W[32], W[33], labels, dw4=G[32], db4=G[33])
         if keep is not None:
-            keep.update(conv=list(saved), flat=flat, h=[h1, h2, h3], d=[d1, d2, d3], dlogits=ce["dlogits"])
+            keep.update(conv=[(a, b) for a, b, _ in saved], flat=flat, h=[h1, h2, h3], d=[d1, d2, d3], dlogits=ce["dlogits"])
 
         # ---------------- backward
         g = T.dropout(ce["dx"], masks[2], DROPOUT_P)
@@ -171,8 +180,11 @@ class StreamTrainer:
         g = T.linear_dgrad(dz, W[26])                                        # [n, ch*hw] in NCHW flatten order
         g = T.transpose_bf16(g.view(n, ch, hw)).view(n, x.shape[1], x.shape[2], ch)
         for i in range(12, -1, -1):
-            xin, y = saved[i]
-            dz = T.relu_pool_bwd(g, y, pooled=POOL_AFTER[i], bias_grad_out=G[2 * i + 1])
+            xin, y, codes = saved[i]
+            if codes is not None:
+                dz = T.pool_bwd_codes(g, codes, bias_grad_out=G[2 * i + 1])
+            else:
+                dz = T.relu_pool_bwd(g, y, pooled=False, bias_grad_out=G[2 * i + 1])
             cin = W[2 * i].shape[1]
             T.conv2d_wgrad(dz, xin, cin, out=G[2 * i])
             if i > 0:
