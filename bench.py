@@ -427,7 +427,8 @@ def main():
     #      and flow images its two videos touch (written the reference's way, cv2.imwrite) from pinned host memory, the
     #      CUDA decoder fills the stage store on a side stream one step ahead, then K1 -> networks -> fusion -> D2H.
     e2e_jpeg = None
-    if args.e2e_jpeg:
+    jpeg_ready, jpeg_why = bool(args.e2e_jpeg), "disabled (--no-e2e-jpeg)"
+    if jpeg_ready:
         try:
             import cv2
             from video_analytics_b200 import jpeg
@@ -469,6 +470,17 @@ def main():
 
             for i in range(W + K):
                 step_fileset(step_keys(i))
+        except Exception as e:
+            jpeg_ready, jpeg_why = False, repr(e)
+    if world > 1:                               # every rank takes the same branch: the timed loop below has barriers
+        flag = torch.tensor([1 if jpeg_ready else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if jpeg_ready and int(flag.item()) == 0:
+            jpeg_ready, jpeg_why = False, "set-up failed on another rank"
+    if not jpeg_ready:
+        e2e_jpeg = {"unavailable": jpeg_why}
+    else:
+        try:
             side = torch.cuda.Stream()
             decoded = [torch.cuda.Event() for _ in range(DEPTH)]
             consumed = [torch.cuda.Event() for _ in range(DEPTH)]
