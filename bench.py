@@ -267,7 +267,8 @@ def main():
     ap.add_argument("--workload", default="eval", choices=["eval", "train"],
                     help="eval: the headline two-stream evaluation (BASELINE configs[2]/[3]); train: the training step "
                          "(configs[4], bench_train.py)")
-    ap.add_argument("--batch", type=int, default=64, help="--workload train: snippets per stream per GPU per step")
+    ap.add_argument("--batch", type=int, default=256,
+                    help="--workload train: snippets per stream per GPU per step (BASELINE configs[4]: 256)")
     ap.add_argument("--lr", type=float, default=0.001, help="--workload train: SGD learning rate")
     args = ap.parse_args()
     if args.workload == "train":

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Training-step benchmark (BASELINE.json configs[4]: two-stream training step bf16, gradient all-reduce over NVLink).
 
-`python bench.py --workload train [--gpus N --steps K --warmup W --batch B]` dispatches here; same launch contract and
+`python bench.py --workload train [--gpus N --steps K --warmup W --batch B]` (default B = 256) dispatches here; same launch contract and
 JSON line as bench.py.  One step, per GPU: B RGB snippets + B flow-stack snippets are cropped/flipped/normalised from
 the uint8 store (K1), each stream runs forward + backward + ONE NCCL all-reduce of its gradient arena + the fused
 SGD-momentum update (training.py).  `value` counts two-stream snippets (one RGB + one flow stack) over all ranks.
