@@ -297,6 +297,168 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// 256-wide layers: a 2-CTA cluster computes a 256 (co) x 256 (ci) tile with tcgen05 cta_group::2.  Each CTA loads its
+// own 128 output channels of dZ and only HALF of the 256 input channels of X per K block (32 instead of 48 KB -> 6
+// pipeline stages, a third less L2 -> SM traffic per FLOP; the one-CTA kernel sits at ~51 % tensor-pipe activity, bound
+// by operand delivery).  Same protocol as conv_tc2_kernel: both producers credit the LEADER's full barrier, the leader
+// issues the MMAs, tcgen05.commit multicasts to both CTAs, both epilogues release the accumulator on the leader's
+// barrier.  Work unit = (tap, ci tile, pair of co tiles, K split).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgradThreads, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
+  constexpr int BN = 256;
+  constexpr uint32_t BLOCK = kWgradKP * 128;                 // one [64 px][64 ch] block: 8 KB
+  constexpr uint32_t A_BYTES = 2 * BLOCK, B_HALF = 2 * BLOCK, STAGE = A_BYTES + B_HALF;   // 32 KB per CTA
+  constexpr uint32_t TMEM_COLS = 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * STAGE);   // used in the leader CTA
+  uint64_t* empty_bar = full_bar + kMaxStages;                                               // own copy in each CTA
+  uint64_t* tfull_bar = empty_bar + kMaxStages;                                              // own copy in each CTA
+  uint64_t* tempty_bar = tfull_bar + 2;                                                      // used in the leader CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  constexpr int kProducerWarp = 4, kMmaWarp = 5;
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }   // 4 warps x 2 CTAs
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) { tmem_alloc2(tmem_slot, TMEM_COLS); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int unit, int& tap, int& ci_t, int& co_p, int& split) {
+    uint32_t q, t;
+    p.div_taps.divmod((uint32_t)unit, q, t); tap = (int)t;
+    p.div_ci.divmod(q, q, t); ci_t = (int)t;
+    p.div_co.divmod(q, q, t); co_p = (int)t;         // div_co divides by the number of co PAIRS here
+    split = (int)q;
+  };
+
+  if (warp == kProducerWarp) {
+    uint32_t stage = 0, phase = 0;
+    for (int unit = cluster_id; unit < p.total_units; unit += n_clusters) {
+      int tap, ci_t, co_p, split;
+      decode(unit, tap, ci_t, co_p, split);
+      const int s = tap / p.ks, r = tap - s * p.ks;
+      const int pt0 = split_begin(p, split), pt1 = split_begin(p, split + 1);
+      const int co0 = co_p * 256 + (int)rank * 128, ci0 = ci_t * BN + (int)rank * 128;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        uint32_t q, tw, th, tn;
+        p.div_tw.divmod((uint32_t)pt, q, tw);
+        p.div_th.divmod(q, tn, th);
+        const int w0 = (int)tw * p.w_t, h0 = (int)th * p.h_t, n0 = (int)tn * p.n_t;
+        mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+        if (elect_one()) {
+          uint8_t* a_dst = smem + (size_t)stage * STAGE;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE);
+          tma_load_4d_2sm(a_dst, &tmA, &full_bar[stage], co0, w0, h0, n0);
+          tma_load_4d_2sm(a_dst + BLOCK, &tmA, &full_bar[stage], co0 + 64, w0, h0, n0);
+          tma_load_4d_2sm(a_dst + A_BYTES, &tmB, &full_bar[stage], ci0, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_4d_2sm(a_dst + A_BYTES + BLOCK, &tmB, &full_bar[stage], ci0 + 64, w0 + s - p.pad, h0 + r - p.pad, n0);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(256, BN);
+      const uint32_t smem_base_u32 = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
+      for (int unit = cluster_id; unit < p.total_units; unit += n_clusters) {
+        int tap, ci_t, co_p, split;
+        decode(unit, tap, ci_t, co_p, split);
+        const int pt0 = split_begin(p, split), pt1 = split_begin(p, split + 1);
+        mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + as * BN;
+        uint32_t acc = 0;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base_u32 + stage * STAGE;
+          const uint64_t da0 = make_smem_desc_mn<128>(a_addr, BLOCK);
+          const uint64_t db0 = make_smem_desc_mn<128>(a_addr + A_BYTES, BLOCK);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kWgradKP / 16; ++k)
+              umma_bf16_2sm(d_tmem, da0 + ((k * 16 * 128) >> 4), db0 + ((k * 16 * 128) >> 4), idesc, k ? 1u : acc);
+            umma_commit_2sm(&empty_bar[stage], 3);
+            if (pt == pt1 - 1) umma_commit_2sm(&tfull_bar[as], 3);
+          }
+          __syncwarp();
+          acc = 1;
+          if (++stage == (uint32_t)p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        as ^= 1;
+        if (as == 0) as_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t as = 0, as_phase = 0;
+    for (int unit = cluster_id; unit < p.total_units; unit += n_clusters) {
+      int tap, ci_t, co_p, split;
+      decode(unit, tap, ci_t, co_p, split);
+      mbar_wait(&tfull_bar[as], as_phase, 400 + as);
+      tc_fence_after();
+      const int co = co_p * 256 + (int)rank * 128 + m;
+      float* dst = p.dwt + ((size_t)tap * p.Cout + co) * p.row_stride + ci_t * BN;
+#pragma unroll 1
+      for (int c16 = 0; c16 < BN / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c16 * 16, v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          if (ci_t * BN + c16 * 16 + 16 <= p.Cin && (p.row_stride & 3) == 0) {
+            if (p.plain_store) {
+              float4* d4 = reinterpret_cast<float4*>(dst + c16 * 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                    __uint_as_float(v[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                red_add_v4(dst + c16 * 16 + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int ci = ci_t * BN + c16 * 16 + i;
+              if (ci < p.Cin) {
+                if (p.plain_store) dst[c16 * 16 + i] = __uint_as_float(v[i]);
+                else atomicAdd(dst + c16 * 16 + i, __uint_as_float(v[i]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) as_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
 // [taps][Cout][Cin] (tap' = s*ks + r) -> OIHW fp32 [Cout][Cin][ks][ks]; one thread per (co, ci): coalesced reads of each
 // tap plane, ks*ks consecutive floats written per thread.
 __global__ void wgrad_to_oihw_kernel(const float* __restrict__ dwt, float* __restrict__ dw, int Cout, int Cin, int ks) {
@@ -405,22 +567,26 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   const int T = ks == 1 ? 1 : (BN <= 32 ? 9 : (BN <= 128 ? 3 : 1));
   p.tap_groups = p.taps / T;
   const int sms = sm_count_cached();
-  const int base_units = p.tap_groups * p.co_tiles * p.ci_tiles;
+  // CTA pairs for the 256-wide tiles of the conv layers (the FC weight gradients are one K block per tile: no pipeline)
+  const bool pair = BN == 256 && T == 1 && ks == 3 && Cout >= 256 && getenv("VA_WGRAD_NO_PAIR") == nullptr;
+  const int co_units = pair ? (Cout + 255) / 256 : p.co_tiles;
+  const int exec_units = pair ? sms / 2 : sms;              // clusters (pair) or CTAs that run concurrently
+  const int base_units = p.tap_groups * co_units * p.ci_tiles;
   // K splits: 2..8 units per SM, picked for the fullest last wave (units are dealt round-robin to one CTA per SM, so
   // 2.07 waves cost 3); fewer splits win ties (less atomic traffic)
   int ksplit = 1;
   {
     double best = -1.0;
-    const int k_lo = std::max(1, (2 * sms + base_units - 1) / base_units);
-    const int k_hi = std::max(k_lo, (8 * sms) / base_units);
+    const int k_lo = std::max(1, (2 * exec_units + base_units - 1) / base_units);
+    const int k_hi = std::max(k_lo, (8 * exec_units) / base_units);
     for (int k = k_lo; k <= k_hi && k <= p.pixel_tiles; ++k) {
       const int units = base_units * k;
-      const int waves = (units + sms - 1) / sms;
-      const double eff = (double)units / ((double)waves * sms);
+      const int waves = (units + exec_units - 1) / exec_units;
+      const double eff = (double)units / ((double)waves * exec_units);
       if (eff > best + 0.01) { best = eff; ksplit = k; }
     }
     if (ksplit > p.pixel_tiles) ksplit = p.pixel_tiles;
-    if (base_units >= 2 * sms) ksplit = 1;       // enough independent output tiles (the FC layers): no split-K
+    if (base_units >= 2 * exec_units) ksplit = 1;       // enough independent output tiles (the FC layers): no split-K
   }
   p.ksplit = ksplit;
   p.total_units = base_units * ksplit;
@@ -428,7 +594,7 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   p.dwt = target;
   p.div_taps = FastDiv::make((uint32_t)p.tap_groups);
   p.div_ci = FastDiv::make((uint32_t)p.ci_tiles);
-  p.div_co = FastDiv::make((uint32_t)p.co_tiles);
+  p.div_co = FastDiv::make((uint32_t)co_units);
   p.div_tw = FastDiv::make((uint32_t)p.tiles_w);
   p.div_th = FastDiv::make((uint32_t)p.tiles_h);
   p.plain_store = ksplit == 1 ? 1 : 0;
@@ -443,6 +609,24 @@ const char* wgrad_run(const void* dz, const void* x, int n, int H, int W, int Co
   if (const char* e = encode_nhwc(&tB, x, n, H, W, cin_pad, CB, p.w_t, vr ? p.h_t + 2 : p.h_t, p.n_t)) return e;
   const int grid = p.total_units < sms ? p.total_units : sms;
   const char* err = nullptr;
+  if (pair) {
+    constexpr uint32_t STAGE2 = 4 * kWgradKP * 128;
+    int stages = (int)((227 * 1024 - 1024 - 256) / STAGE2);
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.num_stages = stages;
+    const size_t smem = 1024 + (size_t)stages * STAGE2 + 256;
+    static size_t configured2 = 0;
+    if (configured2 < smem) {
+      cudaError_t e2 = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e2 != cudaSuccess) return werrf("cudaFuncSetAttribute(wgrad pair, smem=%zu): %s", smem, cudaGetErrorString(e2));
+      configured2 = smem;
+    }
+    const int clusters = p.total_units < sms / 2 ? p.total_units : sms / 2;
+    count_launch();
+    wgrad_tc2_kernel<<<2 * clusters, kWgradThreads, smem, st>>>(tA, tB, p);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return werrf("wgrad_tc2_kernel launch: %s", cudaGetErrorString(e2));
+  } else
 #define VA_W(bn, cb, t, v) if (BN == bn && CB == cb && T == t && vr == v) err = launch_wgrad<bn, cb, t, v>(tA, tB, p, grid, st); else
   VA_W(256, 64, 1, false) VA_W(128, 64, 3, false) VA_W(64, 64, 3, false) VA_W(32, 32, 9, false) VA_W(16, 16, 9, false)
   VA_W(128, 64, 3, true) VA_W(64, 64, 3, true)
