@@ -1,4 +1,4 @@
-"""Diagnostic: per-tensor gradient agreement of the K5 training step with (a) the fp32 oracle and (b) a torch-autograd
+"""Diagnostic (test infrastructure; run from the repo root: python tests/diag_train_parity.py [spatial|temporal] [batch]): per-tensor gradient agreement of the K5 training step with (a) the fp32 oracle and (b) a torch-autograd
 emulation that rounds activations to bf16 at the same points as the kernels (so that ReLU masks and pool routing are
 identical and only gradient rounding differs).  Test infrastructure only."""
 import copy

@@ -5,7 +5,7 @@
     The forward runs in bf16 storage / fp32 accumulate, so ReLU masks and max-pool routing differ from the fp32
     reference at the few units whose pre-activation (or window maximum) is decided by the last bits.  A routing change
     moves a gradient entry by its full value, so the L2 distance of a gradient tensor to the fp32 one grows like
-    sqrt(fraction of re-routed units) per layer -- tools/diag_train.py shows torch autograd over a bf16-rounded forward
+    sqrt(fraction of re-routed units) per layer -- tests/diag_train_parity.py shows torch autograd over a bf16-rounded forward
     is exactly as far from the fp32 oracle as these kernels are (features.0.weight: 0.42 vs 0.41).  What is stable, and
     what is asserted against the fp32 oracle:
         loss                      1e-3 relative      (measured 2e-5)

@@ -5,14 +5,15 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from oracle import two_stream as ts  # noqa: E402  (model builder only: random-init parameter container)
+from video_analytics_b200.spatialModel import build_spatial_torch_model  # noqa: E402
+from video_analytics_b200.temporalModel import build_temporal_torch_model  # noqa: E402
 from video_analytics_b200 import ops, train_ops as T  # noqa: E402
 from video_analytics_b200.training import StreamTrainer  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "spatial"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 cin, c_pad = (3, 16) if kind == "spatial" else (20, 32)
-model = ts.build_spatial_model(seed=1) if kind == "spatial" else ts.build_temporal_model(seed=1)
+model = build_spatial_torch_model(101, 256, seed=1) if kind == "spatial" else build_temporal_torch_model(101, 10, 256, seed=1)
 trainer = StreamTrainer(model, None, c_pad=c_pad)
 x = torch.randn(n, 224, 224, c_pad, device="cuda").bfloat16()
 x[..., cin:] = 0
