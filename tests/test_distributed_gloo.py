@@ -43,3 +43,28 @@ def test_two_rank_gather_cpu():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(results) == [(0, True, n_videos), (1, True, n_videos)]
+
+
+def test_bench_reference_arm_contract_under_torchrun():
+    """`bench.py --impl reference` launched the driver's way with 2 ranks: rank 0 alone prints ONE JSON line carrying the
+    contract keys, the other rank exits 0 without work (both workloads; tiny samples)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra, metric in (([], "two-stream snippets/sec"), (["--workload", "train"], "two-stream training snippets/sec")):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29655", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+               "--warmup", "0", "--ref-snippets", "1"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1, r.stdout[-2000:]
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"].startswith(metric) and d["value"] > 0
+        for key in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+                    "cpu_baseline", "e2e"):
+            assert key in d, key
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
