@@ -567,12 +567,19 @@ def main():
         fout = ev.alloc_outputs(gv, D, C, with_svm=True)
         ms_f = timed(lambda: combined.fuse(fd[0], fd[1], fs[0], fs[1], offs, out=fout))
         hbm = read_peaks()["hbm"]
-        for name, nbytes, ms_k in (("preprocess_kernel (RGB, 3->16ch bf16 NHWC)", 451_584 * nsn, ms_s),
-                                   ("preprocess_kernel (flow stack, 20->32ch bf16 NHWC)", 3_010_560 * nsn, ms_t),
-                                   ("fuse_kernel (consensus + late fusion + SVM scoring)", (714_000 + (2 * D + C) * 4 + 8 + C * 8) * gv, ms_f)):
+        px = 224 * 224
+        fuse_b = (714_000 + (2 * D + C) * 4 + 8 + C * 8) * gv
+        # moved = bytes the launch really reads + writes: the network-input layout pads 3 -> 16 and 20 -> 32 channels
+        # (TMA / UMMA K granularity), so K1 writes more than the algorithmic bf16 tensor of SURVEY.md 8d
+        for name, nbytes, moved, ms_k in (
+                ("preprocess_rows_kernel (RGB, 3->16ch bf16 NHWC)", 451_584 * nsn, (px * 3 + px * spatial.c_pad * 2) * nsn, ms_s),
+                ("preprocess_rows_kernel (flow stack, 20->32ch bf16 NHWC)", 3_010_560 * nsn, (px * 20 + px * temporal.c_pad * 2) * nsn, ms_t),
+                ("fuse_kernel (consensus + late fusion + SVM scoring)", fuse_b, fuse_b, ms_f)):
             gbs = nbytes / (ms_k * 1e-3) / 1e9
             aux.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                        "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": nbytes})
+                        "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": nbytes,
+                        "moved_bytes_per_launch": moved, "moved_gbs": moved / (ms_k * 1e-3) / 1e9,
+                        "moved_frac": moved / (ms_k * 1e-3) / 1e9 / hbm})
         del fd, fs, fout
         jpeg_line = jpeg_decode_measurement(store, layout, dev)
 

@@ -213,6 +213,167 @@ static float* cached_lut(const PreprocessParams& p, cudaStream_t st) {
   return lut;
 }
 
+// ---- row-staged path (bf16 NHWC, crop 224): coalesced words in, one contiguous 16-byte chunk per thread out ---------
+// preprocess4_kernel above moves 2.3-2.6 TB/s: every thread stores 4 x C_PAD bf16 of its own, so one warp store
+// instruction touches 32 different 128-byte lines with 16 bytes each, and the source bytes arrive one `ld.u8` at a time.
+// Here a persistent block works on items of RB output rows of one snippet:
+//   stage   the RB x PLANES source rows arrive as aligned 32-bit words through `cp.async` (global -> shared, no
+//           registers), double-buffered: the rows of the block's NEXT item are in flight while this item is converted;
+//   convert thread k of the item produces output chunk k = 8 consecutive channels of one pixel: 8 byte reads from the
+//           staged rows (row stride S = 1 mod 4 words, so the planes of a warp's chunk groups sit in different banks),
+//           8 LUT reads, 4 cvt.bf16x2, ONE 16-byte store.  Consecutive threads write consecutive chunks: a warp store is
+//           512 contiguous bytes, an item RB*224*C_PAD*2 contiguous bytes (rows of a snippet are adjacent in NHWC).
+// The flow stack has one (mean, std) pair for all 20 planes: its LUT is kept 32x replicated ([value][lane], 32 KB) so the
+// data-dependent lookup is bank-conflict-free; RGB (3 pairs, 3 lookups per 32 output bytes) keeps the plain 3 KB table.
+// Needs 4-byte aligned image rows (store base, image_bytes and img_w*img_c multiples of 4) - true for the store layouts of
+// the path (320x3, 340x1); anything else takes preprocess4_kernel.
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int C_PAD, int PLANES, int IMG_C, int RB, int REP>
+struct K1Rows {
+  static constexpr int CROP = 224;
+  static constexpr int NCH = PLANES * IMG_C;
+  static constexpr int CPC = C_PAD / 8;                      // 16-byte chunks per output pixel
+  static constexpr int ROWB = CROP * IMG_C;                  // source bytes of one plane row
+  static constexpr int NW = (ROWB + 6) / 4;                  // aligned words covering a row at any byte shift 0..3
+  static constexpr int S = NW + ((5 - (NW & 3)) & 3);        // row stride in words, S = 1 (mod 4)
+  static constexpr int RAWW = RB * PLANES * S;               // words per staging buffer
+  static constexpr int NLUT = REP == 32 ? 1 : 3;
+  static constexpr int ITEMS_PER_SNIP = CROP / RB;
+  static constexpr size_t SMEM = (size_t)NLUT * 256 * REP * 4 + 2 * (size_t)RAWW * 4 + 2 * PLANES * 4 + 32;
+  static_assert(CROP % RB == 0 && 256 % CPC == 0 && (RB * CROP * CPC) % 256 == 0, "item shape");
+};
+
+template <int C_PAD, int PLANES, int IMG_C, int RB, int REP, int MINB>
+__global__ void __launch_bounds__(256, MINB) preprocess_rows_kernel(const PreprocessParams p, const float* __restrict__ lut_g,
+                                                                   int n_items) {
+  using K = K1Rows<C_PAD, PLANES, IMG_C, RB, REP>;
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  float* lut = reinterpret_cast<float*>(k1_smem);
+  uint32_t* raw0 = reinterpret_cast<uint32_t*>(lut + K::NLUT * 256 * REP);
+  int* meta0 = reinterpret_cast<int*>(raw0 + 2 * K::RAWW);          // per buffer and plane: byte shift | flip << 8
+  unsigned char* s_lutof = reinterpret_cast<unsigned char*>(meta0 + 2 * PLANES);
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (REP == 32) {
+    for (int i = tid; i < 256 * 32; i += 256) lut[i] = __ldg(lut_g + (i >> 5));
+  } else {
+    for (int k = 0; k < p.n_luts; ++k) lut[k * 256 + tid] = __ldg(lut_g + k * 256 + tid);
+  }
+  if (tid < 32) s_lutof[tid] = p.lut_of[tid];
+
+  auto stage = [&](int item, int buf) {
+    const int snip = item / K::ITEMS_PER_SNIP;
+    const int y0 = (item - snip * K::ITEMS_PER_SNIP) * RB;
+    const int4* tab = reinterpret_cast<const int4*>(p.table) + (size_t)snip * PLANES;
+    uint32_t* raw = raw0 + buf * K::RAWW;
+    for (int t = tid; t < RB * PLANES * K::NW; t += 256) {
+      const int rp = t / K::NW, w = t - rp * K::NW;           // rp = r * PLANES + pl
+      const int r = rp / PLANES, pl = rp - r * PLANES;
+      const int4 e = __ldg(tab + pl);                          // {image id, crop_i, crop_j, flip}
+      const size_t off = (size_t)e.x * p.image_bytes + ((size_t)(e.y + y0 + r) * p.img_w + e.z) * IMG_C;
+      const int sh = (int)(off & 3);                           // same for every row: img_w * IMG_C is a multiple of 4
+      if (w * 4 < sh + K::ROWB) cp_async_4(raw + rp * K::S + w, p.images + (off - sh) + 4 * (size_t)w);
+      if (w == 0 && r == 0) meta0[buf * PLANES + pl] = sh | (e.w ? 256 : 0);
+    }
+  };
+
+  // this thread's chunk group g (the same for all its chunks: 256 % CPC == 0) and, per item, its 8 channels' bases
+  const int g = tid & (K::CPC - 1);
+  int item = blockIdx.x, buf = 0;
+  if (item < n_items) stage(item, 0);
+  cp_async_commit();
+  for (; item < n_items; item += gridDim.x, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();   // buffer `buf` has landed for everyone; everyone is done reading buffer buf^1 (previous item)
+    const int next = item + gridDim.x;
+    if (next < n_items) stage(next, buf ^ 1);
+    cp_async_commit();
+
+    const unsigned char* rawb = reinterpret_cast<const unsigned char*>(raw0 + buf * K::RAWW);
+    const int* meta = meta0 + buf * PLANES;
+    int base[8], step[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      base[j] = -1; step[j] = 0;
+      if (j < K::NCH && c < K::NCH) {
+        const int pl = c / IMG_C, kk = c - pl * IMG_C;
+        const int m = meta[pl];
+        const bool flip = (m & 256) != 0;
+        // pixel x of the crop reads source column x, or 223 - x when flipped (hflip of the crop = reversed columns)
+        base[j] = pl * K::S * 4 + (m & 3) + kk + (flip ? (K::CROP - 1) * IMG_C : 0);
+        step[j] = flip ? -IMG_C : IMG_C;
+      }
+    }
+    const int snip = item / K::ITEMS_PER_SNIP;
+    const int y0 = (item - snip * K::ITEMS_PER_SNIP) * RB;
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                          ((size_t)snip * K::CROP + y0) * K::CROP * C_PAD);
+#pragma unroll 2
+    for (int k = tid; k < RB * K::CROP * K::CPC; k += 256) {
+      const int px = k / K::CPC;                               // r * 224 + x
+      const int r = px / K::CROP, x = px - r * K::CROP;
+      const int rowoff = r * PLANES * K::S * 4;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = 0.f;
+        if (j < K::NCH && base[j] >= 0) {
+          const unsigned b = rawb[rowoff + base[j] + x * step[j]];
+          v[j] = (REP == 32) ? lut[b * 32 + lane] : lut[s_lutof[g * 8 + j] * 256 + b];
+        }
+      }
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), bb = __floats2bfloat162_rn(v[2], v[3]);
+      const __nv_bfloat162 cc = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+      uint4 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&bb);
+      o.z = *reinterpret_cast<const uint32_t*>(&cc); o.w = *reinterpret_cast<const uint32_t*>(&d);
+      dst[k] = o;
+    }
+  }
+  cp_async_wait_all();
+}
+
+static int sm_count_cached() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+template <int C_PAD, int PLANES, int IMG_C, int RB, int REP, int MINB>
+static cudaError_t launch_preprocess_rows(const PreprocessParams& p, const float* lut, cudaStream_t st) {
+  using K = K1Rows<C_PAD, PLANES, IMG_C, RB, REP>;
+  auto kern = preprocess_rows_kernel<C_PAD, PLANES, IMG_C, RB, REP, MINB>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    if (e != cudaSuccess) return e;
+    // MINB blocks per SM only fit with the shared-memory side of the L1 split at its maximum
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int n_items = p.n * K::ITEMS_PER_SNIP;
+  const int grid = std::min(n_items, sm_count_cached() * MINB);
+  count_launch();
+  kern<<<grid, 256, K::SMEM, st>>>(p, lut, n_items);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_preprocess(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
                               const int32_t* table, int n, int planes, int crop, const float* mean,
                               const float* stdv, int c_pad, int out_mode, void* out, cudaStream_t st) {
@@ -236,6 +397,16 @@ cudaError_t launch_preprocess(const uint8_t* images, size_t image_bytes, int img
   const long long total = (long long)n * crop * crop;
   if (total == 0) return cudaSuccess;
   const bool rgb = (planes == 1 && img_c == 3), flow = (planes == 20 && img_c == 1);
+  // row-staged path: the two network-input shapes of the path, 4-byte aligned image rows
+  const bool rows_ok = out_mode == 0 && crop == 224 && p.n_luts > 0 && n <= (1 << 22) &&
+                       (reinterpret_cast<uintptr_t>(images) & 3) == 0 && image_bytes % 4 == 0 &&
+                       ((size_t)img_w * img_c) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (rows_ok && ((rgb && c_pad == 16) || (flow && c_pad == 32 && p.n_luts == 1))) {
+    float* lut = cached_lut(p, st);
+    if (lut == nullptr) return cudaErrorMemoryAllocation;
+    if (rgb) return launch_preprocess_rows<16, 1, 3, 8, 1, 6>(p, lut, st);
+    return launch_preprocess_rows<32, 20, 1, 4, 32, 3>(p, lut, st);
+  }
   // fast path: 4 pixels per thread (needs crop % 4 == 0, a LUT, one of the two shapes of the path, n <= 65535)
   if ((rgb || flow) && crop % 4 == 0 && p.n_luts > 0 && n <= 65535) {
     float* lut = cached_lut(p, st);
@@ -433,7 +604,22 @@ cudaError_t launch_head(const float* desc, const float* w4t, const float* b4, in
 // ------------------------------------------------------------------------------------------------ K4
 // One CTA per video.  Means are SEQUENTIAL fp32 sums in snippet order followed by one division, i.e. exactly
 // AverageMeter.update (reference utils.py:167-171) -- bit-identical to the reference given identical inputs.
-__global__ void __launch_bounds__(512) fuse_kernel(const float* __restrict__ desc_s, const float* __restrict__ desc_t,
+constexpr int FUSE_U = 10;
+__device__ __forceinline__ float seq_sum(const float* __restrict__ src, int stride, int b, int e) {
+  float sum = 0.f;
+  int i = b;
+  for (; i + FUSE_U <= e; i += FUSE_U) {
+    float a[FUSE_U];
+#pragma unroll
+    for (int u = 0; u < FUSE_U; ++u) a[u] = __ldg(src + (size_t)(i + u) * stride);
+#pragma unroll
+    for (int u = 0; u < FUSE_U; ++u) sum = __fadd_rn(sum, a[u]);
+  }
+  for (; i < e; ++i) sum = __fadd_rn(sum, __ldg(src + (size_t)i * stride));
+  return sum;
+}
+
+__global__ void __launch_bounds__(1024) fuse_kernel(const float* __restrict__ desc_s, const float* __restrict__ desc_t,
                                                    const float* __restrict__ score_s,
                                                    const float* __restrict__ score_t,
                                                    const int32_t* __restrict__ offs, int D, int C,
@@ -445,38 +631,32 @@ __global__ void __launch_bounds__(512) fuse_kernel(const float* __restrict__ des
   double* ssvm = reinterpret_cast<double*>(fsm_raw);          // C
   float* sx = reinterpret_cast<float*>(ssvm + C);             // 2D fused descriptor
   float* ssc = sx + 2 * D;                                    // C fused scores
+  float* smean = ssc + C;                                     // 2C per-stream score means
   const int v = blockIdx.x;
   const int b = offs[v], e = offs[v + 1];
   const float cnt = (float)(e - b);
   const bool has_desc = desc_s != nullptr && desc_t != nullptr;
   const bool has_sc = score_s != nullptr && score_t != nullptr;
-  // descriptors: thread j < 2D owns one output dimension
-  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
-    const float* src = (j < D) ? (desc_s + j) : (desc_t + (j - D));
-    float sum = 0.f;
-    if (has_desc) {
-      int i = b;
-      for (; i + 4 <= e; i += 4) {   // 4 independent loads in flight, adds stay in order
-        const float a0 = __ldg(src + (size_t)i * D), a1 = __ldg(src + (size_t)(i + 1) * D),
-                    a2 = __ldg(src + (size_t)(i + 2) * D), a3 = __ldg(src + (size_t)(i + 3) * D);
-        sum = __fadd_rn(sum, a0); sum = __fadd_rn(sum, a1); sum = __fadd_rn(sum, a2); sum = __fadd_rn(sum, a3);
-      }
-      for (; i < e; ++i) sum = __fadd_rn(sum, __ldg(src + (size_t)i * D));
+  // One thread per column sum: columns [0, 2D) are the descriptor dimensions (spatial | temporal), columns
+  // [2D, 2D + 2C) the class scores of the two streams.  FUSE_U rows are loaded before they are added, so every thread
+  // keeps FUSE_U independent loads in flight while the adds stay in snippet order (= AverageMeter's order).
+  const int ncols = 2 * D + (has_sc ? 2 * C : 0);
+  for (int col = threadIdx.x; col < ncols; col += blockDim.x) {
+    if (col < 2 * D) {
+      const float sum = has_desc ? seq_sum((col < D) ? (desc_s + col) : (desc_t + (col - D)), D, b, e) : 0.f;
+      const float avg = (e > b) ? __fdiv_rn(sum, cnt) : 0.f;
+      sx[col] = avg;
+      if (video_desc) video_desc[(size_t)v * 2 * D + col] = avg;
+    } else {
+      const int k = col - 2 * D;
+      const float sum = seq_sum((k < C) ? (score_s + k) : (score_t + (k - C)), C, b, e);
+      smean[k] = (e > b) ? __fdiv_rn(sum, cnt) : 0.f;
     }
-    const float avg = (e > b) ? __fdiv_rn(sum, cnt) : 0.f;
-    sx[j] = avg;
-    if (video_desc) video_desc[(size_t)v * 2 * D + j] = avg;
   }
-  // class scores: threads 0..C-1 spatial, C..2C-1 temporal (if blockDim allows), else strided
   if (has_sc) {
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s0 = 0.f, s1 = 0.f;
-      for (int i = b; i < e; ++i) {
-        s0 = __fadd_rn(s0, __ldg(score_s + (size_t)i * C + c));
-        s1 = __fadd_rn(s1, __ldg(score_t + (size_t)i * C + c));
-      }
-      const float m0 = (e > b) ? __fdiv_rn(s0, cnt) : 0.f;
-      const float m1 = (e > b) ? __fdiv_rn(s1, cnt) : 0.f;
+      const float m0 = smean[c], m1 = smean[C + c];
       const float f = __fdiv_rn(__fadd_rn(__fmul_rn(w_s, m0), __fmul_rn(w_t, m1)), __fadd_rn(w_s, w_t));
       ssc[c] = f;
       if (video_scores) video_scores[(size_t)v * C + c] = f;
@@ -515,9 +695,11 @@ cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* s
                         float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
                         int32_t* svm_pred, cudaStream_t st) {
   if (V == 0) return cudaSuccess;
-  const size_t smem = C * sizeof(double) + (2 * D + C) * sizeof(float);
+  const size_t smem = C * sizeof(double) + (2 * D + 3 * C) * sizeof(float);
+  const int ncols = 2 * D + 2 * C;                            // one thread per column sum when it fits a block
+  const int threads = std::min(1024, std::max(128, (ncols + 31) / 32 * 32));
   count_launch();
-  fuse_kernel<<<V, 512, smem, st>>>(desc_s, desc_t, score_s, score_t, offs, D, C, svm_w, svm_b, w_s, w_t, video_desc,
+  fuse_kernel<<<V, threads, smem, st>>>(desc_s, desc_t, score_s, score_t, offs, D, C, svm_w, svm_b, w_s, w_t, video_desc,
                                     video_scores, score_pred, svm_scores, svm_pred);
   return cudaGetLastError();
 }
