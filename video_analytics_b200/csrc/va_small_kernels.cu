@@ -2,6 +2,7 @@
 // head, K4 consensus + late fusion, and the synthetic image-store generator.  All integer/byte work stays
 // integer; all fp32 arithmetic that must match the reference bit-for-bit uses explicit IEEE intrinsics.
 #include "va_internal.h"
+#include "va_ptx.cuh"
 
 #include <map>
 #include <mutex>
@@ -213,130 +214,160 @@ static float* cached_lut(const PreprocessParams& p, cudaStream_t st) {
   return lut;
 }
 
-// ---- row-staged path (bf16 NHWC, crop 224): coalesced words in, one contiguous 16-byte chunk per thread out ---------
+// ---- row-staged path (bf16 NHWC, crop 224): bulk-copied rows in, one contiguous 16-byte chunk per thread out -------
 // preprocess4_kernel above moves 2.3-2.6 TB/s: every thread stores 4 x C_PAD bf16 of its own, so one warp store
 // instruction touches 32 different 128-byte lines with 16 bytes each, and the source bytes arrive one `ld.u8` at a time.
-// Here a persistent block works on items of RB output rows of one snippet:
-//   stage   the RB x PLANES source rows arrive as aligned 32-bit words through `cp.async` (global -> shared, no
-//           registers), double-buffered: the rows of the block's NEXT item are in flight while this item is converted;
-//   convert thread k of the item produces output chunk k = 8 consecutive channels of one pixel: 8 byte reads from the
-//           staged rows (row stride S = 1 mod 4 words, so the planes of a warp's chunk groups sit in different banks),
-//           8 LUT reads, 4 cvt.bf16x2, ONE 16-byte store.  Consecutive threads write consecutive chunks: a warp store is
-//           512 contiguous bytes, an item RB*224*C_PAD*2 contiguous bytes (rows of a snippet are adjacent in NHWC).
-// The flow stack has one (mean, std) pair for all 20 planes: its LUT is kept 32x replicated ([value][lane], 32 KB) so the
-// data-dependent lookup is bank-conflict-free; RGB (3 pairs, 3 lookups per 32 output bytes) keeps the plain 3 KB table.
-// Needs 4-byte aligned image rows (store base, image_bytes and img_w*img_c multiples of 4) - true for the store layouts of
-// the path (320x3, 340x1); anything else takes preprocess4_kernel.
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+// Here a persistent block of 224 threads works on items of RB output rows of one snippet:
+//   stage   one thread per (row, plane) issues ONE bulk async copy (`cp.async.bulk`, the non-tensor TMA path) of the
+//           16-byte blocks that cover its 224*IMG_C source bytes, completing on the buffer's mbarrier; two buffers, so
+//           the rows of the block's NEXT item are in flight while this item is converted.  (The first version staged
+//           4-byte words with per-thread `cp.async`: ncu showed the kernel ISSUE bound, 40 % of all instructions in
+//           that loop's address arithmetic.)
+//   convert an output row is 224*C_PAD/8 16-byte chunks (8 channels of one pixel); thread t owns chunks t, t+224, ...
+//           of every row of the item, so its channel group, its first pixel and all store offsets are loop constants:
+//           per channel a byte read from the staged row, a LUT read, half a cvt.bf16x2; per chunk ONE 16-byte store.
+//           Consecutive threads write consecutive chunks: a warp store is 512 contiguous bytes.
+// Staged planes sit 240 (688) bytes apart plus 32 bytes per group of 8 planes, so the three channel groups of a flow
+// warp read different banks.  The flow stack has one (mean, std) pair for all 20 planes: its LUT is kept 32x replicated
+// ([value][lane], 32 KB) so the data-dependent lookup is bank-conflict-free; RGB (3 pairs, 3 lookups per 32 output
+// bytes) keeps the plain 3 KB table.  Needs a 16-byte aligned store base and image size (true for the stores of the
+// path: 240x320x3 and 256x340 bytes per image); anything else takes preprocess4_kernel.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int C_PAD, int PLANES, int IMG_C, int RB, int REP>
 struct K1Rows {
+  static constexpr int THREADS = 224;
   static constexpr int CROP = 224;
   static constexpr int NCH = PLANES * IMG_C;
-  static constexpr int CPC = C_PAD / 8;                      // 16-byte chunks per output pixel
+  static constexpr int JN = NCH < 8 ? NCH : 8;               // channel slots of a chunk that can hold a real channel
+  static constexpr int CPC = C_PAD / 8;                      // 16-byte chunks per output pixel (= chunks per thread and row)
+  static constexpr int XSTEP = CROP / CPC;                   // pixel distance between a thread's chunks in a row
   static constexpr int ROWB = CROP * IMG_C;                  // source bytes of one plane row
-  static constexpr int NW = (ROWB + 6) / 4;                  // aligned words covering a row at any byte shift 0..3
-  static constexpr int S = NW + ((5 - (NW & 3)) & 3);        // row stride in words, S = 1 (mod 4)
-  static constexpr int RAWW = RB * PLANES * S;               // words per staging buffer
+  static constexpr int COPYB = (ROWB + 15 + 15) / 16 * 16;   // 16-byte blocks covering a row at any byte shift 0..15
+  static constexpr int ROWSZ = PLANES * COPYB + (PLANES + 7) / 8 * 32;   // staged bytes per output row
+  static constexpr int BUFB = RB * ROWSZ;
+  static constexpr int NUNITS = RB * PLANES;                 // bulk copies per item, one issuing thread each
   static constexpr int NLUT = REP == 32 ? 1 : 3;
+  static constexpr int LUTB = NLUT * 256 * REP * 4;
   static constexpr int ITEMS_PER_SNIP = CROP / RB;
-  static constexpr size_t SMEM = (size_t)NLUT * 256 * REP * 4 + 2 * (size_t)RAWW * 4 + 2 * PLANES * 4 + 32;
-  static_assert(CROP % RB == 0 && 256 % CPC == 0 && (RB * CROP * CPC) % 256 == 0, "item shape");
+  static constexpr size_t SMEM = 16 + (size_t)LUTB + 2 * (size_t)BUFB + 2 * NUNITS * 4 + 2 * PLANES * 4;
+  __host__ __device__ static constexpr int ploff(int pl) { return pl * COPYB + (pl >> 3) * 32; }
+  static_assert(CROP % RB == 0 && CROP % CPC == 0 && NUNITS <= THREADS && ROWSZ % 16 == 0, "item shape");
 };
 
 template <int C_PAD, int PLANES, int IMG_C, int RB, int REP, int MINB>
-__global__ void __launch_bounds__(256, MINB) preprocess_rows_kernel(const PreprocessParams p, const float* __restrict__ lut_g,
+__global__ void __launch_bounds__(224, MINB) preprocess_rows_kernel(const PreprocessParams p, const float* __restrict__ lut_g,
                                                                    int n_items) {
   using K = K1Rows<C_PAD, PLANES, IMG_C, RB, REP>;
-  extern __shared__ __align__(16) unsigned char k1_smem[];
-  float* lut = reinterpret_cast<float*>(k1_smem);
-  uint32_t* raw0 = reinterpret_cast<uint32_t*>(lut + K::NLUT * 256 * REP);
-  int* meta0 = reinterpret_cast<int*>(raw0 + 2 * K::RAWW);          // per buffer and plane: byte shift | flip << 8
-  unsigned char* s_lutof = reinterpret_cast<unsigned char*>(meta0 + 2 * PLANES);
+  extern __shared__ __align__(128) unsigned char k1_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(k1_smem);            // one mbarrier per staging buffer
+  float* lut = reinterpret_cast<float*>(k1_smem + 16);
+  unsigned char* raw0 = k1_smem + 16 + K::LUTB;
+  int* rowoff0 = reinterpret_cast<int*>(raw0 + 2 * K::BUFB);        // [buf][r][pl]: byte offset of crop column 0 (or 223
+                                                                    // when flipped) of that staged row inside the buffer
+  int* flip0 = rowoff0 + 2 * K::NUNITS;                             // [buf][pl]
   const int tid = threadIdx.x, lane = tid & 31;
   if (REP == 32) {
-    for (int i = tid; i < 256 * 32; i += 256) lut[i] = __ldg(lut_g + (i >> 5));
+    for (int i = tid; i < 256 * 32; i += K::THREADS) lut[i] = __ldg(lut_g + (i >> 5));
   } else {
-    for (int k = 0; k < p.n_luts; ++k) lut[k * 256 + tid] = __ldg(lut_g + k * 256 + tid);
+    for (int i = tid; i < p.n_luts * 256; i += K::THREADS) lut[i] = __ldg(lut_g + i);
   }
-  if (tid < 32) s_lutof[tid] = p.lut_of[tid];
+  if (tid == 0) {
+    mbar_init(&full[0], K::NUNITS);
+    mbar_init(&full[1], K::NUNITS);
+    fence_mbar_init();
+  }
+  __syncthreads();
 
   auto stage = [&](int item, int buf) {
-    const int snip = item / K::ITEMS_PER_SNIP;
-    const int y0 = (item - snip * K::ITEMS_PER_SNIP) * RB;
-    const int4* tab = reinterpret_cast<const int4*>(p.table) + (size_t)snip * PLANES;
-    uint32_t* raw = raw0 + buf * K::RAWW;
-    for (int t = tid; t < RB * PLANES * K::NW; t += 256) {
-      const int rp = t / K::NW, w = t - rp * K::NW;           // rp = r * PLANES + pl
-      const int r = rp / PLANES, pl = rp - r * PLANES;
-      const int4 e = __ldg(tab + pl);                          // {image id, crop_i, crop_j, flip}
+    if (tid < K::NUNITS) {
+      const int r = tid / PLANES, pl = tid - r * PLANES;
+      const int snip = item / K::ITEMS_PER_SNIP;
+      const int y0 = (item - snip * K::ITEMS_PER_SNIP) * RB;
+      const int4 e = __ldg(reinterpret_cast<const int4*>(p.table) + (size_t)snip * PLANES + pl);   // {id, crop_i, crop_j, flip}
       const size_t off = (size_t)e.x * p.image_bytes + ((size_t)(e.y + y0 + r) * p.img_w + e.z) * IMG_C;
-      const int sh = (int)(off & 3);                           // same for every row: img_w * IMG_C is a multiple of 4
-      if (w * 4 < sh + K::ROWB) cp_async_4(raw + rp * K::S + w, p.images + (off - sh) + 4 * (size_t)w);
-      if (w == 0 && r == 0) meta0[buf * PLANES + pl] = sh | (e.w ? 256 : 0);
+      const int sh = (int)(off & 15);
+      const uint32_t bytes = (uint32_t)(sh + K::ROWB + 15) & ~15u;
+      const int dst = r * K::ROWSZ + K::ploff(pl);
+      // pixel x of the crop reads source column x, or 223 - x when flipped (hflip of the crop = reversed columns)
+      rowoff0[buf * K::NUNITS + tid] = dst + sh + (e.w ? (K::CROP - 1) * IMG_C : 0);
+      if (r == 0) flip0[buf * PLANES + pl] = e.w ? 1 : 0;
+      mbar_arrive_expect_tx(&full[buf], bytes);
+      bulk_copy_g2s(raw0 + buf * K::BUFB + dst, p.images + (off - sh), bytes, &full[buf]);
     }
   };
 
-  // this thread's chunk group g (the same for all its chunks: 256 % CPC == 0) and, per item, its 8 channels' bases
-  const int g = tid & (K::CPC - 1);
-  int item = blockIdx.x, buf = 0;
+  // loop constants of this thread: channel group g, first pixel x0, the LUT of each of its channels
+  const int g = tid % K::CPC, x0 = tid / K::CPC;
+  const float* lutp[K::JN];
+#pragma unroll
+  for (int j = 0; j < K::JN; ++j) {
+    const int c = g * 8 + j;
+    lutp[j] = (REP == 32) ? (lut + lane) : (lut + (c < K::NCH ? p.lut_of[c] : 0) * 256);
+  }
+
+  int item = blockIdx.x;
   if (item < n_items) stage(item, 0);
-  cp_async_commit();
-  for (; item < n_items; item += gridDim.x, buf ^= 1) {
-    cp_async_wait_all();
-    __syncthreads();   // buffer `buf` has landed for everyone; everyone is done reading buffer buf^1 (previous item)
+  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    __syncthreads();   // everyone is done reading buffer buf^1 (previous item); this item's rowoff/flip are visible
     const int next = item + gridDim.x;
     if (next < n_items) stage(next, buf ^ 1);
-    cp_async_commit();
+    mbar_wait(&full[buf], (uint32_t)(it >> 1) & 1u, 70 + buf);
 
-    const unsigned char* rawb = reinterpret_cast<const unsigned char*>(raw0 + buf * K::RAWW);
-    const int* meta = meta0 + buf * PLANES;
-    int base[8], step[8];
+    const unsigned char* raw = raw0 + buf * K::BUFB;
+    const int* rowoff = rowoff0 + buf * K::NUNITS;
+    int xoff[K::JN], xd[K::JN];      // byte offset of pixel x0 relative to a row's column 0 / of one XSTEP
+    bool valid[K::JN];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < K::JN; ++j) {
       const int c = g * 8 + j;
-      base[j] = -1; step[j] = 0;
-      if (j < K::NCH && c < K::NCH) {
-        const int pl = c / IMG_C, kk = c - pl * IMG_C;
-        const int m = meta[pl];
-        const bool flip = (m & 256) != 0;
-        // pixel x of the crop reads source column x, or 223 - x when flipped (hflip of the crop = reversed columns)
-        base[j] = pl * K::S * 4 + (m & 3) + kk + (flip ? (K::CROP - 1) * IMG_C : 0);
-        step[j] = flip ? -IMG_C : IMG_C;
-      }
+      valid[j] = c < K::NCH;
+      const int pl = valid[j] ? c / IMG_C : 0;
+      const int step = flip0[buf * PLANES + pl] ? -IMG_C : IMG_C;
+      xoff[j] = x0 * step + (c - pl * IMG_C);
+      xd[j] = K::XSTEP * step;
     }
     const int snip = item / K::ITEMS_PER_SNIP;
     const int y0 = (item - snip * K::ITEMS_PER_SNIP) * RB;
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                          ((size_t)snip * K::CROP + y0) * K::CROP * C_PAD);
-#pragma unroll 2
-    for (int k = tid; k < RB * K::CROP * K::CPC; k += 256) {
-      const int px = k / K::CPC;                               // r * 224 + x
-      const int r = px / K::CROP, x = px - r * K::CROP;
-      const int rowoff = r * PLANES * K::S * 4;
-      float v[8];
+                                          ((size_t)snip * K::CROP + y0) * K::CROP * C_PAD) + tid;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = 0.f;
-        if (j < K::NCH && base[j] >= 0) {
-          const unsigned b = rawb[rowoff + base[j] + x * step[j]];
-          v[j] = (REP == 32) ? lut[b * 32 + lane] : lut[s_lutof[g * 8 + j] * 256 + b];
-        }
+    for (int r = 0; r < RB; ++r) {
+      int a[K::JN];
+#pragma unroll
+      for (int j = 0; j < K::JN; ++j) {
+        const int c = g * 8 + j;
+        const int pl = valid[j] ? c / IMG_C : 0;
+        a[j] = rowoff[r * PLANES + pl] + xoff[j];
       }
-      const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), bb = __floats2bfloat162_rn(v[2], v[3]);
-      const __nv_bfloat162 cc = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-      uint4 o;
-      o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&bb);
-      o.z = *reinterpret_cast<const uint32_t*>(&cc); o.w = *reinterpret_cast<const uint32_t*>(&d);
-      dst[k] = o;
+#pragma unroll
+      for (int i = 0; i < K::CPC; ++i) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = 0.f;
+          if (j < K::JN) {
+            if (valid[j < K::JN ? j : 0]) {
+              const unsigned b = raw[a[j < K::JN ? j : 0] + i * xd[j < K::JN ? j : 0]];
+              v[j] = lutp[j < K::JN ? j : 0][b * REP];
+            }
+          }
+        }
+        const __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
+        const __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&q0); o.y = *reinterpret_cast<const uint32_t*>(&q1);
+        o.z = *reinterpret_cast<const uint32_t*>(&q2); o.w = *reinterpret_cast<const uint32_t*>(&q3);
+        dst[(r * K::CPC + i) * K::THREADS] = o;
+      }
     }
   }
-  cp_async_wait_all();
 }
 
 static int sm_count_cached() {
@@ -370,7 +401,7 @@ static cudaError_t launch_preprocess_rows(const PreprocessParams& p, const float
   const int n_items = p.n * K::ITEMS_PER_SNIP;
   const int grid = std::min(n_items, sm_count_cached() * MINB);
   count_launch();
-  kern<<<grid, 256, K::SMEM, st>>>(p, lut, n_items);
+  kern<<<grid, K::THREADS, K::SMEM, st>>>(p, lut, n_items);
   return cudaGetLastError();
 }
 
@@ -397,14 +428,14 @@ cudaError_t launch_preprocess(const uint8_t* images, size_t image_bytes, int img
   const long long total = (long long)n * crop * crop;
   if (total == 0) return cudaSuccess;
   const bool rgb = (planes == 1 && img_c == 3), flow = (planes == 20 && img_c == 1);
-  // row-staged path: the two network-input shapes of the path, 4-byte aligned image rows
+  // row-staged path: the two network-input shapes of the path, 16-byte aligned store base and image size
   const bool rows_ok = out_mode == 0 && crop == 224 && p.n_luts > 0 && n <= (1 << 22) &&
-                       (reinterpret_cast<uintptr_t>(images) & 3) == 0 && image_bytes % 4 == 0 &&
-                       ((size_t)img_w * img_c) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+                       (reinterpret_cast<uintptr_t>(images) & 15) == 0 && image_bytes % 16 == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (rows_ok && ((rgb && c_pad == 16) || (flow && c_pad == 32 && p.n_luts == 1))) {
     float* lut = cached_lut(p, st);
     if (lut == nullptr) return cudaErrorMemoryAllocation;
-    if (rgb) return launch_preprocess_rows<16, 1, 3, 8, 1, 6>(p, lut, st);
+    if (rgb) return launch_preprocess_rows<16, 1, 3, 7, 1, 6>(p, lut, st);
     return launch_preprocess_rows<32, 20, 1, 4, 32, 3>(p, lut, st);
   }
   // fast path: 4 pixels per thread (needs crop % 4 == 0, a LUT, one of the two shapes of the path, n <= 65535)
