@@ -211,6 +211,22 @@ typedef struct va_jpeg_huff {
 va_status va_jpeg_decode(const uint8_t* bitstreams, const va_jpeg_image* images, int n_images, const uint16_t* qtables,
                          int n_qtables, const va_jpeg_huff* htables, int n_htables, uint8_t* out, va_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Linear SVM fit of the late-fusion step.  Replaces `svm.LinearSVC().fit(svmTrainData,
+ * svmTrainLabels)` (combinedModel.py:34-35): scikit-learn's defaults = LIBLINEAR's L2-regularised L2-loss dual
+ * coordinate descent, one-vs-rest, intercept as an extra constant feature `bias` (intercept_scaling, 1), C = 1,
+ * tol = 1e-4 on the projected-gradient range of an epoch, max_iter = 1000 epochs.  fp64 throughout.
+ *   X fp64 [V][F] row-major (F <= 1024; the path has F = 2*256); class_index int32 [V] in [0, n_classes) = index into
+ *   the sorted unique labels (classes_).  n_classes == 2 fits ONE problem with class 1 positive (coef [1][F], like
+ *   scikit-learn); otherwise n_classes problems.  bias <= 0: no intercept.
+ *   out: coef fp64 [P][F], intercept fp64 [P], epochs int32 [P] (epochs run per problem; == max_iter means the
+ *   tolerance was not reached, scikit-learn's ConvergenceWarning), P = n_classes == 2 ? 1 : n_classes.
+ *   work: fp64 [(P + 1) * V] scratch (dual variables, Q_ii).
+ * --------------------------------------------------------------------------------------------------------- */
+va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, int n_classes, double C, double bias,
+                     double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
+                     va_stream_t stream);
+
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,

@@ -1,0 +1,126 @@
+"""TEST INFRASTRUCTURE (oracle side) -- the linear SVM fit of the late-fusion step, numpy restatement.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this package.
+
+Reference call site: `linearClassifier = svm.LinearSVC(); linearClassifier.fit(svmTrainData, svmTrainLabels)`
+(Sheet03/combinedModel.py:34-35), i.e. scikit-learn's LinearSVC with its defaults (penalty l2, loss squared_hinge,
+C=1, one-vs-rest, fit_intercept with intercept_scaling 1, tol 1e-4, max_iter 1000).  The arithmetic lives in a
+third-party dependency that is not under /root/reference: scikit-learn's vendored LIBLINEAR (the reference pins no
+version; installed here: scikit-learn 1.9.0, LIBLINEAR 2.x), solver L2R_L2LOSS_SVC_DUAL.  Its published algorithm
+(Hsieh et al., "A Dual Coordinate Descent Method for Large-scale Linear SVM", ICML 2008, Algorithm 1; liblinear
+`solve_l2r_l1l2_svc`) is restated here:
+
+  per class c (one-vs-rest, y_i = +1 if label_i == classes[c] else -1), features x_i extended by one constant `bias`:
+    minimise over alpha >= 0:  1/2 alpha' (Q + D) alpha - e' alpha,   Q_ij = y_i y_j x_i.x_j,  D_ii = 1 / (2 C)
+    w = sum_i alpha_i y_i x_i ;  one pass ("epoch") visits every i once:
+       G  = y_i w.x_i - 1 + D_ii alpha_i
+       PG = G if alpha_i > 0 else min(G, 0)
+       if |PG| > 1e-12:  alpha_i <- max(alpha_i - G / (x_i.x_i + D_ii), 0);  w += (alpha_i - old) y_i x_i
+    stop after an epoch with max PG - min PG <= tol (or max_iter epochs)
+  coef_[c] = w[:F], intercept_[c] = bias * w[F].
+
+The problem is strictly convex in w, so every converging visiting order reaches the same coef_/intercept_.  Two
+deliberate differences from LIBLINEAR, neither of which changes the optimum: the visiting order is a deterministic
+affine permutation per epoch (`epoch_order`; LIBLINEAR draws random swaps from an unseeded generator, so the reference
+itself is not reproducible beyond the solver tolerance), and there is no active-set shrinking.  The CUDA solver
+(`va_svm_fit`) follows exactly this statement, including `epoch_order`, so GPU and oracle agree to rounding.
+
+Pinning: `oracle/make_golden.py` fits scikit-learn's LinearSVC (this container) at tight tolerance on a seeded
+problem and stores data + coefficients in tests/golden/svm_fit.npz; tests check this restatement against it.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def _mix32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def epoch_order_params(epoch: int, n: int):
+    """(a, b) of the epoch's visiting order i -> (a * i + b) mod n, gcd(a, n) == 1; pure uint32 arithmetic shared with
+    the CUDA solver (csrc/va_svm_fit.cu::epoch_order_params)."""
+    h = _mix32((epoch * 0x9E3779B1 + 0x7F4A7C15) & 0xFFFFFFFF)
+    a = h % n
+    while math.gcd(a, n) != 1:
+        a = (a + 1) % n
+    b = _mix32(h ^ 0x85EBCA6B) % n
+    return a, b
+
+
+def epoch_order(epoch: int, n: int) -> np.ndarray:
+    a, b = epoch_order_params(epoch, n)
+    return ((a * np.arange(n, dtype=np.int64) + b) % n).astype(np.int64)
+
+
+def fit_linear_svc(X: np.ndarray, labels: np.ndarray, C: float = 1.0, bias: float = 1.0, tol: float = 1e-4,
+                   max_iter: int = 1000):
+    """Returns (coef [n_classes or 1, F], intercept, classes, epochs per class).  Two classes give ONE row (positive
+    class = classes[1]), as scikit-learn stores it.  All classes step through the same visiting order; a class stops
+    updating after its own converged epoch, so the result equals solving the classes one after another."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    V, F = X.shape
+    classes = np.unique(labels)
+    if len(classes) < 2:
+        raise ValueError("This solver needs samples of at least 2 classes in the data")
+    pos = classes[1:] if len(classes) == 2 else classes
+    K = len(pos)
+    Y = np.where(labels[None, :] == pos[:, None], 1.0, -1.0)                 # [K, V]
+    use_bias = bias > 0
+    Xe = np.concatenate([X, np.full((V, 1), bias)], axis=1) if use_bias else X
+    D = 0.5 / C
+    QD = np.einsum("ij,ij->i", Xe, Xe) + D
+    W = np.zeros((K, Xe.shape[1]))
+    alpha = np.zeros((K, V))
+    active = np.ones(K, dtype=bool)
+    epochs = np.zeros(K, dtype=np.int64)
+    for epoch in range(max_iter):
+        if not active.any():
+            break
+        pgmax = np.full(K, -np.inf)
+        pgmin = np.full(K, np.inf)
+        for i in epoch_order(epoch, V):
+            x = Xe[i]
+            yi = Y[:, i]
+            ai = alpha[:, i]
+            G = yi * (W @ x) - 1.0 + ai * D
+            PG = np.where(ai > 0, G, np.minimum(G, 0.0))
+            pgmax = np.where(active, np.maximum(pgmax, PG), pgmax)
+            pgmin = np.where(active, np.minimum(pgmin, PG), pgmin)
+            upd = active & (np.abs(PG) > 1e-12)
+            if upd.any():
+                new = np.maximum(ai - G / QD[i], 0.0)
+                d = np.where(upd, (new - ai) * yi, 0.0)
+                alpha[:, i] = np.where(upd, new, ai)
+                W += d[:, None] * x[None, :]
+        epochs[active] += 1
+        active &= ~((pgmax - pgmin) <= tol)
+    coef = W[:, :F].copy()
+    intercept = W[:, F] * bias if use_bias else np.zeros(K)
+    return coef, intercept, classes, epochs
+
+
+def decision(X, coef, intercept, classes):
+    """LinearSVC.decision_function / predict (combinedModel.py:38)."""
+    s = np.asarray(X, dtype=np.float64) @ coef.T + intercept
+    if coef.shape[0] == 1:
+        return s, classes[(s[:, 0] > 0).astype(int)]
+    return s, classes[np.argmax(s, axis=1)]
+
+
+def primal_objective(X, labels, coef, intercept, classes, C=1.0, bias=1.0):
+    """LIBLINEAR's primal per class: 1/2 (|w|^2 + (b/bias)^2) + C sum max(0, 1 - y (w.x + b))^2 -- the regularised
+    intercept is the extended feature's weight b / bias."""
+    pos = classes[1:] if len(classes) == 2 else classes
+    Y = np.where(labels[None, :] == pos[:, None], 1.0, -1.0)
+    m = 1.0 - Y * (np.asarray(X, dtype=np.float64) @ coef.T + intercept).T
+    wb = intercept / bias if bias > 0 else np.zeros_like(intercept)
+    return 0.5 * ((coef ** 2).sum(1) + wb ** 2) + C * (np.maximum(m, 0.0) ** 2).sum(1)

@@ -3,7 +3,7 @@
 
 `combineDescriptors` keeps the CSV wire format (it is a one-off host-side join); per-video consensus, the 512-d
 concatenation, LinearSVC scoring (argmax_c X.W_c + b_c) and the class-score average run in the CUDA fusion kernel
-(`va_fuse`).  Fitting the SVM stays in scikit-learn on the host (out of scope).
+(`va_fuse`); fitting the SVM (reference :34-35) is `va_svm_fit`.
 """
 from __future__ import annotations
 
@@ -31,7 +31,7 @@ def combineDescriptors(spatialCsv, temporalCsv):
 class CombinedModel:
     """Two-stream late fusion on the GPU.
 
-    * `fit(X, y)`: scikit-learn LinearSVC on the host (reference :34-35), coefficients uploaded once.
+    * `fit(X, y)`: LinearSVC().fit of reference :34-35 on the device (`va_svm_fit`, fp64 dual coordinate descent).
     * `predict(X)`: reference :38 -- `classes_[argmax(X @ coef.T + intercept)]`, scored by `va_fuse` in fp64.
     * `fuse(...)`: the whole K4 step for a batch of videos straight from per-snippet network outputs.
     """
@@ -43,11 +43,28 @@ class CombinedModel:
         self._w_dev = self._b_dev = None
 
     # ---- SVM
-    def fit(self, descriptors: np.ndarray, labels: np.ndarray):
-        from sklearn import svm
-        clf = svm.LinearSVC()
-        clf.fit(descriptors, labels)
-        return self.set_svm(clf.coef_, clf.intercept_, clf.classes_)
+    def fit(self, descriptors, labels, C: float = 1.0, intercept_scaling: float = 1.0, tol: float = 1e-4,
+            max_iter: int = 1000):
+        """reference :34-35 `svm.LinearSVC().fit(X, y)` -- same model (one-vs-rest, L2 penalty, squared hinge, regularised
+        intercept) and the same solver family and stopping rule (LIBLINEAR's dual coordinate descent, projected-gradient
+        range <= tol or max_iter epochs), run by `va_svm_fit` on the device in fp64.  `n_iter_` holds the epochs per class
+        problem; reaching max_iter is scikit-learn's ConvergenceWarning case and is reported the same way."""
+        y = np.asarray(labels.detach().cpu() if isinstance(labels, torch.Tensor) else labels)
+        classes, index = np.unique(y, return_inverse=True)
+        if len(classes) < 2:
+            raise ValueError("This solver needs samples of at least 2 classes in the data, but the data contains only "
+                             "one class: %r" % classes[0])
+        X = descriptors if isinstance(descriptors, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(descriptors))
+        X = X.to(device="cuda", dtype=torch.float64).contiguous()
+        idx = torch.from_numpy(index.astype(np.int32)).cuda()
+        coef, intercept, epochs = ops.svm_fit(X, idx, len(classes), C_reg=C, bias=intercept_scaling, tol=tol,
+                                              max_iter=max_iter)
+        self.n_iter_ = epochs.cpu().numpy()
+        if int(self.n_iter_.max()) >= max_iter:
+            import warnings
+            warnings.warn("va_svm_fit reached max_iter before the tolerance (scikit-learn: 'Liblinear failed to "
+                          "converge, increase the number of iterations.')", RuntimeWarning)
+        return self.set_svm(coef.cpu().numpy(), intercept.cpu().numpy(), classes)
 
     def set_svm(self, coef, intercept, classes=None):
         coef = np.ascontiguousarray(coef, dtype=np.float64)

@@ -524,6 +524,20 @@ va_status va_jpeg_decode(const uint8_t* bitstreams, const va_jpeg_image* images,
   return VA_OK;
 }
 
+va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, int n_classes, double C, double bias,
+                     double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
+                     va_stream_t stream) {
+  if (!X || !class_index || !coef || !intercept || !epochs || !work) return fail(VA_ERR_INVALID, "va_svm_fit: NULL argument");
+  if (V < 1 || F < 1 || F > 1024) return fail(VA_ERR_INVALID, "va_svm_fit: bad sizes V=%d F=%d (F <= 1024)", V, F);
+  if (n_classes < 2) return fail(VA_ERR_INVALID, "va_svm_fit: needs samples of at least 2 classes, got %d", n_classes);
+  if (!(C > 0.0) || !(tol >= 0.0) || max_iter < 1) return fail(VA_ERR_INVALID, "va_svm_fit: bad C / tol / max_iter");
+  if (va_status s = require_sm100()) return s;
+  const char* e = va::svm_fit_run(X, class_index, V, F, n_classes, C, bias, tol, max_iter, coef, intercept, epochs, work,
+                                  static_cast<cudaStream_t>(stream));
+  if (e) return fail(VA_ERR_INVALID, "va_svm_fit: %s", e);
+  return VA_OK;
+}
+
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c, uint32_t seed,
                         uint32_t first_id, va_stream_t stream) {
   if (!images) return fail(VA_ERR_INVALID, "va_synth_fill: NULL");

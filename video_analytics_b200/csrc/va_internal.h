@@ -59,6 +59,11 @@ const char* jpeg_decode_run(const unsigned char* bitstreams, const void* images_
                             const unsigned short* qtables_host, int n_q, const void* htables_host, int n_h,
                             unsigned char* out, cudaStream_t st);
 
+// ---- linear SVM fit (va_svm_fit.cu)
+const char* svm_fit_run(const double* X, const int32_t* class_index, int V, int F, int n_classes, double C, double bias,
+                        double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
+                        cudaStream_t st);
+
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
 struct ConvLayerDesc {
   const void* x;        // bf16 NHWC [n][H][W][cin_pad]

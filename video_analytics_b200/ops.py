@@ -88,6 +88,26 @@ def preprocess(images: torch.Tensor, image_shape: Sequence[int], index_table: to
     return out
 
 
+def svm_fit(X: torch.Tensor, class_index: torch.Tensor, n_classes: int, *, C_reg: float = 1.0, bias: float = 1.0,
+            tol: float = 1e-4, max_iter: int = 1000):
+    """LinearSVC().fit (reference combinedModel.py:34-35) on the device: one-vs-rest L2-regularised squared-hinge SVM by
+    dual coordinate descent in fp64.  X fp64 [V, F] (device), class_index int32 [V] in [0, n_classes).  Returns
+    (coef [P, F], intercept [P], epochs [P]) device tensors, P = 1 for two classes else n_classes."""
+    _need_cuda(X, class_index)
+    assert X.dtype == torch.float64 and X.dim() == 2 and X.is_contiguous()
+    assert class_index.dtype == torch.int32 and class_index.numel() == X.shape[0]
+    V, F = X.shape
+    P = 1 if n_classes == 2 else n_classes
+    dev = X.device
+    coef = torch.empty((max(P, 0), F), dtype=torch.float64, device=dev)
+    intercept = torch.empty((max(P, 0),), dtype=torch.float64, device=dev)
+    epochs = torch.empty((max(P, 0),), dtype=torch.int32, device=dev)
+    work = torch.empty(((max(P, 0) + 1) * max(V, 1),), dtype=torch.float64, device=dev)
+    check(_lib.load().va_svm_fit(ptr(X), ptr(class_index), V, F, n_classes, C_reg, bias, tol, max_iter, ptr(coef),
+                                 ptr(intercept), ptr(epochs), ptr(work), stream_ptr()), "va_svm_fit")
+    return coef, intercept, epochs
+
+
 def fuse(desc_s, desc_t, score_s, score_t, video_offsets: torch.Tensor, *, svm_w=None, svm_b=None, w_s=1.0, w_t=1.0,
          out: Optional[dict] = None) -> dict:
     """K4.  Per-video consensus (sequential-sum means) + late fusion.  Returns dict with video_desc [V,2D],
