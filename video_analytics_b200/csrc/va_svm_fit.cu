@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(32) svm_dcd_kernel(const double* __restrict__ 
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) x[j] = xn[j];
       if (i + 1 < n) {
-        nxt = (uint32_t)(((uint64_t)a * (i + 1) + b) % n);
+        nxt += a;                                // (a * (i + 1) + b) mod n without the 64-bit division: a, nxt < n
+        if (nxt >= n) nxt -= n;
         load(nxt);
       }
       // the step's critical path: up to four independent FMA chains, then the butterfly
