@@ -55,6 +55,19 @@ def test_oracle_two_classes_single_row(gold):
         sf.fit_linear_svc(X, np.ones(len(X), dtype=int))
 
 
+def test_independent_newton_oracle_vs_sklearn_fixture(gold):
+    """The second, independent statement of the same optimum (primal finite Newton) -- used as the full-size checker of
+    the GPU solver -- against scikit-learn's converged coefficients and against the coordinate-descent restatement."""
+    from oracle import svm_fit as sf
+    X = gold["X"]
+    c, i, classes, its = sf.fit_primal_newton(X, gold["labels"])
+    assert its < 50 and np.abs(c - gold["sk_coef"]).max() < 1e-6 and np.abs(i - gold["sk_intercept"]).max() < 1e-6
+    c2, i2, _, _ = sf.fit_primal_newton(X, gold["labels2"])
+    assert c2.shape == (1, X.shape[1]) and np.abs(c2 - gold["sk_coef2"]).max() < 1e-6
+    cd, icd, _, _ = sf.fit_linear_svc(X, gold["labels2"], tol=1e-10, max_iter=20000)
+    assert np.abs(cd - c2).max() < 1e-7 and np.abs(icd - i2).max() < 1e-7
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_gpu_fit_matches_oracle_and_sklearn(gold):
@@ -130,3 +143,9 @@ def test_gpu_fit_full_fusion_size_optimality():
     assert float(((primal - dual).abs() / primal).max()) < 1e-5
     pred = (coef @ Xd.T + ic[:, None]).argmax(0)
     assert float((pred == idx).double().mean()) > 0.99
+    # and against the independent primal Newton oracle at this size (10 s of numpy; the coordinate-descent oracle at
+    # tol 1e-7 is 2.4e-7 from it, max |w| = 0.12)
+    from oracle import svm_fit as sf
+    cn, icn, _, _ = sf.fit_primal_newton(X.numpy(), lab.numpy())
+    assert np.abs(coef.cpu().numpy() - cn).max() < 5e-6 and np.abs(ic.cpu().numpy() - icn).max() < 5e-6
+    assert np.array_equal((Xd.cpu().numpy() @ cn.T + icn).argmax(1), pred.cpu().numpy())
