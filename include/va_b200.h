@@ -221,7 +221,7 @@ va_status va_jpeg_decode(const uint8_t* bitstreams, const va_jpeg_image* images,
  *   scikit-learn); otherwise n_classes problems.  bias <= 0: no intercept.
  *   out: coef fp64 [P][F], intercept fp64 [P], epochs int32 [P] (epochs run per problem; == max_iter means the
  *   tolerance was not reached, scikit-learn's ConvergenceWarning), P = n_classes == 2 ? 1 : n_classes.
- *   work: fp64 [(P + 1) * V] scratch (dual variables, Q_ii).
+ *   work: fp64 [(P + 1) * V + (P * V + 1) / 2] scratch (Q_ii, dual variables, active sets as int32).
  * --------------------------------------------------------------------------------------------------------- */
 va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, int n_classes, double C, double bias,
                      double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,

@@ -16,14 +16,16 @@ version; installed here: scikit-learn 1.9.0, LIBLINEAR 2.x), solver L2R_L2LOSS_S
        G  = y_i w.x_i - 1 + D_ii alpha_i
        PG = G if alpha_i > 0 else min(G, 0)
        if |PG| > 1e-12:  alpha_i <- max(alpha_i - G / (x_i.x_i + D_ii), 0);  w += (alpha_i - old) y_i x_i
-    stop after an epoch with max PG - min PG <= tol (or max_iter epochs)
+    stop after an epoch over ALL samples with max PG - min PG <= tol (or max_iter epochs); samples with alpha_i = 0
+    whose gradient exceeds the previous epoch's largest PG sit out until then ("shrinking", see fit_linear_svc)
   coef_[c] = w[:F], intercept_[c] = bias * w[F].
 
 The problem is strictly convex in w, so every converging visiting order reaches the same coef_/intercept_.  Two
 deliberate differences from LIBLINEAR, neither of which changes the optimum: the visiting order is a deterministic
 affine permutation per epoch (`epoch_order`; LIBLINEAR draws random swaps from an unseeded generator, so the reference
-itself is not reproducible beyond the solver tolerance), and there is no active-set shrinking.  The CUDA solver
-(`va_svm_fit`) follows exactly this statement, including `epoch_order`, so GPU and oracle agree to rounding.
+itself is not reproducible beyond the solver tolerance), and shrunk samples leave the active set at the end of the
+epoch instead of on the spot.  The CUDA solver (`va_svm_fit`) follows exactly this statement, including `epoch_order`,
+so GPU and oracle agree to rounding.
 
 Pinning: `oracle/make_golden.py` fits scikit-learn's LinearSVC (this container) at tight tolerance on a seeded
 problem and stores data + coefficients in tests/golden/svm_fit.npz; tests check this restatement against it.
@@ -62,50 +64,76 @@ def epoch_order(epoch: int, n: int) -> np.ndarray:
 
 
 def fit_linear_svc(X: np.ndarray, labels: np.ndarray, C: float = 1.0, bias: float = 1.0, tol: float = 1e-4,
-                   max_iter: int = 1000):
+                   max_iter: int = 1000, shrinking: bool = True, return_steps: bool = False):
     """Returns (coef [n_classes or 1, F], intercept, classes, epochs per class).  Two classes give ONE row (positive
-    class = classes[1]), as scikit-learn stores it.  All classes step through the same visiting order; a class stops
-    updating after its own converged epoch, so the result equals solving the classes one after another."""
+    class = classes[1]), as scikit-learn stores it.  One class problem after the other, LIBLINEAR's loop structure:
+
+      active set = all samples; PGmax_old = +inf
+      epoch: visit the active samples in `epoch_order(epoch, n_active)`; for sample s
+                 G = y_s w.x_s - 1 + D alpha_s
+                 alpha_s == 0 and G > PGmax_old  -> s leaves the active set (no update, not counted in the PG range)
+                 PG = G if alpha_s > 0 else min(G, 0);  track max / min PG;  update alpha_s, w if |PG| > 1e-12
+             PG range <= tol:  all samples were visited -> done;  else re-activate all, PGmax_old = +inf, next epoch
+             otherwise PGmax_old = PGmax if PGmax > 0 else +inf
+      (LIBLINEAR's second bound, alpha == U with G < PGmin_old, never applies: U = inf for the squared hinge.)
+
+    The samples that left are removed at the END of the epoch, keeping the order of the rest (LIBLINEAR swaps a leaving
+    sample with the last active one on the spot; which heuristic trims the active set does not change the optimum)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     V, F = X.shape
     classes = np.unique(labels)
     if len(classes) < 2:
         raise ValueError("This solver needs samples of at least 2 classes in the data")
     pos = classes[1:] if len(classes) == 2 else classes
-    K = len(pos)
-    Y = np.where(labels[None, :] == pos[:, None], 1.0, -1.0)                 # [K, V]
     use_bias = bias > 0
     Xe = np.concatenate([X, np.full((V, 1), bias)], axis=1) if use_bias else X
     D = 0.5 / C
     QD = np.einsum("ij,ij->i", Xe, Xe) + D
-    W = np.zeros((K, Xe.shape[1]))
-    alpha = np.zeros((K, V))
-    active = np.ones(K, dtype=bool)
-    epochs = np.zeros(K, dtype=np.int64)
-    for epoch in range(max_iter):
-        if not active.any():
-            break
-        pgmax = np.full(K, -np.inf)
-        pgmin = np.full(K, np.inf)
-        for i in epoch_order(epoch, V):
-            x = Xe[i]
-            yi = Y[:, i]
-            ai = alpha[:, i]
-            G = yi * (W @ x) - 1.0 + ai * D
-            PG = np.where(ai > 0, G, np.minimum(G, 0.0))
-            pgmax = np.where(active, np.maximum(pgmax, PG), pgmax)
-            pgmin = np.where(active, np.minimum(pgmin, PG), pgmin)
-            upd = active & (np.abs(PG) > 1e-12)
-            if upd.any():
-                new = np.maximum(ai - G / QD[i], 0.0)
-                d = np.where(upd, (new - ai) * yi, 0.0)
-                alpha[:, i] = np.where(upd, new, ai)
-                W += d[:, None] * x[None, :]
-        epochs[active] += 1
-        active &= ~((pgmax - pgmin) <= tol)
+    W, epochs, steps = [], [], []
+    for c in pos:
+        y = np.where(labels == c, 1.0, -1.0)
+        w = np.zeros(Xe.shape[1])
+        alpha = np.zeros(V)
+        idx = np.arange(V)
+        n, pgmax_old, it, nsteps = V, np.inf, 0, 0
+        while it < max_iter:
+            pgmax, pgmin = -np.inf, np.inf
+            keep = np.ones(n, dtype=bool)
+            if n > 0:
+                a, b = epoch_order_params(it, n)
+                for i in range(n):
+                    p_ = (a * i + b) % n
+                    s = idx[p_]
+                    nsteps += 1
+                    ai = alpha[s]
+                    G = y[s] * (w @ Xe[s]) - 1.0 + ai * D
+                    if ai == 0.0 and shrinking and G > pgmax_old:
+                        keep[p_] = False
+                        continue
+                    PG = G if ai > 0 else min(G, 0.0)
+                    pgmax, pgmin = max(pgmax, PG), min(pgmin, PG)
+                    if abs(PG) > 1e-12:
+                        new = max(ai - G / QD[s], 0.0)
+                        w += ((new - ai) * y[s]) * Xe[s]
+                        alpha[s] = new
+            it += 1
+            if pgmax - pgmin <= tol:
+                if n == V and keep.all():        # the range was taken over ALL samples
+                    break
+                idx, n, pgmax_old = np.arange(V), V, np.inf
+                continue
+            idx = idx[:n][keep]
+            n = len(idx)
+            pgmax_old = pgmax if pgmax > 0 else np.inf
+        W.append(w)
+        epochs.append(it)
+        steps.append(nsteps)
+    W = np.array(W)
     coef = W[:, :F].copy()
-    intercept = W[:, F] * bias if use_bias else np.zeros(K)
-    return coef, intercept, classes, epochs
+    intercept = W[:, F] * bias if use_bias else np.zeros(len(pos))
+    if return_steps:
+        return coef, intercept, classes, np.array(epochs), np.array(steps)
+    return coef, intercept, classes, np.array(epochs)
 
 
 def decision(X, coef, intercept, classes):

@@ -34,8 +34,8 @@ def main():
         ms = e0.elapsed_time(e1)
         ep = epochs.cpu().numpy()
         pred = (coef @ Xd.T + ic[:, None]).argmax(0)
-        print(f"va_svm_fit tol={tol:g}: {ms:.1f} ms, epochs min/mean/max {ep.min()}/{ep.mean():.0f}/{ep.max()}, "
-              f"{ms * 1e3 / ep.max() / V:.3f} us per coordinate step (slowest class), train acc {(pred == idx).double().mean():.4f}")
+        print(f"va_svm_fit tol={tol:g}: {ms:.1f} ms, epochs min/mean/max {ep.min()}/{ep.mean():.0f}/{ep.max()} "
+              f"(an epoch visits the ACTIVE samples only), train acc {(pred == idx).double().mean():.4f}")
         if tol == 1e-4:
             c_gpu = coef.cpu().numpy()
     t0 = time.perf_counter()

@@ -1,7 +1,8 @@
 // Linear SVM fit of the late-fusion step: replaces `svm.LinearSVC().fit(X, y)` at reference
 // Sheet03/combinedModel.py:34-35, i.e. LIBLINEAR's L2-regularised L2-loss dual coordinate descent, one-vs-rest.
-// The statement of the algorithm (and what deliberately differs from LIBLINEAR: a deterministic visiting order, no
-// shrinking) is in oracle/svm_fit.py; this file follows it step for step, in fp64.
+// The statement of the algorithm (and what deliberately differs from LIBLINEAR: a deterministic visiting order, shrunk
+// samples removed at the end of an epoch instead of on the spot) is in oracle/svm_fit.py; this file follows it step for
+// step, in fp64.
 //
 // Mapping: coordinate descent is sequential in the samples of ONE class problem (every step reads the w the previous
 // step wrote) and the classes are independent, so each class is one warp: lane l keeps w[l], w[l+32], ... of the
@@ -50,79 +51,126 @@ template <int KMAX>
 __global__ void __launch_bounds__(32) svm_dcd_kernel(const double* __restrict__ X, int V, int F,
                                                      const int32_t* __restrict__ class_index, int first_class,
                                                      const double* __restrict__ qd, double D, double bias, double tol,
-                                                     int max_iter, double* __restrict__ alpha, double* __restrict__ coef,
-                                                     double* __restrict__ intercept, int32_t* __restrict__ epochs) {
+                                                     int max_iter, double* __restrict__ alpha, int32_t* __restrict__ active,
+                                                     double* __restrict__ coef, double* __restrict__ intercept,
+                                                     int32_t* __restrict__ epochs) {
   const int k = blockIdx.x, cls = k + first_class, lane = threadIdx.x;
   double* al = alpha + (size_t)k * V;          // zeroed by the caller
+  int32_t* idx = active + (size_t)k * V;       // the active set, in visiting-position order
   double w[KMAX], x[KMAX], xn[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) w[j] = 0.0;
   double wb = 0.0;
-  const uint32_t n = (uint32_t)V;
-  int done_epochs = 0;
-  for (int epoch = 0; epoch < max_iter; ++epoch) {
-    uint32_t a, b;
-    epoch_order_params((uint32_t)epoch, n, a, b);
+  for (int i = lane; i < V; i += 32) idx[i] = i;
+  __syncwarp();
+  uint32_t n = (uint32_t)V;                    // active samples
+  double pgmax_old = INFINITY;
+  int it = 0;
+  while (it < max_iter) {
     double pgmax = -INFINITY, pgmin = INFINITY;
-    uint32_t nxt = b % n;
-    double a_n, q_n, y_n;
-    auto load = [&](uint32_t idx) {
-      const double* row = X + (size_t)idx * F;
+    bool any_left = false;
+    if (n > 0) {
+      uint32_t a, b;
+      epoch_order_params((uint32_t)it, n, a, b);
+      // software pipeline: sample index two steps ahead, its row / alpha / Q_ii / label one step ahead
+      double a_n = 0.0, q_n = 1.0, y_n = 1.0;
+      auto load_row = [&](int32_t s) {
+        const double* row = X + (size_t)s * F;
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) xn[j] = (lane + 32 * j < F) ? row[lane + 32 * j] : 0.0;
-      a_n = al[idx];
-      q_n = qd[idx];
-      y_n = (class_index[idx] == cls) ? 1.0 : -1.0;
-    };
-    load(nxt);
-    for (uint32_t i = 0; i < n; ++i) {
-      const uint32_t cur = nxt;
-      const double ai = a_n, qi = q_n, yi = y_n;
+        for (int j = 0; j < KMAX; ++j) xn[j] = (lane + 32 * j < F) ? row[lane + 32 * j] : 0.0;
+        a_n = al[s];
+        q_n = qd[s];
+        y_n = (class_index[s] == cls) ? 1.0 : -1.0;
+      };
+      uint32_t pos1 = b;                       // position of step i + 1 while step i runs (b < n)
+      int32_t s1 = idx[pos1];
+      load_row(s1);
+      uint32_t pos2 = pos1 + a;                // (a * i + b) mod n without a division: a, pos < n
+      if (pos2 >= n) pos2 -= n;
+      int32_t s2 = (n > 1) ? idx[pos2] : 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        const int32_t cur = s1;
+        const uint32_t curpos = pos1;
+        const double ai = a_n, qi = q_n, yi = y_n;
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) x[j] = xn[j];
-      if (i + 1 < n) {
-        nxt += a;                                // (a * (i + 1) + b) mod n without the 64-bit division: a, nxt < n
-        if (nxt >= n) nxt -= n;
-        load(nxt);
-      }
-      // the step's critical path: up to four independent FMA chains, then the butterfly
-      constexpr int NACC = KMAX >= 4 ? 4 : KMAX;
-      double acc[NACC];
+        for (int j = 0; j < KMAX; ++j) x[j] = xn[j];
+        if (i + 1 < n) {
+          s1 = s2;
+          pos1 = pos2;
+          load_row(s1);
+          if (i + 2 < n) {
+            pos2 += a;
+            if (pos2 >= n) pos2 -= n;
+            s2 = idx[pos2];
+          }
+        }
+        // the step's critical path: up to four independent FMA chains, then the butterfly
+        constexpr int NACC = KMAX >= 4 ? 4 : KMAX;
+        double acc[NACC];
 #pragma unroll
-      for (int j = 0; j < NACC; ++j) acc[j] = w[j] * x[j];
+        for (int j = 0; j < NACC; ++j) acc[j] = w[j] * x[j];
 #pragma unroll
-      for (int j = NACC; j < KMAX; ++j) acc[j % NACC] = fma(w[j], x[j], acc[j % NACC]);
-      double dot = acc[0];
+        for (int j = NACC; j < KMAX; ++j) acc[j % NACC] = fma(w[j], x[j], acc[j % NACC]);
+        double dot = acc[0];
 #pragma unroll
-      for (int j = 1; j < NACC; ++j) dot += acc[j];
-      dot = warp_sum_all(dot);
-      const double G = yi * (dot + wb * bias) - 1.0 + ai * D;
-      const double PG = (ai > 0.0) ? G : fmin(G, 0.0);
-      pgmax = fmax(pgmax, PG);
-      pgmin = fmin(pgmin, PG);
-      if (fabs(PG) > 1e-12) {
-        const double nw = fmax(ai - G / qi, 0.0);
-        const double d = (nw - ai) * yi;
-        al[cur] = nw;                           // every lane stores the same value: each lane later reads its own store
+        for (int j = 1; j < NACC; ++j) dot += acc[j];
+        dot = warp_sum_all(dot);
+        const double G = yi * (dot + wb * bias) - 1.0 + ai * D;
+        if (ai == 0.0 && G > pgmax_old) {       // shrinking: sits out until the active set has converged
+          idx[curpos] = ~cur;                   // (every lane stores the same value) removed after the epoch
+          any_left = true;
+          continue;
+        }
+        const double PG = (ai > 0.0) ? G : fmin(G, 0.0);
+        pgmax = fmax(pgmax, PG);
+        pgmin = fmin(pgmin, PG);
+        if (fabs(PG) > 1e-12) {
+          const double nw = fmax(ai - G / qi, 0.0);
+          const double d = (nw - ai) * yi;
+          al[cur] = nw;                         // every lane stores the same value: each lane later reads its own store
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) w[j] = fma(d, x[j], w[j]);
-        wb = fma(d, bias, wb);
+          for (int j = 0; j < KMAX; ++j) w[j] = fma(d, x[j], w[j]);
+          wb = fma(d, bias, wb);
+        }
       }
     }
-    done_epochs = epoch + 1;
-    if (pgmax - pgmin <= tol) break;
+    ++it;
+    if (pgmax - pgmin <= tol) {                 // (-inf - inf for an empty active set)
+      if (n == (uint32_t)V && !any_left) break;   // the range was taken over ALL samples
+      __syncwarp();
+      for (int i = lane; i < V; i += 32) idx[i] = i;   // converged on the active set: check again on all samples
+      __syncwarp();
+      n = (uint32_t)V;
+      pgmax_old = INFINITY;
+      continue;
+    }
+    if (any_left) {                             // drop the marked entries, keep the order of the rest
+      __syncwarp();
+      uint32_t wpos = 0;
+      for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const int32_t v = (i < n) ? idx[i] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+        if (v >= 0) idx[wpos + __popc(m & ((1u << lane) - 1u))] = v;   // wpos + rank <= i: never ahead of the reads
+        wpos += __popc(m);
+      }
+      __syncwarp();
+      n = wpos;
+    }
+    pgmax_old = pgmax > 0.0 ? pgmax : INFINITY;
   }
 #pragma unroll
   for (int j = 0; j < KMAX; ++j)
     if (lane + 32 * j < F) coef[(size_t)k * F + lane + 32 * j] = w[j];
   if (lane == 0) {
     intercept[k] = wb * bias;
-    epochs[k] = done_epochs;
+    epochs[k] = it;
   }
 }
 
 // X fp64 [V][F] row-major; class_index int32 [V] in [0, n_classes); n_classes == 2 fits ONE problem (positive = class 1,
-// like scikit-learn's coef_ of shape [1][F]).  work: fp64 [(n_problems + 1) * V].  Returns nullptr or an error string.
+// like scikit-learn's coef_ of shape [1][F]).  work: fp64 [(P + 1) * V + (P * V + 1) / 2] (Q_ii, dual variables, active
+// sets as int32), P = number of problems.  Returns nullptr or an error string.
 const char* svm_fit_run(const double* X, const int32_t* class_index, int V, int F, int n_classes, double C, double bias,
                         double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
                         cudaStream_t st) {
@@ -131,12 +179,13 @@ const char* svm_fit_run(const double* X, const int32_t* class_index, int V, int 
   const double b = use_bias ? bias : 0.0, D = 0.5 / C;
   double* qd = work;
   double* alpha = work + V;
+  int32_t* active = reinterpret_cast<int32_t*>(work + (size_t)(K + 1) * V);
   if (cudaMemsetAsync(alpha, 0, (size_t)K * V * sizeof(double), st) != cudaSuccess) return "svm_fit: memset failed";
   count_launch();
   svm_qd_kernel<<<(V + 7) / 8, 256, 0, st>>>(X, V, F, b * b, D, qd);
   count_launch();
 #define VA_SVM_LAUNCH(KM) \
-  svm_dcd_kernel<KM><<<K, 32, 0, st>>>(X, V, F, class_index, first, qd, D, b, tol, max_iter, alpha, coef, intercept, epochs)
+  svm_dcd_kernel<KM><<<K, 32, 0, st>>>(X, V, F, class_index, first, qd, D, b, tol, max_iter, alpha, active, coef, intercept, epochs)
   if (F <= 64) VA_SVM_LAUNCH(2);
   else if (F <= 256) VA_SVM_LAUNCH(8);
   else if (F <= 512) VA_SVM_LAUNCH(16);

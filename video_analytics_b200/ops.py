@@ -99,10 +99,10 @@ def svm_fit(X: torch.Tensor, class_index: torch.Tensor, n_classes: int, *, C_reg
     V, F = X.shape
     P = 1 if n_classes == 2 else n_classes
     dev = X.device
-    coef = torch.empty((max(P, 0), F), dtype=torch.float64, device=dev)
-    intercept = torch.empty((max(P, 0),), dtype=torch.float64, device=dev)
-    epochs = torch.empty((max(P, 0),), dtype=torch.int32, device=dev)
-    work = torch.empty(((max(P, 0) + 1) * max(V, 1),), dtype=torch.float64, device=dev)
+    coef = torch.empty((P, F), dtype=torch.float64, device=dev)
+    intercept = torch.empty((P,), dtype=torch.float64, device=dev)
+    epochs = torch.empty((P,), dtype=torch.int32, device=dev)
+    work = torch.empty(((P + 1) * max(V, 1) + (P * max(V, 1) + 1) // 2,), dtype=torch.float64, device=dev)
     check(_lib.load().va_svm_fit(ptr(X), ptr(class_index), V, F, n_classes, C_reg, bias, tol, max_iter, ptr(coef),
                                  ptr(intercept), ptr(epochs), ptr(work), stream_ptr()), "va_svm_fit")
     return coef, intercept, epochs
