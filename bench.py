@@ -594,7 +594,11 @@ def main():
         traffic = None      # DRAM bytes per layer-kernel launch from the committed ncu --set full capture (profiles/)
         tpath = os.path.join(ROOT, "profiles", "r01_ncu_conv_tc_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+            # the capture ran 125-snippet chunks; a launch of this run processes `chunk` snippets: activation bytes scale
+            # with the chunk, the weights (29 MB of 4.7 GB per 125-snippet chunk) do not -- scaled linearly, 0.6 % high
+            captured = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+            chunk = min(args.max_batch, vps * SNIPPETS_PER_VIDEO)
+            traffic = captured * chunk / 125.0 if captured is not None else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -609,7 +613,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                         "traffic_source": "profiles/r01_ncu_conv_tc_traffic.json (ncu --set full, 16 launches of one 125-snippet temporal chunk)",
+                         "traffic_source": "profiles/r01_ncu_conv_tc_traffic.json (ncu --set full, 16 launches of one 125-snippet temporal chunk: "
+                                           "297.4 MB per launch), scaled to this run's snippets per launch",
                          "peak_source": peaks["src"], "launches": int(t_l.value), "avg_launch_ms": t_ms.value / max(1, t_l.value),
                          "flops_per_launch": t_f.value / max(1, t_l.value),
                          "share_of_step": t_ms.value / total_ms if total_ms > 0 else None},
