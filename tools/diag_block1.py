@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Block-1 experiments (conv1_2 kernel variants): correctness against torch fp32 and against the plain one-tap-per-stage
+kernel, plus event-timed duration at the bench's chunk size.  Each variant runs in its own subprocess so that a device
+trap (e.g. a descriptor the hardware rejects) cannot poison the others.
+  python tools/diag_block1.py [batch]        -> all variants
+  python tools/diag_block1.py case <force_r> <batch>
+force_r: 1 plain, 0 default, 3 R=3 (vertical tap reuse), 10 HALO (one haloed box per tile)
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+VARIANTS = [1, 3, 0, 10]
+
+
+def run_case(force_r, batch):
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from video_analytics_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(99)
+    dev = "cuda"
+    # correctness on 3 images (partial last tiles do not exist at 224, but image borders and batch edges do)
+    n, H, cin, cout = 3, 224, 64, 64
+    xc = torch.randn(n, cin, H, H, generator=g).to(dev).bfloat16()
+    x = xc.permute(0, 2, 3, 1).contiguous()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).to(dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = dict(force_r=force_r, batch=batch)
+    for pool in (True, False):
+        y = ops.conv2d_nhwc(x, w, b, relu=True, pool=pool, force_bn=0, force_r=force_r).float()
+        torch.cuda.synchronize()
+        ref = torch.relu(torch.nn.functional.conv2d(xc.float(), w.bfloat16().float(), b, padding=1))
+        if pool:
+            ref = torch.nn.functional.max_pool2d(ref, 2, 2)
+        ref = ref.permute(0, 2, 3, 1).contiguous()
+        diff = (y - ref).abs()
+        tol = 2.0 ** -7 * ref.abs() + 2e-2 * ref.abs().mean()
+        res[f"bad_frac_pool{int(pool)}"] = float((diff > tol).float().mean())
+        res[f"max_abs_pool{int(pool)}"] = float(diff.max())
+        y1 = ops.conv2d_nhwc(x, w, b, relu=True, pool=pool, force_bn=0, force_r=1).float()
+        res[f"bitequal_plain_pool{int(pool)}"] = bool(torch.equal(y, y1))
+        res[f"maxdiff_plain_pool{int(pool)}"] = float((y - y1).abs().max())
+    # timing at the bench's chunk size
+    xb = torch.randn(batch, H, H, cin, device=dev).bfloat16()
+    for _ in range(2):
+        ops.conv2d_nhwc(xb, w, b, relu=True, pool=True, force_r=force_r)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv2d_nhwc(xb, w, b, relu=True, pool=True, force_r=force_r)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    res["ms_median"] = ts[len(ts) // 2]
+    res["ms_min"] = ts[0]
+    res["tflops"] = 2.0 * batch * H * H * cout * 9 * cin / (ts[len(ts) // 2] * 1e-3) / 1e12
+    res["ok"] = res["bad_frac_pool1"] == 0.0 and res["bad_frac_pool0"] == 0.0
+    return res
+
+
+def main():
+    if len(sys.argv) >= 4 and sys.argv[1] == "case":
+        try:
+            res = run_case(int(sys.argv[2]), int(sys.argv[3]))
+        except Exception as e:  # noqa
+            res = dict(force_r=int(sys.argv[2]), ok=False, error=f"{type(e).__name__}: {e}"[:600])
+        print("RESULT " + json.dumps(res), flush=True)
+        return
+    batch = int(sys.argv[1]) if len(sys.argv) > 1 else 250
+    for fr in VARIANTS:
+        t0 = time.time()
+        try:
+            pr = subprocess.run([sys.executable, os.path.abspath(__file__), "case", str(fr), str(batch)], capture_output=True,
+                                text=True, timeout=200)
+            lines = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
+            print(f"[force_r={fr}] rc={pr.returncode} {time.time()-t0:.1f}s {lines[-1] if lines else 'NO RESULT ' + pr.stderr[-500:]}",
+                  flush=True)
+        except subprocess.TimeoutExpired:
+            print(f"[force_r={fr}] TIMEOUT", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,10 +80,10 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int CK, int R, int S, bool WRES, bool DRAIN = false>
+template <int BN, int CK, int R, int S, bool WRES, bool DRAIN = false, bool HALO = false>
 const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const CUtensorMap& tO,
                            const ConvKernelParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = conv_tc_kernel<BN, CK, R, S, WRES, DRAIN>;
+  auto kfn = conv_tc_kernel<BN, CK, R, S, WRES, DRAIN, HALO>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -113,7 +113,18 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
 
   ConvKernelParams p;
   p.n_img = d.n; p.H = d.H; p.W = d.W;
-  if (d.H == 1 && d.W == 1) { p.h_t = 1; p.w_t = 1; p.n_t = 128; }
+  p.hb_pitch = 0;
+  // HALO variant (one haloed A box per 16x8 tile serves all nine taps; resident weights): the 64->64 3x3 layers
+  // (conv1_2 and its data gradient).  force_r = 10 requests it, any other non-zero force_r disables it.
+  const bool halo_ok = d.ks == 3 && CK == 64 && d.cin_pad == 64 && d.Cout == 64 && d.H % 16 == 0 && d.W % 8 == 0 && !d.split6 &&
+                       (d.force_bn == 0 || d.force_bn == 64);
+  if (d.force_r == 10 && !halo_ok) return "HALO variant needs a 3x3 64->64 layer with H%16==0 and W%8==0";
+  const bool halo = halo_ok && (d.force_r == 10 || d.force_r == 0);
+  if (halo) {
+    p.h_t = 16; p.w_t = 8; p.n_t = 1;
+    p.hb_pitch = p.w_t + 2;
+  }
+  else if (d.H == 1 && d.W == 1) { p.h_t = 1; p.w_t = 1; p.n_t = 128; }
   else if (d.W % 16 == 0 && d.H % 8 == 0) { p.h_t = 8; p.w_t = 16; p.n_t = 1; }
   else if (d.W % 8 == 0 && d.H % 8 == 0) { p.h_t = 8; p.w_t = 8; p.n_t = 2; }
   else if (d.W % 4 == 0 && d.H % 4 == 0) { p.h_t = 4; p.w_t = 4; p.n_t = 8; }
@@ -131,6 +142,8 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   int R = 1, S = 1;
   if (d.split6) {
     // fp32-accuracy mode: one tap per stage, BN = 64, per-stage accumulator drain (kernel template DRAIN)
+  } else if (halo) {
+    R = 3;
   } else if (d.force_r == 3) {
     if (!r3_ok) return "force_r=3 needs ks=3 and a single-image tile with w_t%8==0";
     R = 3;
@@ -138,8 +151,8 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     R = 3;
   }
   if (R == 3 && CK < 64 && d.force_r != 3) S = 3;
-  if (d.force_r == 9) {   // test hook: whole-filter stages
-    if (!r3_ok || CK == 64) return "force_r=9 (S=3) needs an R=3-capable tile and Cin_pad 16/32";
+  if (d.force_r == 9 || halo) {   // whole-filter stages
+    if (!r3_ok || (CK == 64 && (d.cin_pad != 64 || d.Cout != 64))) return "force_r=9 (S=3) needs an R=3-capable tile and Cin_pad 16/32, or a 64->64 layer";
     R = 3; S = 3;
   }
   const int sms = sm_count();
@@ -181,7 +194,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.Cout = d.Cout;
   p.bias = d.bias; p.out_f32_ptr = d.y_f32; p.dbg = g_dbg_counters;
   const int rowb = CK * 2;
-  const int a_rows = p.n_t * (p.h_t + (R - 1)) * p.w_t;
+  const int a_rows = p.n_t * (p.h_t + (R - 1)) * (halo ? p.hb_pitch : p.w_t);
   p.a_tx_bytes = (uint32_t)a_rows * rowb;
   p.a_box_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
   p.staging_bytes = d.pool ? 4096u : 16384u;
@@ -189,18 +202,20 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   const int groups = (d.ks * d.ks) / (R * S);
   const bool wres = !d.split6 && R == 3 && p.n_tiles_cout == 1 && p.cin_chunks == 1 && BN == 64 && getenv("VA_CONV_NO_WRES") == nullptr &&
                     (size_t)groups * conv_b_stage_bytes(BN, CK, R, S) <= 80 * 1024;
-  const uint32_t stage_bytes = S * p.a_box_bytes + (wres ? 0u : conv_b_stage_bytes(BN, CK, R, S));
+  if (halo && !wres) return "HALO variant needs resident weights";
+  const int a_boxes = halo ? 1 : S;
+  const uint32_t stage_bytes = a_boxes * p.a_box_bytes + (wres ? 0u : conv_b_stage_bytes(BN, CK, R, S));
   const size_t smem_cap = 227 * 1024;
-  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, 0)) / stage_bytes);
+  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, 0, a_boxes)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return errf("not enough shared memory for 2 stages (stage %u B)", stage_bytes);
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, stages);
+  const size_t smem = conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, stages, a_boxes);
 
   CUtensorMap tA, tW, tO;
   {
     const uint64_t dims[4] = {(uint64_t)d.cin_pad, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.n};
-    const uint32_t box[4] = {(uint32_t)CK, (uint32_t)p.w_t, (uint32_t)(p.h_t + R - 1), (uint32_t)p.n_t};
+    const uint32_t box[4] = {(uint32_t)CK, (uint32_t)(halo ? p.hb_pitch : p.w_t), (uint32_t)(p.h_t + R - 1), (uint32_t)p.n_t};
     if (const char* e = encode_bf16(&tA, d.x, 4, dims, box, rowb, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
   }
   {
@@ -249,6 +264,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     if (BN == 64 && CK == 64) return launch_variant<64, 64, 1, 1, false, true>(tA, tW, tO, p, grid, smem, st);
     return errf("fp32-accuracy mode: no kernel for BN=%d CK=%d", BN, CK);
   }
+  if (halo) return launch_variant<64, 64, 3, 3, true, false, true>(tA, tW, tO, p, grid, smem, st);
 #define VA_CASE(bn, ck, r, sv, wr) \
   if (BN == bn && CK == ck && R == r && S == sv && wres == wr) \
     return launch_variant<bn, ck, r, sv, wr>(tA, tW, tO, p, grid, smem, st);
@@ -256,7 +272,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   VA_CASE(256, 64, 1, 1, false) VA_CASE(64, 64, 3, 1, false) VA_CASE(128, 64, 3, 1, false) VA_CASE(64, 16, 3, 1, false)
   VA_CASE(64, 32, 3, 1, false) VA_CASE(64, 16, 3, 3, false) VA_CASE(64, 32, 3, 3, false)
   VA_CASE(64, 64, 3, 1, true) VA_CASE(64, 16, 3, 1, true) VA_CASE(64, 32, 3, 1, true) VA_CASE(64, 16, 3, 3, true)
-  VA_CASE(64, 32, 3, 3, true)
+  VA_CASE(64, 32, 3, 3, true) VA_CASE(64, 64, 3, 3, true)
 #undef VA_CASE
   return errf("no kernel variant for BN=%d CK=%d R=%d S=%d wres=%d", BN, CK, R, S, (int)wres);
 }

@@ -76,6 +76,7 @@ struct ConvKernelParams {
   const float* bias;               // [Cout]
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
   long long* dbg;                  // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
+  int hb_pitch;                    // HALO variant: pixels per row of the haloed A box (w_t + 2)
 };
 
 // wait on an mbarrier, charging the stalled cycles to *acc when diagnostics are on
@@ -92,9 +93,10 @@ constexpr int kMaxStages = 8;
 __host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R, int S) { return R * S * BN * CK * 2; }
 
 inline size_t conv_smem_bytes(int BN, int CK, int R, int S, bool wres, int groups, uint32_t a_box_bytes,
-                              uint32_t staging_bytes, int stages) {
+                              uint32_t staging_bytes, int stages, int a_boxes = 0) {
   const size_t b = conv_b_stage_bytes(BN, CK, R, S);
-  return 1024 /*align slack*/ + (wres ? (size_t)groups * b : 0) + (size_t)stages * (S * a_box_bytes + (wres ? 0 : b)) +
+  if (a_boxes == 0) a_boxes = S;
+  return 1024 /*align slack*/ + (wres ? (size_t)groups * b : 0) + (size_t)stages * (a_boxes * a_box_bytes + (wres ? 0 : b)) +
          2 * (size_t)staging_bytes + 2 * 256 * sizeof(float) + 256;
 }
 
@@ -108,7 +110,14 @@ __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
 // DRAIN (fp32-accuracy mode only): the tensor core adds into its fp32 accumulator with truncation, so a long K loop
 // drifts by ~1e-5 per layer (measured: descriptors 4e-4 off after 16 layers).  With DRAIN every pipeline stage gets a
 // fresh TMEM accumulator that epilogue group 0 drains and sums in registers with round-to-nearest fp32 adds.
-template <int BN, int CK, int R, int S, bool WRES, bool DRAIN = false>
+// HALO (conv1_2: Cin = Cout = 64, resident weights): ONE TMA box of (h_t+2) x pitch pixels per tile serves all nine
+// taps.  Tap (r,s) reads the box from pixel row r*pitch + s on, 8-pixel groups (one output row of the 16x8 tile) are
+// pitch*128 B apart (SBO).  The start address is then no longer a multiple of the 1024-byte swizzle atom; measured on
+// B200 (tools/diag_block1.py, profiles/r02_conv1_2_variants.log): the 128B swizzle of both TMA and UMMA is a function
+// of the ABSOLUTE shared-memory address bits, so such a window reads exactly what TMA wrote with the descriptor's
+// base-offset field left 0 (setting it to (start >> 7) & 7 gives wrong results).  36 MMAs per pipeline stage, 23 KB
+// (instead of 60 KB) of smem writes per tile: 1.171 -> 0.943 ms per 250 snippets, bit-identical output.
+template <int BN, int CK, int R, int S, bool WRES, bool DRAIN = false, bool HALO = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
@@ -116,6 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(CK == 16 || CK == 32 || CK == 64, "CK");
   static_assert(R == 1 || R == 3, "R");
   static_assert(S == 1 || (S == 3 && R == 3), "S");
+  static_assert(!HALO || (S == 3 && R == 3 && WRES && CK == 64), "HALO");
   constexpr int ROWB = CK * 2;
   constexpr uint32_t B_STAGE = conv_b_stage_bytes(BN, CK, R, S);
   constexpr uint32_t TMEM_COLS = 2 * BN;   // 128 / 256 / 512: powers of two >= 32
@@ -125,7 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int groups = (p.ks * p.ks) / (R * S);    // stages per channel chunk: 9 (per tap), 3 (per filter column) or 1
   const int num_kb = groups * p.cin_chunks;      // pipeline stages consumed per tile
   const uint32_t wres_bytes = WRES ? (uint32_t)groups * B_STAGE : 0u;   // resident weights sit in front of the ring
-  const uint32_t a_stage_bytes = S * p.a_box_bytes;
+  const uint32_t a_stage_bytes = (HALO ? 1 : S) * p.a_box_bytes;
   const uint32_t stage_bytes = a_stage_bytes + (WRES ? 0u : B_STAGE);
   uint8_t* ring = smem + wres_bytes;
   uint8_t* staging = ring + (size_t)p.num_stages * stage_bytes;
@@ -194,9 +204,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait_t(&empty_bar[stage], phase ^ 1, 100 + stage, dbg, t_wait);
           if (elect_one()) {
             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], S * p.a_tx_bytes + (WRES ? 0u : B_STAGE));
+            mbar_arrive_expect_tx(&full_bar[stage], (HALO ? 1 : S) * p.a_tx_bytes + (WRES ? 0u : B_STAGE));
 #pragma unroll
-            for (int sa = 0; sa < S; ++sa)
+            for (int sa = 0; sa < (HALO ? 1 : S); ++sa)
               tma_load_4d(a_dst + sa * p.a_box_bytes, &tmA, &full_bar[stage], cc * CK, wx + sa, hy, n0);
             if (!WRES) tma_load_3d(a_dst + a_stage_bytes, &tmW, &full_bar[stage], cc * CK, c0, g * (R * S));
           }
@@ -216,11 +226,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
     // descriptor start-address offsets (>>4) of the S*R operand windows inside a stage: launch constants, hoisted so
     // that nothing but one 64-bit add per operand separates consecutive MMAs in the issue stream
-    uint32_t a_win[S * R];
+    uint64_t a_win[S * R];
 #pragma unroll
     for (int sa = 0; sa < S; ++sa)
 #pragma unroll
-      for (int r = 0; r < R; ++r) a_win[sa * R + r] = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
+      for (int r = 0; r < R; ++r) {
+        if (HALO) {
+          const uint32_t prow = (uint32_t)(r * p.hb_pitch + sa);            // first pixel row of the tap's window
+          a_win[sa * R + r] = (uint64_t)((prow * ROWB) >> 4);
+        } else {
+          a_win[sa * R + r] = (sa * p.a_box_bytes + r * a_r_stride) >> 4;
+        }
+      }
+    const uint64_t a_sbo_fix = HALO ? ((uint64_t)(((uint32_t)p.hb_pitch * ROWB) >> 4) << 32) - ((uint64_t)((ROWB * 8) >> 4) << 32) : 0ull;
     if (WRES) mbar_wait(wres_bar, 0, 500);
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
@@ -243,14 +261,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4) to a base
         const uint32_t a_addr = ring_u32 + stage * stage_bytes;
-        const uint64_t da0 = make_smem_desc<ROWB>(a_addr);
+        const uint64_t da0 = make_smem_desc<ROWB>(a_addr) + a_sbo_fix;
         const uint64_t db0 = make_smem_desc<ROWB>(WRES ? smem_base_u32 + (uint32_t)kb * B_STAGE : a_addr + a_stage_bytes);
         if (elect_one()) {
 #pragma unroll
           for (int sa = 0; sa < S; ++sa) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              const uint32_t a_off = a_win[sa * R + r];
+              const uint64_t a_off = a_win[sa * R + r];
 #pragma unroll
               for (int k = 0; k < CK / 16; ++k) {
                 umma_bf16(d_tmem, da0 + a_off + 2 * k, db0 + (((sa * R + r) * (BN * ROWB)) >> 4) + 2 * k, idesc,
