@@ -85,11 +85,28 @@ va_status va_preprocess(const uint8_t* images, size_t image_bytes, int img_h, in
 va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptors, float* logits, float* probs,
                      int32_t* pred, va_stream_t stream);
 
+/* Fused front end: the same forward, but fed from the image store.  The snippet transform (va_preprocess: utils.py:137-151,
+ * spatialModel.py:64-81, temporalModel.py:67-92) is gathered straight into the first convolution's shared-memory operand
+ * (csrc/va_conv1_fused.cu), so no preprocessed tensor exists in HBM.  Arguments as va_preprocess (crop is 224) and
+ * va_forward; planes * img_c must equal the handle's in_channels; (planes, img_c) = (1, 3) or (any, 1).  Results are
+ * those of va_preprocess + va_forward up to the summation order inside the first layer's fp32 accumulation.
+ * Returns VA_ERR_UNSUPPORTED for precision-1 handles (use va_preprocess + va_forward). */
+va_status va_forward_store(va_handle* h, const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                           const int32_t* index_table, int n, int planes, const float* mean, const float* std,
+                           float* descriptors, float* logits, float* probs, int32_t* pred, va_stream_t stream);
+
+/* The fused gather + first-layer kernel alone (parity tests, profiling): y bf16 NHWC [n][224][224][64] =
+ * ReLU(conv3x3(normalised crop, w) + bias); w fp32 OIHW [64][planes*img_c][3][3]. */
+va_status va_conv1_fused(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                         const int32_t* index_table, int n, int planes, const float* mean, const float* std,
+                         const float* w, const float* bias, void* y, va_stream_t stream);
+
 /* Layer primitives behind va_forward, exported for per-layer parity tests and profiling.
  * conv: x bf16 NHWC [n][H][W][cin_pad]; w fp32 OIHW [cout][cin][ks][ks]; y bf16 NHWC [n][H(/2)][W(/2)][cout].
  *       ks in {1,3}, stride 1, zero pad (ks-1)/2; optional fused ReLU and 2x2/2 max-pool.
  *       force_bn in {0 (auto),64,128,256}; force_r in {0 (auto), 1 (one tap per stage), 3 (vertical tap reuse),
- *       9 (whole 3x3 filter per stage, Cin_pad 16/32 only)} select kernel variants.
+ *       9 (whole 3x3 filter per stage, Cin_pad 16/32 only), 10 (one haloed box per 16x8 tile, 64->64 layers)} select
+ *       kernel variants.
  * linear: x bf16 [n][in]; w fp32 [out][in]; y bf16 [n][out] and/or y_f32 fp32 [n][out] (exactly one). */
 va_status va_conv2d_nhwc(const void* x, int n, int H, int W, int cin, int cin_pad, const float* w,
                          const float* bias, int cout, int ks, int relu, int pool, void* y, int force_bn,

@@ -29,6 +29,8 @@ SIGNATURES = {
     "va_load_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp]),
     "va_preprocess": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _i, _i, _vp, _vp]),
     "va_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "va_forward_store": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp, _vp, _vp]),
+    "va_conv1_fused": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp, _vp]),
     "va_conv2d_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "va_linear": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "va_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -59,6 +59,7 @@ struct va_handle {
   int precision;    // 0 = bf16 storage; 1 = fp32-accuracy (bf16x3 slices, six cross terms along K)
   bool loaded;
   void* wconv[13];
+  void* wconv1_fused;   // conv1_1 in the dense-K layout of the fused gather kernel (precision 0 only)
   float* bconv[13];
   void* wfc[3];     // FC1, FC2, FC3 packed bf16
   float* bfc[3];
@@ -141,6 +142,10 @@ va_status va_create_ex(va_handle** out, int stream_kind, int in_channels, int n_
     }
     cin = kVgg16[i].cout * kmul;
   }
+  if (!precision && cudaMalloc(&h->wconv1_fused, (size_t)va::conv1_fused_packed_bytes(in_channels)) != cudaSuccess) {
+    va_destroy(h);
+    return fail(VA_ERR_CUDA, "cudaMalloc conv1 fused weights failed");
+  }
   const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
   const int fout[3] = {kFcHidden, kFcHidden, desc_dim};
   for (int i = 0; i < 3; ++i) {
@@ -165,6 +170,7 @@ va_status va_create_ex(va_handle** out, int stream_kind, int in_channels, int n_
 va_status va_destroy(va_handle* h) {
   if (!h) return VA_OK;
   for (int i = 0; i < 13; ++i) { cudaFree(h->wconv[i]); cudaFree(h->bconv[i]); }
+  cudaFree(h->wconv1_fused);
   for (int i = 0; i < 3; ++i) { cudaFree(h->wfc[i]); cudaFree(h->bfc[i]); }
   cudaFree(h->w4t); cudaFree(h->b4); cudaFree(h->act[0]); cudaFree(h->act[1]); cudaFree(h->desc_ws);
   delete h;
@@ -185,6 +191,8 @@ va_status va_load_weights(va_handle* h, const void* const* tensors, int n_tensor
     else
       VA_CUDA(va::launch_pack_conv_w(static_cast<const float*>(tensors[2 * i]), h->wconv[i], cout, cin, cin_pad, 3, st));
     VA_CUDA(cudaMemcpyAsync(h->bconv[i], tensors[2 * i + 1], cout * 4, cudaMemcpyDeviceToDevice, st));
+    if (i == 0 && h->wconv1_fused)
+      VA_CUDA(va::launch_pack_conv1_fused_w(static_cast<const float*>(tensors[0]), h->wconv1_fused, cin, st));
     cin = cout; cin_pad = cout * (h->precision ? 6 : 1);
   }
   const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
@@ -219,15 +227,20 @@ va_status va_preprocess(const uint8_t* images, size_t image_bytes, int img_h, in
   return VA_OK;
 }
 
-va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptors, float* logits, float* probs,
-                     int32_t* pred, va_stream_t stream) {
-  if (!h || !in_nhwc) return fail(VA_ERR_INVALID, "va_forward: NULL argument");
-  if (!h->loaded) return fail(VA_ERR_INVALID, "va_forward: weights not loaded");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+namespace {
+struct StoreInput {          // front end of va_forward_store
+  const uint8_t* images; size_t image_bytes; int img_h, img_w, img_c;
+  const int32_t* table; int planes; const float* mean; const float* stdv;
+};
+
+// Layers of one stream over n snippets in chunks of max_batch.  `in_nhwc` (preprocessed input) or `src` (image store +
+// index table: the first layer is the fused gather kernel) -- exactly one of the two.
+va_status forward_impl(va_handle* h, const void* in_nhwc, const StoreInput* src, int n, float* descriptors, float* logits,
+                       float* probs, int32_t* pred, cudaStream_t st) {
   const size_t in_stride = (size_t)kCrop * kCrop * h->cin_pad * 2;
   for (int off = 0; off < n; off += h->max_batch) {
     const int nb = (n - off) < h->max_batch ? (n - off) : h->max_batch;
-    const void* x = static_cast<const uint8_t*>(in_nhwc) + (size_t)off * in_stride;
+    const void* x = in_nhwc ? static_cast<const uint8_t*>(in_nhwc) + (size_t)off * in_stride : nullptr;
     int H = kCrop, cin_pad = h->cin_pad, cur = 0;
     ProfSpan span{nullptr, nullptr};
     if (g_prof_on) {
@@ -237,16 +250,24 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
     }
     int cin_real = h->cin;
     for (int i = 0; i < 13; ++i) {
-      va::ConvLayerDesc d;
-      d.x = x; d.n = nb; d.H = H; d.W = H; d.cin_pad = cin_pad;
-      d.w_packed = h->wconv[i]; d.bias = h->bconv[i]; d.Cout = kVgg16[i].cout; d.ks = 3;
-      d.relu = 1; d.pool = kVgg16[i].pool ? 1 : 0; d.y = h->act[cur]; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0;
-      d.split6 = h->precision;
-      if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "conv layer %d: %s", i, e);
+      const int cout = kVgg16[i].cout;
+      if (i == 0 && src) {
+        const int32_t* tab = src->table + (size_t)off * src->planes * 4;
+        if (const char* e = va::conv1_fused_run(src->images, src->image_bytes, src->img_h, src->img_w, src->img_c, tab, nb,
+                                                src->planes, src->mean, src->stdv, h->wconv1_fused, h->bconv[0], h->act[cur], st))
+          return fail(VA_ERR_CUDA, "fused conv layer 0: %s", e);
+      } else {
+        va::ConvLayerDesc d;
+        d.x = x; d.n = nb; d.H = H; d.W = H; d.cin_pad = cin_pad;
+        d.w_packed = h->wconv[i]; d.bias = h->bconv[i]; d.Cout = cout; d.ks = 3;
+        d.relu = 1; d.pool = kVgg16[i].pool ? 1 : 0; d.y = h->act[cur]; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0;
+        d.split6 = h->precision;
+        if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "conv layer %d: %s", i, e);
+      }
       x = h->act[cur]; cur ^= 1;
-      if (g_prof_on) { g_prof_flops += 2.0 * nb * H * H * (double)d.Cout * 9.0 * cin_real; ++g_prof_launches; }
-      cin_pad = d.Cout * (h->precision ? 6 : 1); cin_real = d.Cout;
-      if (d.pool) H >>= 1;
+      if (g_prof_on) { g_prof_flops += 2.0 * nb * H * H * (double)cout * 9.0 * cin_real; ++g_prof_launches; }
+      cin_pad = cout * (h->precision ? 6 : 1); cin_real = cout;
+      if (kVgg16[i].pool) H >>= 1;
     }
     float* desc_out = descriptors ? descriptors + (size_t)off * h->desc_dim : h->desc_ws;
     const int fin[3] = {kFc1In, kFcHidden, kFcHidden};
@@ -271,6 +292,52 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
                             logits ? logits + (size_t)off * h->n_classes : nullptr,
                             probs ? probs + (size_t)off * h->n_classes : nullptr, pred ? pred + off : nullptr, st));
   }
+  return VA_OK;
+}
+}  // namespace
+
+va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptors, float* logits, float* probs,
+                     int32_t* pred, va_stream_t stream) {
+  if (!h || !in_nhwc) return fail(VA_ERR_INVALID, "va_forward: NULL argument");
+  if (!h->loaded) return fail(VA_ERR_INVALID, "va_forward: weights not loaded");
+  return forward_impl(h, in_nhwc, nullptr, n, descriptors, logits, probs, pred, static_cast<cudaStream_t>(stream));
+}
+
+va_status va_forward_store(va_handle* h, const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                           const int32_t* index_table, int n, int planes, const float* mean, const float* std,
+                           float* descriptors, float* logits, float* probs, int32_t* pred, va_stream_t stream) {
+  if (!h || !images || !index_table || !mean || !std) return fail(VA_ERR_INVALID, "va_forward_store: NULL argument");
+  if (!h->loaded) return fail(VA_ERR_INVALID, "va_forward_store: weights not loaded");
+  if (h->precision || !h->wconv1_fused)
+    return fail(VA_ERR_UNSUPPORTED, "va_forward_store: precision-1 handles use va_preprocess + va_forward");
+  if (planes < 1 || img_c < 1 || planes * img_c != h->cin)
+    return fail(VA_ERR_INVALID, "va_forward_store: planes %d x img_c %d != in_channels %d", planes, img_c, h->cin);
+  if (!va::conv1_fused_supported(planes, img_c, kCrop))
+    return fail(VA_ERR_UNSUPPORTED, "va_forward_store: (planes, img_c) = (%d, %d); supported (1, 3) and (any, 1)", planes, img_c);
+  if (img_h < kCrop || img_w < kCrop || image_bytes < (size_t)img_h * img_w * img_c)
+    return fail(VA_ERR_INVALID, "va_forward_store: image %dx%dx%d (%zu bytes) cannot hold a %d crop", img_h, img_w, img_c, image_bytes, kCrop);
+  const StoreInput src{images, image_bytes, img_h, img_w, img_c, index_table, planes, mean, std};
+  return forward_impl(h, nullptr, &src, n, descriptors, logits, probs, pred, static_cast<cudaStream_t>(stream));
+}
+
+va_status va_conv1_fused(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                         const int32_t* index_table, int n, int planes, const float* mean, const float* std,
+                         const float* w, const float* bias, void* y, va_stream_t stream) {
+  if (!images || !index_table || !mean || !std || !w || !bias || !y) return fail(VA_ERR_INVALID, "va_conv1_fused: NULL argument");
+  if (n < 0 || planes < 1 || img_c < 1 || planes * img_c > 32) return fail(VA_ERR_INVALID, "va_conv1_fused: bad shape");
+  if (!va::conv1_fused_supported(planes, img_c, kCrop))
+    return fail(VA_ERR_UNSUPPORTED, "va_conv1_fused: (planes, img_c) = (%d, %d); supported (1, 3) and (any, 1)", planes, img_c);
+  if (img_h < kCrop || img_w < kCrop) return fail(VA_ERR_INVALID, "va_conv1_fused: image smaller than the crop");
+  if (va_status s = require_sm100()) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* wp = nullptr;
+  VA_CUDA(cudaMallocAsync(&wp, (size_t)va::conv1_fused_packed_bytes(planes * img_c), st));
+  cudaError_t pe = va::launch_pack_conv1_fused_w(w, wp, planes * img_c, st);
+  const char* e = pe == cudaSuccess ? va::conv1_fused_run(images, image_bytes, img_h, img_w, img_c, index_table, n, planes, mean,
+                                                          std, wp, bias, y, st)
+                                    : cudaGetErrorString(pe);
+  cudaFreeAsync(wp, st);
+  if (e) return fail(VA_ERR_CUDA, "va_conv1_fused: %s", e);
   return VA_OK;
 }
 

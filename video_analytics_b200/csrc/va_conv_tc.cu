@@ -103,6 +103,7 @@ static long long* g_dbg_counters = nullptr;
 void conv_set_debug_counters(long long* dev_buf) { g_dbg_counters = dev_buf; }
 
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
+  cudaStream_t st_ = st;
   if (d.n <= 0) return nullptr;
   if (d.ks != 1 && d.ks != 3) return "ks must be 1 or 3";
   const int CK = (d.cin_pad % 64 == 0) ? 64 : d.cin_pad;
@@ -119,6 +120,69 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   const bool halo_ok = d.ks == 3 && CK == 64 && d.cin_pad == 64 && d.Cout == 64 && d.H % 16 == 0 && d.W % 8 == 0 && !d.split6 &&
                        (d.force_bn == 0 || d.force_bn == 64);
   if (d.force_r == 10 && !halo_ok) return "HALO variant needs a 3x3 64->64 layer with H%16==0 and W%8==0";
+  // CTA-pair HALO kernel with resident weight halves (conv_tc2h_kernel): the 3x3 layers at 224^2 / 112^2 with
+  // Cout, Cin in {64, 128}.  force_r = 11 requests it, any other non-zero force_r disables it.
+  const bool pairh_ok = d.ks == 3 && CK == 64 && (d.cin_pad == 64 || d.cin_pad == 128) && (d.Cout == 64 || d.Cout == 128) &&
+                        d.H % 16 == 0 && d.W % 8 == 0 && !d.split6 && !d.y_f32 && (d.force_bn == 0 || d.force_bn == d.Cout);
+  if (d.force_r == 11 && !pairh_ok) return "pair-HALO variant needs a 3x3 layer with Cout, Cin in {64,128}, H%16==0, W%8==0";
+  if (pairh_ok && (d.force_r == 11 || d.force_r == 0)) {
+    const int BNh = d.Cout, chunks = d.cin_pad / 64;
+    p.h_t = 16; p.w_t = 8; p.n_t = 1; p.hb_pitch = p.w_t + 2;
+    p.log2_w_t = 3; p.log2_h_t = 4;
+    p.tiles_w = d.W / p.w_t; p.tiles_h = d.H / p.h_t; p.tiles_n = d.n;
+    const int tiles_m_h = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.n_tiles_cout = 1;
+    p.total_tiles = (tiles_m_h + 1) / 2;                          // work units of a CTA pair
+    p.div_cout = FastDiv::make(1u);
+    p.div_w = FastDiv::make((uint32_t)p.tiles_w);
+    p.div_h = FastDiv::make((uint32_t)p.tiles_h);
+    p.ks = 3; p.pad = 1; p.cin_chunks = chunks;
+    p.pool = d.pool; p.relu = d.relu; p.out_f32 = 0; p.split6 = 0; p.Cout = d.Cout;
+    p.bias = d.bias; p.out_f32_ptr = nullptr; p.dbg = nullptr;
+    p.a_tx_bytes = (uint32_t)((p.h_t + 2) * p.hb_pitch * 128);
+    p.a_box_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    p.staging_bytes = d.pool ? 4096u : 16384u;
+    int st = (int)((227 * 1024 - conv2h_smem_bytes(BNh, chunks, p.a_box_bytes, p.staging_bytes, 0)) / p.a_box_bytes);
+    if (st > kMaxStages) st = kMaxStages;
+    if (st >= 2) {
+      p.num_stages = st;
+      const size_t smem_h = conv2h_smem_bytes(BNh, chunks, p.a_box_bytes, p.staging_bytes, st);
+      CUtensorMap tA, tW, tO;
+      {
+        const uint64_t dims[4] = {(uint64_t)d.cin_pad, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.n};
+        const uint32_t box[4] = {64u, (uint32_t)p.hb_pitch, (uint32_t)(p.h_t + 2), 1u};
+        if (const char* e = encode_bf16(&tA, d.x, 4, dims, box, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
+      }
+      {
+        const uint64_t dims[3] = {(uint64_t)d.cin_pad, (uint64_t)d.Cout, 9ull};
+        const uint32_t box[3] = {64u, (uint32_t)(BNh / 2), 9u};
+        if (const char* e = encode_bf16(&tW, d.w_packed, 3, dims, box, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
+      }
+      {
+        const int sh = d.pool ? 1 : 0;
+        const uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)(d.W >> sh), (uint64_t)(d.H >> sh), (uint64_t)d.n};
+        const uint32_t box[4] = {64u, (uint32_t)(p.w_t >> sh), (uint32_t)(p.h_t >> sh), 1u};
+        if (const char* e = encode_bf16(&tO, d.y, 4, dims, box, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
+      }
+      const int sms_h = sm_count();
+      const int clusters = p.total_tiles < sms_h / 2 ? p.total_tiles : sms_h / 2;
+      static size_t configured_h[2] = {0, 0};
+      const int vi = BNh == 64 ? 0 : 1;
+      if (configured_h[vi] < smem_h) {
+        cudaError_t e = BNh == 64 ? cudaFuncSetAttribute(conv_tc2h_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h)
+                                  : cudaFuncSetAttribute(conv_tc2h_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
+        if (e != cudaSuccess) return errf("cudaFuncSetAttribute(pair-halo, smem=%zu): %s", smem_h, cudaGetErrorString(e));
+        configured_h[vi] = smem_h;
+      }
+      count_launch();
+      if (BNh == 64) conv_tc2h_kernel<64><<<2 * clusters, kConv2hThreads, smem_h, st_>>>(tA, tW, tO, p);
+      else conv_tc2h_kernel<128><<<2 * clusters, kConv2hThreads, smem_h, st_>>>(tA, tW, tO, p);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return errf("conv_tc2h_kernel<%d> launch: %s", BNh, cudaGetErrorString(e));
+      return nullptr;
+    }
+    if (d.force_r == 11) return "pair-HALO variant: not enough shared memory for 2 stages";
+  }
   const bool halo = halo_ok && (d.force_r == 10 || d.force_r == 0);
   if (halo) {
     p.h_t = 16; p.w_t = 8; p.n_t = 1;

@@ -80,6 +80,15 @@ struct ConvLayerDesc {
 // Plans (tile shape, kernel variant, tensor maps) and launches one layer.  Returns nullptr on success or a
 // static/thread-local error string.
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st);
-void conv_set_debug_counters(long long* dev_buf);   // diagnostics: per-role stall cycles of CTA 0 (nullptr = off)
+void conv_set_debug_counters(long long* dev_buf);
+
+// ---- fused snippet gather + conv1_1 (va_conv1_fused.cu)
+bool conv1_fused_supported(int planes, int img_c, int crop);
+int conv1_fused_packed_bytes(int cin);     // size of the dense-K weight pack for `cin` stacked input channels
+cudaError_t launch_pack_conv1_fused_w(const float* w_oihw, void* out, int cin, cudaStream_t st);
+// images/table as for launch_preprocess; y = bf16 NHWC [n][224][224][64] = ReLU(conv3x3(normalised crop) + bias)
+const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c, const int32_t* table,
+                            int n, int planes, const float* mean, const float* stdv, const void* w_fused, const float* bias,
+                            void* y, cudaStream_t st);   // diagnostics: per-role stall cycles of CTA 0 (nullptr = off)
 
 }  // namespace va

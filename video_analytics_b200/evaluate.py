@@ -50,6 +50,7 @@ class TwoStreamEvaluator:
         self.spatial, self.temporal, self.store = spatial, temporal, store
         self.combined = combined if combined is not None else CombinedModel()
         self.L = L
+        self.fused_front_end = False      # True: gather the crops inside conv1_1 (va_forward_store) instead of the K1 tensor
         self._tables: Dict[int, tuple] = {}
         self.mean_s, self.std_s = list(NORM_MEANS_TF), list(NORM_STDS_TF)
         self.mean_t, self.std_t = [FLOW_NORM_MEAN] * (2 * L), [FLOW_NORM_STD] * (2 * L)
@@ -80,16 +81,22 @@ class TwoStreamEvaluator:
         store = store if store is not None else self.store
         offs = torch.arange(0, (V + 1) * SNIPPETS_PER_VIDEO, SNIPPETS_PER_VIDEO, dtype=torch.int32, device=ts.device)
         lay = store.layout
-        xs = ops.preprocess(store.rgb, lay.rgb_shape, ts, self.mean_s, self.std_s, c_pad=self.spatial.c_pad)
-        desc_s, _, prob_s, _ = self.spatial.forward(xs, want_logits=False, want_pred=False)
-        del xs
-        xt = ops.preprocess(store.flow, lay.flow_shape, tt, self.mean_t, self.std_t, c_pad=self.temporal.c_pad)
-        desc_t, _, prob_t, _ = self.temporal.forward(xt, want_logits=False, want_pred=False)
-        del xt
+        desc_s, prob_s = self._stream(self.spatial, store.rgb, lay.rgb_shape, ts, self.mean_s, self.std_s)
+        desc_t, prob_t = self._stream(self.temporal, store.flow, lay.flow_shape, tt, self.mean_t, self.std_t)
         sub = None
         if out is not None:
             sub = {k: t[out_row:out_row + V] for k, t in out.items()}
         return self.combined.fuse(desc_s, desc_t, prob_s, prob_t, offs, out=sub)
+
+    def _stream(self, net: ops.StreamNet, images, shape, table, mean, std):
+        """One stream over a table of snippets -> (descriptors, softmax scores).  bf16 handles gather the crops inside the
+        first convolution (va_forward_store); fp32-parity handles go through the K1 tensor (va_preprocess + va_forward)."""
+        if self.fused_front_end and net.precision == "bf16":
+            desc, _, prob, _ = net.forward_store(images, shape, table, mean, std, want_logits=False, want_pred=False)
+        else:
+            x = ops.preprocess(images, shape, table, mean, std, c_pad=net.c_pad)
+            desc, _, prob, _ = net.forward(x, want_logits=False, want_pred=False)
+        return desc, prob
 
     def alloc_outputs(self, n_rows: int, D: int, C: int, with_svm: bool) -> dict:
         dev = self.store.rgb.device

@@ -88,6 +88,26 @@ def preprocess(images: torch.Tensor, image_shape: Sequence[int], index_table: to
     return out
 
 
+def conv1_fused(images: torch.Tensor, image_shape: Sequence[int], index_table: torch.Tensor, mean: Sequence[float],
+                std: Sequence[float], w: torch.Tensor, bias: torch.Tensor, *, image_bytes: Optional[int] = None) -> torch.Tensor:
+    """K1+conv1_1 fused (csrc/va_conv1_fused.cu): store + index table -> bf16 NHWC [n,224,224,64] =
+    ReLU(conv3x3(normalised crop, w) + bias), w fp32 OIHW [64, planes*c, 3, 3]."""
+    _need_cuda(images, index_table, w, bias)
+    assert images.dtype == torch.uint8 and index_table.dtype == torch.int32 and index_table.dim() == 3
+    h, wd, c = image_shape
+    n, planes, four = index_table.shape
+    assert four == 4 and tuple(w.shape) == (64, planes * c, 3, 3) and w.dtype == torch.float32
+    if image_bytes is None:
+        image_bytes = h * wd * c
+    nch = planes * c
+    fm = (C.c_float * nch)(*mean)
+    fs = (C.c_float * nch)(*std)
+    y = torch.empty((n, CROP, CROP, 64), dtype=torch.bfloat16, device=images.device)
+    check(_lib.load().va_conv1_fused(ptr(images), image_bytes, h, wd, c, ptr(index_table), n, planes, fm, fs, ptr(w),
+                                     ptr(bias), ptr(y), stream_ptr()), "va_conv1_fused")
+    return y
+
+
 def svm_fit(X: torch.Tensor, class_index: torch.Tensor, n_classes: int, *, C_reg: float = 1.0, bias: float = 1.0,
             tol: float = 1e-4, max_iter: int = 1000):
     """LinearSVC().fit (reference combinedModel.py:34-35) on the device: one-vs-rest L2-regularised squared-hinge SVM by
@@ -212,6 +232,31 @@ class StreamNet:
         pred = torch.empty((n,), dtype=torch.int32, device=dev) if want_pred else None
         check(_lib.load().va_forward(self._h, ptr(x_nhwc), n, ptr(desc), ptr(logits), ptr(probs), ptr(pred),
                                      stream_ptr()), "va_forward")
+        return desc, logits, probs, pred
+
+    def forward_store(self, images: torch.Tensor, image_shape: Sequence[int], index_table: torch.Tensor,
+                      mean: Sequence[float], std: Sequence[float], *, image_bytes: Optional[int] = None, want_logits=True,
+                      want_probs=True, want_pred=True):
+        """The forward fed from the image store: the snippet transform is gathered straight into the first
+        convolution (va_forward_store), no preprocessed tensor is materialised.  Same returns as forward()."""
+        _need_cuda(images, index_table)
+        assert images.dtype == torch.uint8 and index_table.dtype == torch.int32 and index_table.dim() == 3
+        h, wd, c = image_shape
+        n, planes, four = index_table.shape
+        assert four == 4
+        nch = planes * c
+        assert len(mean) == nch and len(std) == nch, "one mean/std per stacked channel"
+        if image_bytes is None:
+            image_bytes = h * wd * c
+        dev = images.device
+        desc = torch.empty((n, self.desc_dim), dtype=torch.float32, device=dev)
+        logits = torch.empty((n, self.n_classes), dtype=torch.float32, device=dev) if want_logits else None
+        probs = torch.empty((n, self.n_classes), dtype=torch.float32, device=dev) if want_probs else None
+        pred = torch.empty((n,), dtype=torch.int32, device=dev) if want_pred else None
+        fm = (C.c_float * nch)(*mean)
+        fs = (C.c_float * nch)(*std)
+        check(_lib.load().va_forward_store(self._h, ptr(images), image_bytes, h, wd, c, ptr(index_table), n, planes, fm, fs,
+                                           ptr(desc), ptr(logits), ptr(probs), ptr(pred), stream_ptr()), "va_forward_store")
         return desc, logits, probs, pred
 
     def close(self):
