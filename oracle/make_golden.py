@@ -236,6 +236,83 @@ def main():
               open(os.path.join(GOLD, "train_step.json"), "w"), indent=1)
     report["train_step_vs_reference_loop_body"] = [st["loss"] for st in steps]
 
+    # ---- (i) model surgery: the reference's OWN __copyFirstLayer__ / __swapClassifier__ (temporalModel.py:149-181, py3-clean
+    #          method bodies) exec'd as plain functions on a shim `self`, vs the restated builders, same seed -> every
+    #          state_dict tensor bit-equal (the fresh conv1 bias and the classifier consume the RNG in the same order).
+    import torchvision.models as tv_models
+    with open(os.path.join(REF, "temporalModel.py")) as f:
+        tlines = f.readlines()
+    i0 = next(i for i, l in enumerate(tlines) if "def __copyFirstLayer__" in l)
+    i1 = next(i for i, l in enumerate(tlines) if i > i0 and l.strip().startswith("def ") and "__swapClassifier__" not in l
+              and "__copyFirstLayer__" not in l)
+    surgery_src = textwrap.dedent("".join(tlines[i0:i1]).expandtabs(4))
+    ns4 = {"nn": torch.nn}
+    exec(surgery_src, ns4)
+    surgery = {}
+    for seed in (0, 3):
+        torch.manual_seed(seed)
+        shim_t = types.SimpleNamespace(model=tv_models.vgg16(weights=None), flowSampleSize=ref_params.VIDEO_INPUT_FLOW_COUNT,
+                                       descriptorDim=ref_params.VIDEO_DESCRIPTOR_DIM, nActionClasses=ref_params.NACTION_CLASSES)
+        ns4["__copyFirstLayer__"](shim_t)
+        ns4["__swapClassifier__"](shim_t)
+        mine_t = ts.build_temporal_model(seed=seed)
+        sd_r, sd_m = shim_t.model.state_dict(), mine_t.state_dict()
+        assert list(sd_r.keys()) == list(sd_m.keys())
+        for k in sd_r:
+            assert torch.equal(sd_r[k], sd_m[k]), ("temporal surgery", seed, k)
+        # spatial: only the classifier swap (spatialModel.py:136-152 is the same method body)
+        torch.manual_seed(seed)
+        shim_s = types.SimpleNamespace(model=tv_models.vgg16(weights=None), descriptorDim=ref_params.VIDEO_DESCRIPTOR_DIM,
+                                       nActionClasses=ref_params.NACTION_CLASSES)
+        ns4["__swapClassifier__"](shim_s)
+        mine_s = ts.build_spatial_model(seed=seed)
+        for k, v in shim_s.model.state_dict().items():
+            assert torch.equal(v, mine_s.state_dict()[k]), ("spatial surgery", seed, k)
+        surgery[str(seed)] = {"temporal_conv1_w_sha256": sha(sd_m["features.0.weight"]), "temporal_conv1_b_sha256": sha(sd_m["features.0.bias"]),
+                              "temporal_fc4_w_sha256": sha(sd_m["classifier.9.weight"]),
+                              "spatial_fc1_w_sha256": sha(mine_s.state_dict()["classifier.0.weight"])}
+    json.dump({"reference_lines": [i0 + 1, i1], "seeds": surgery}, open(os.path.join(GOLD, "model_surgery.json"), "w"), indent=1)
+    report["model_surgery_vs_reference_methods"] = "bit-equal (seeds 0, 3)"
+
+    # ---- (j) validate(): the reference's own loop-body lines (spatialModel.py:212-228: forward, summed loss, argmax, correct
+    #          count, per-video AverageMeter update) exec'd on a shim, vs ts.forward_eval + ts.update_video_dict
+    with open(os.path.join(REF, "spatialModel.py")) as f:
+        lines = f.readlines()
+    v0 = next(i for i, l in enumerate(lines) if "def validate" in l)
+    first = next(i for i, l in enumerate(lines) if i > v0 and "op = self.features(ip)" in l)
+    last = max(i for i, l in enumerate(lines) if i > first and i < first + 25 and "self.testDict[videoNames[i]][0].update(featureVectors[i])" in l)
+    vbody = textwrap.dedent("".join(lines[first:last + 1]).expandtabs(4))
+    model_v = ts.build_spatial_model(seed=6)
+    model_v.eval()
+    shim_v = types.SimpleNamespace(features=model_v.features, classifierList=list(model_v.classifier),
+                                   classifierLen=len(list(model_v.classifier)), criterion=torch.nn.CrossEntropyLoss(), testDict={})
+    my_dict = {}
+    g = torch.Generator().manual_seed(78)
+    val = {"loss": 0, "correct": 0}
+    my_loss, my_correct = 0, 0
+    names_all = [("v_A_g01_c01", "v_B_g01_c01"), ("v_B_g01_c01", "v_C_g01_c02")]
+    for it in range(2):
+        ip = torch.randn(2, 3, 224, 224, generator=g)
+        labels = torch.randint(1, 101, (2,), generator=g)
+        ns5 = {"self": shim_v, "ip": ip, "labelVar": labels, "labels": labels, "videoNames": names_all[it],
+               "AverageMeter": ref_utils.AverageMeter, "loss": val["loss"], "correct": val["correct"]}
+        with torch.no_grad():
+            exec(vbody, ns5)
+        val["loss"], val["correct"] = ns5["loss"], ns5["correct"]
+        fv, op, pred = ts.forward_eval(model_v, ip)
+        assert torch.equal(ns5["featureVectors"], fv) and torch.equal(ns5["op"], op) and torch.equal(ns5["pred"].view(-1), pred)
+        my_loss = my_loss + torch.nn.CrossEntropyLoss()(op, labels)
+        my_correct += int(pred.eq(labels).sum())
+        ts.update_video_dict(my_dict, names_all[it], labels, fv)
+    assert torch.equal(val["loss"], my_loss) and val["correct"] == my_correct
+    assert sorted(shim_v.testDict) == sorted(my_dict)
+    for k in my_dict:
+        assert torch.equal(shim_v.testDict[k][0].avg, my_dict[k][0].avg) and shim_v.testDict[k][0].count == my_dict[k][0].count
+    json.dump({"model_seed": 6, "input_seed": 78, "reference_lines": [first + 1, last + 1], "loss": float(my_loss), "correct": my_correct,
+               "avg_sha256": {k: sha(v[0].avg) for k, v in sorted(my_dict.items())}},
+              open(os.path.join(GOLD, "validate_body.json"), "w"), indent=1)
+    report["validate_body_vs_reference_lines"] = "bit-equal (2 batches)"
+
     # ---- (g) oracle forward vectors (restated model; pins the oracle to itself across machines)
     lay = make_layout(2)
     rgb, flow = synth.build_store_numpy(lay)

@@ -202,3 +202,35 @@ def test_jpeg_restatement_vs_pillow():
     Image.fromarray(synth(32, 32, 3)).save(b, "JPEG", progressive=True)
     with pytest.raises(J.JpegUnsupported):
         J.decode(b.getvalue())
+
+
+def test_model_surgery_vs_golden(golden):
+    """State-dict hashes recorded while the reference's own __copyFirstLayer__ / __swapClassifier__ methods
+    (temporalModel.py:149-181) were exec'd next to the restated builders (oracle/make_golden.py section (i))."""
+    g = golden("model_surgery.json")
+    for seed, h in g["seeds"].items():
+        mt = ts.build_temporal_model(seed=int(seed)).state_dict()
+        assert sha(mt["features.0.weight"]) == h["temporal_conv1_w_sha256"]
+        assert sha(mt["features.0.bias"]) == h["temporal_conv1_b_sha256"]
+        assert sha(mt["classifier.9.weight"]) == h["temporal_fc4_w_sha256"]
+        ms = ts.build_spatial_model(seed=int(seed)).state_dict()
+        assert sha(ms["classifier.0.weight"]) == h["spatial_fc1_w_sha256"]
+
+
+def test_validate_body_vs_golden(golden):
+    """validate() loop body (spatialModel.py:212-228) as recorded from the reference's own lines: summed loss, correct
+    count and per-video AverageMeter means."""
+    g = golden("validate_body.json")
+    model = ts.build_spatial_model(seed=g["model_seed"])
+    gen = torch.Generator().manual_seed(g["input_seed"])
+    names_all = [("v_A_g01_c01", "v_B_g01_c01"), ("v_B_g01_c01", "v_C_g01_c02")]
+    d, loss, correct = {}, 0, 0
+    for it in range(2):
+        ip = torch.randn(2, 3, 224, 224, generator=gen)
+        labels = torch.randint(1, 101, (2,), generator=gen)
+        fv, op, pred = ts.forward_eval(model, ip)
+        loss = loss + torch.nn.CrossEntropyLoss()(op, labels)
+        correct += int(pred.eq(labels).sum())
+        ts.update_video_dict(d, names_all[it], labels, fv)
+    assert float(loss) == g["loss"] and correct == g["correct"]
+    assert {k: sha(v[0].avg) for k, v in sorted(d.items())} == g["avg_sha256"]
