@@ -121,14 +121,21 @@ va_status va_linear(const void* x, int n, int in_features, const float* w, const
  * argmax_c X.W[c] + b[c] in fp64), plus the score-averaging protocol of notes.txt:113-116,121-124,225-230.
  *   desc_s/desc_t  fp32 [N][D]; score_s/score_t fp32 [N][C] (softmax); snippets of video v are rows
  *   video_offsets[v] .. video_offsets[v+1]-1 (int32 [V+1]) of all four arrays.
- *   svm_w fp64 [C][2D], svm_b fp64 [C] (NULL = skip SVM scoring).
+ *   svm_w fp64 [C_svm][2D], svm_b fp64 [C_svm] (NULL = skip SVM scoring).  C_svm is the number of classes the SVM was
+ *   FITTED on (len(np.unique(y)), as LinearSVC: 25 on mini-UCF-101) and is independent of the network's score width C (101).
  *   out: video_desc fp32 [V][2D]; video_scores fp32 [V][C] = (w_s*mean_s + w_t*mean_t)/(w_s+w_t);
- *        score_pred int32 [V]; svm_scores fp64 [V][C]; svm_pred int32 [V].  Any output may be NULL.
+ *        score_pred int32 [V]; svm_scores fp64 [V][C_svm]; svm_pred int32 [V] in [0, C_svm).  Any output may be NULL.
  * --------------------------------------------------------------------------------------------------------- */
 va_status va_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
-                  const int32_t* video_offsets, int V, int D, int C, const double* svm_w, const double* svm_b,
+                  const int32_t* video_offsets, int V, int D, int C, int C_svm, const double* svm_w, const double* svm_b,
                   float w_s, float w_t, float* video_desc, float* video_scores, int32_t* score_pred,
                   double* svm_scores, int32_t* svm_pred, va_stream_t stream);
+
+/* LinearSVC.predict on fp64 rows (combinedModel.py:38 on the fp64 matrix combineDescriptors returns, :19-25):
+ * scores[v][c] = X[v] . W[c] + b[c] in fp64, pred[v] = index of the first maximum.  X fp64 [V][F], W fp64 [P][F],
+ * b fp64 [P]; scores fp64 [V][P] and pred int32 [V] (either may be NULL). */
+va_status va_svm_decision(const double* X, int V, int F, const double* W, const double* b, int P, double* scores,
+                          int32_t* pred, va_stream_t stream);
 
 /* Running per-video descriptor sums: the device form of the reference's per-sample AverageMeter loop in
  * train()/validate() (spatialModel.py:183-188, 223-228).  For b = 0..B-1 in order: sum[video_ids[b]][:] +=

@@ -33,7 +33,8 @@ SIGNATURES = {
     "va_conv1_fused": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _vp, _vp]),
     "va_conv2d_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "va_linear": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
-    "va_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "va_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "va_svm_decision": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "va_consensus_update": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "va_pack_input_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "va_pack_input_nchw_split6": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

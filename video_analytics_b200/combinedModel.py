@@ -81,17 +81,15 @@ class CombinedModel:
         return self
 
     def decision_function(self, descriptors) -> torch.Tensor:
-        """[V, C] fp64 scores on the device for already-fused descriptors [V, 2D] (numpy or tensor)."""
+        """[V, C_svm] fp64 scores on the device for already-fused descriptors [V, 2D] (numpy or tensor), scored in fp64 on
+        the fp64 values -- what `linearClassifier.predict(svmTestData)` (reference :38) sees after pandas parsed the CSVs."""
+        if self._w_dev is None:
+            raise ops.VAError("CombinedModel: no SVM set (call fit() or set_svm() first)")
         X = torch.as_tensor(np.asarray(descriptors) if not isinstance(descriptors, torch.Tensor) else descriptors)
-        X = X.to(device="cuda", dtype=torch.float32).contiguous()
-        V, twoD = X.shape
-        D = twoD // 2
-        # each video is its own 1-snippet segment; the kernel's mean over one element is the identity
-        offs = torch.arange(V + 1, dtype=torch.int32, device="cuda")
-        ds, dt = X[:, :D].contiguous(), X[:, D:].contiguous()
-        res = ops.fuse(ds, dt, None, None, offs, svm_w=self._w_dev, svm_b=self._b_dev)
-        self._last = res
-        return res["svm_scores"]
+        X = X.to(device="cuda", dtype=torch.float64).contiguous()
+        scores, pred = ops.svm_decision(X, self._w_dev, self._b_dev)
+        self._last = {"svm_scores": scores, "svm_pred": pred}
+        return scores
 
     def predict(self, descriptors) -> np.ndarray:
         self.decision_function(descriptors)

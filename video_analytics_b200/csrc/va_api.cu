@@ -43,6 +43,20 @@ va_status fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(VA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));      \
   } while (0)
 
+// Stream-ordered scratch that is released on every exit path (early error returns included).
+struct AsyncScratch {
+  cudaStream_t st;
+  void* ptrs[4];
+  int n;
+  explicit AsyncScratch(cudaStream_t s) : st(s), ptrs{nullptr, nullptr, nullptr, nullptr}, n(0) {}
+  cudaError_t alloc(void** out, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(out, bytes, st);
+    if (e == cudaSuccess && n < 4) ptrs[n++] = *out;
+    return e;
+  }
+  ~AsyncScratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st); }
+};
+
 // VGG16 configuration "D" (torchvision models.vgg16; reference spatialModel.py:110): output channels per conv,
 // `true` = followed by MaxPool2d(2,2).
 struct ConvSpec { int cout; bool pool; };
@@ -95,11 +109,13 @@ static va_status require_sm100() {
   if (major != 10) return fail(VA_ERR_UNSUPPORTED, "libva_b200 is built for sm_100a only; device has cc %d.x", major);
   // Stream-ordered scratch (cudaMallocAsync in the training primitives) must stay cached across synchronisation
   // points: the default pool releases everything on every sync, which turns each step into GBs of re-allocation.
+  // Bounded: the pool may keep up to 2 GiB (the largest scratch set of a batch-256 step is ~1 GiB: FC1's bf16 repack
+  // + weight-gradient planes); anything above goes back to the driver, so torch's allocator is not starved.
   static bool pool_set[64] = {false};
   if (dev < 64 && !pool_set[dev]) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
+      uint64_t keep = 2ull << 30;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     pool_set[dev] = true;
@@ -331,12 +347,12 @@ va_status va_conv1_fused(const uint8_t* images, size_t image_bytes, int img_h, i
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* wp = nullptr;
-  VA_CUDA(cudaMallocAsync(&wp, (size_t)va::conv1_fused_packed_bytes(planes * img_c), st));
+  AsyncScratch scratch(st);
+  VA_CUDA(scratch.alloc(&wp, (size_t)va::conv1_fused_packed_bytes(planes * img_c)));
   cudaError_t pe = va::launch_pack_conv1_fused_w(w, wp, planes * img_c, st);
   const char* e = pe == cudaSuccess ? va::conv1_fused_run(images, image_bytes, img_h, img_w, img_c, index_table, n, planes, mean,
                                                           std, wp, bias, y, st)
                                     : cudaGetErrorString(pe);
-  cudaFreeAsync(wp, st);
   if (e) return fail(VA_ERR_CUDA, "va_conv1_fused: %s", e);
   return VA_OK;
 }
@@ -348,13 +364,13 @@ va_status va_conv2d_nhwc(const void* x, int n, int H, int W, int cin, int cin_pa
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* wp = nullptr;
-  VA_CUDA(cudaMallocAsync(&wp, (size_t)ks * ks * cout * cin_pad * 2, st));
+  AsyncScratch scratch(st);
+  VA_CUDA(scratch.alloc(&wp, (size_t)ks * ks * cout * cin_pad * 2));
   VA_CUDA(va::launch_pack_conv_w(w, wp, cout, cin, cin_pad, ks, st));
   va::ConvLayerDesc d;
   d.x = x; d.n = n; d.H = H; d.W = W; d.cin_pad = cin_pad; d.w_packed = wp; d.bias = bias; d.Cout = cout; d.ks = ks;
   d.relu = relu; d.pool = pool; d.y = y; d.y_f32 = nullptr; d.force_bn = force_bn; d.force_r = force_r; d.split6 = 0;
   const char* e = va::conv_layer_run(d, st);
-  cudaFreeAsync(wp, st);
   if (e) return fail(VA_ERR_CUDA, "va_conv2d_nhwc: %s", e);
   return VA_OK;
 }
@@ -367,29 +383,41 @@ va_status va_linear(const void* x, int n, int in_features, const float* w, const
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* wp = nullptr;
-  VA_CUDA(cudaMallocAsync(&wp, (size_t)out_features * in_features * 2, st));
+  AsyncScratch scratch(st);
+  VA_CUDA(scratch.alloc(&wp, (size_t)out_features * in_features * 2));
   VA_CUDA(va::launch_pack_fc_w(w, wp, out_features, in_features, 0, 0, st));
   va::ConvLayerDesc d;
   d.x = x; d.n = n; d.H = 1; d.W = 1; d.cin_pad = in_features; d.w_packed = wp; d.bias = bias; d.Cout = out_features;
   d.ks = 1; d.relu = relu; d.pool = 0; d.y = y_bf16; d.y_f32 = y_f32; d.force_bn = force_bn; d.force_r = 0; d.split6 = 0;
   const char* e = va::conv_layer_run(d, st);
-  cudaFreeAsync(wp, st);
   if (e) return fail(VA_ERR_CUDA, "va_linear: %s", e);
   return VA_OK;
 }
 
 va_status va_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
-                  const int32_t* video_offsets, int V, int D, int C, const double* svm_w, const double* svm_b, float w_s,
+                  const int32_t* video_offsets, int V, int D, int C, int C_svm, const double* svm_w, const double* svm_b, float w_s,
                   float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
                   int32_t* svm_pred, va_stream_t stream) {
   if (!video_offsets) return fail(VA_ERR_INVALID, "va_fuse: video_offsets is NULL");
   if (V < 0 || D < 1 || C < 1) return fail(VA_ERR_INVALID, "va_fuse: bad sizes V=%d D=%d C=%d", V, D, C);
+  if (svm_w && (C_svm < 1 || C_svm > 4096)) return fail(VA_ERR_INVALID, "va_fuse: C_svm %d (rows of svm_w) out of range", C_svm);
+  if (!svm_w) C_svm = 0;
   if ((svm_w == nullptr) != (svm_b == nullptr)) return fail(VA_ERR_INVALID, "va_fuse: svm_w and svm_b go together");
   if (svm_w && !(desc_s && desc_t)) return fail(VA_ERR_INVALID, "va_fuse: SVM scoring needs both descriptor arrays");
   if (w_s + w_t == 0.f) return fail(VA_ERR_INVALID, "va_fuse: w_s + w_t == 0");
   if (va_status s = require_sm100()) return s;
-  VA_CUDA(va::launch_fuse(desc_s, desc_t, score_s, score_t, video_offsets, V, D, C, svm_w, svm_b, w_s, w_t, video_desc,
+  VA_CUDA(va::launch_fuse(desc_s, desc_t, score_s, score_t, video_offsets, V, D, C, C_svm, svm_w, svm_b, w_s, w_t, video_desc,
                           video_scores, score_pred, svm_scores, svm_pred, static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
+
+va_status va_svm_decision(const double* X, int V, int F, const double* W, const double* b, int P, double* scores,
+                          int32_t* pred, va_stream_t stream) {
+  if (!X || !W || !b) return fail(VA_ERR_INVALID, "va_svm_decision: NULL argument");
+  if (V < 0 || F < 1 || P < 1 || (size_t)(F + P) * sizeof(double) > 48 * 1024)
+    return fail(VA_ERR_INVALID, "va_svm_decision: bad sizes V=%d F=%d P=%d", V, F, P);
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_svm_decision(X, V, F, W, b, P, scores, pred, static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }
 
@@ -497,9 +525,10 @@ va_status va_conv2d_dgrad(const void* dZ, int n, int H, int W, int cout, const f
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* wt = nullptr; void* wp = nullptr; float* zero_bias = nullptr;
-  VA_CUDA(cudaMallocAsync(&wt, (size_t)cout * cin * 9 * 4, st));
-  VA_CUDA(cudaMallocAsync(&wp, (size_t)9 * cin * cout * 2, st));
-  VA_CUDA(cudaMallocAsync(&zero_bias, (size_t)cin * 4, st));
+  AsyncScratch scratch(st);
+  VA_CUDA(scratch.alloc(reinterpret_cast<void**>(&wt), (size_t)cout * cin * 9 * 4));
+  VA_CUDA(scratch.alloc(&wp, (size_t)9 * cin * cout * 2));
+  VA_CUDA(scratch.alloc(reinterpret_cast<void**>(&zero_bias), (size_t)cin * 4));
   VA_CUDA(cudaMemsetAsync(zero_bias, 0, (size_t)cin * 4, st));
   VA_CUDA(va::launch_flip_transpose_conv_w(w, wt, cout, cin, 3, st));          // OIHW' [cin][cout][3][3]
   VA_CUDA(va::launch_pack_conv_w(wt, wp, cin, cout, cout, 3, st));             // the dgrad conv: cout -> cin channels
@@ -507,7 +536,6 @@ va_status va_conv2d_dgrad(const void* dZ, int n, int H, int W, int cout, const f
   d.x = dZ; d.n = n; d.H = H; d.W = W; d.cin_pad = cout; d.w_packed = wp; d.bias = zero_bias; d.Cout = cin; d.ks = 3;
   d.relu = 0; d.pool = 0; d.y = dX; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0; d.split6 = 0;
   const char* e = va::conv_layer_run(d, st);
-  cudaFreeAsync(wt, st); cudaFreeAsync(wp, st); cudaFreeAsync(zero_bias, st);
   if (e) return fail(VA_ERR_CUDA, "va_conv2d_dgrad: %s", e);
   return VA_OK;
 }
@@ -518,15 +546,15 @@ va_status va_linear_dgrad(const void* dY, int n, int out_features, const float* 
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* wp = nullptr; float* zero_bias = nullptr;
-  VA_CUDA(cudaMallocAsync(&wp, (size_t)in_features * out_features * 2, st));
-  VA_CUDA(cudaMallocAsync(&zero_bias, (size_t)in_features * 4, st));
+  AsyncScratch scratch(st);
+  VA_CUDA(scratch.alloc(&wp, (size_t)in_features * out_features * 2));
+  VA_CUDA(scratch.alloc(reinterpret_cast<void**>(&zero_bias), (size_t)in_features * 4));
   VA_CUDA(cudaMemsetAsync(zero_bias, 0, (size_t)in_features * 4, st));
   VA_CUDA(va::launch_pack_fc_w_t(w, wp, out_features, in_features, st));      // bf16 [in][out]
   va::ConvLayerDesc d;
   d.x = dY; d.n = n; d.H = 1; d.W = 1; d.cin_pad = out_features; d.w_packed = wp; d.bias = zero_bias; d.Cout = in_features;
   d.ks = 1; d.relu = 0; d.pool = 0; d.y = dX; d.y_f32 = nullptr; d.force_bn = 0; d.force_r = 0; d.split6 = 0;
   const char* e = va::conv_layer_run(d, st);
-  cudaFreeAsync(wp, st); cudaFreeAsync(zero_bias, st);
   if (e) return fail(VA_ERR_CUDA, "va_linear_dgrad: %s", e);
   return VA_OK;
 }
@@ -538,9 +566,9 @@ va_status va_wgrad(const void* dZ, const void* X, int n, int H, int W, int cout,
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* ws = nullptr;                       // [tap][cout][cin] accumulation planes of the 3x3 case
-  if (ks != 1) VA_CUDA(cudaMallocAsync(&ws, (size_t)ks * ks * cout * cin * 4, st));
+  AsyncScratch scratch(st);
+  if (ks != 1) VA_CUDA(scratch.alloc(reinterpret_cast<void**>(&ws), (size_t)ks * ks * cout * cin * 4));
   const char* e = va::wgrad_run(dZ, X, n, H, W, cout, cin, cin_pad, ks, ws, dW, st);
-  if (ws) cudaFreeAsync(ws, st);
   if (e) return fail(VA_ERR_CUDA, "va_wgrad: %s", e);
   return VA_OK;
 }

@@ -22,9 +22,11 @@ cudaError_t launch_transpose_f32(const float* w, float* out, int rows, int cols,
 cudaError_t launch_head(const float* desc, const float* w4t, const float* b4, int n, int D, int C, float* logits,
                         float* probs, int32_t* pred, cudaStream_t st);
 cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
-                        const int32_t* offs, int V, int D, int C, const double* svm_w, const double* svm_b, float w_s,
+                        const int32_t* offs, int V, int D, int C, int Csvm, const double* svm_w, const double* svm_b, float w_s,
                         float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
                         int32_t* svm_pred, cudaStream_t st);
+cudaError_t launch_svm_decision(const double* X, int V, int F, const double* W, const double* b, int P, double* scores,
+                                int32_t* pred, cudaStream_t st);
 
 cudaError_t launch_consensus_update(float* sum, int32_t* count, const int32_t* video_ids, const float* fv, int B, int D,
                                     cudaStream_t st);

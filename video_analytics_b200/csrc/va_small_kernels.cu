@@ -653,14 +653,14 @@ __device__ __forceinline__ float seq_sum(const float* __restrict__ src, int stri
 __global__ void __launch_bounds__(1024) fuse_kernel(const float* __restrict__ desc_s, const float* __restrict__ desc_t,
                                                    const float* __restrict__ score_s,
                                                    const float* __restrict__ score_t,
-                                                   const int32_t* __restrict__ offs, int D, int C,
+                                                   const int32_t* __restrict__ offs, int D, int C, int Csvm,
                                                    const double* __restrict__ svm_w, const double* __restrict__ svm_b,
                                                    float w_s, float w_t, float* __restrict__ video_desc,
                                                    float* __restrict__ video_scores, int32_t* __restrict__ score_pred,
                                                    double* __restrict__ svm_scores, int32_t* __restrict__ svm_pred) {
   extern __shared__ unsigned char fsm_raw[];
-  double* ssvm = reinterpret_cast<double*>(fsm_raw);          // C
-  float* sx = reinterpret_cast<float*>(ssvm + C);             // 2D fused descriptor
+  double* ssvm = reinterpret_cast<double*>(fsm_raw);          // Csvm (rows of svm_w: the classes the SVM was fitted on)
+  float* sx = reinterpret_cast<float*>(ssvm + Csvm);          // 2D fused descriptor
   float* ssc = sx + 2 * D;                                    // C fused scores
   float* smean = ssc + C;                                     // 2C per-stream score means
   const int v = blockIdx.x;
@@ -702,36 +702,75 @@ __global__ void __launch_bounds__(1024) fuse_kernel(const float* __restrict__ de
   if (svm_w != nullptr) {
     // decision_function in fp64 like sklearn: one warp per class, lanes stride the 2D-long dot product.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int c = warp; c < C; c += nwarps) {
+    for (int c = warp; c < Csvm; c += nwarps) {
       double acc = 0.0;
       for (int j = lane; j < 2 * D; j += 32) acc += (double)sx[j] * svm_w[(size_t)c * 2 * D + j];
       for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
       if (lane == 0) {
         acc += svm_b[c];
         ssvm[c] = acc;
-        if (svm_scores) svm_scores[(size_t)v * C + c] = acc;
+        if (svm_scores) svm_scores[(size_t)v * Csvm + c] = acc;
       }
     }
     __syncthreads();
     if (threadIdx.x == 0 && svm_pred) {
       double bv = ssvm[0]; int bi = 0;
-      for (int c = 1; c < C; ++c) if (ssvm[c] > bv) { bv = ssvm[c]; bi = c; }
+      for (int c = 1; c < Csvm; ++c) if (ssvm[c] > bv) { bv = ssvm[c]; bi = c; }
       svm_pred[v] = bi;
     }
   }
 }
 
 cudaError_t launch_fuse(const float* desc_s, const float* desc_t, const float* score_s, const float* score_t,
-                        const int32_t* offs, int V, int D, int C, const double* svm_w, const double* svm_b, float w_s,
+                        const int32_t* offs, int V, int D, int C, int Csvm, const double* svm_w, const double* svm_b, float w_s,
                         float w_t, float* video_desc, float* video_scores, int32_t* score_pred, double* svm_scores,
                         int32_t* svm_pred, cudaStream_t st) {
   if (V == 0) return cudaSuccess;
-  const size_t smem = C * sizeof(double) + (2 * D + 3 * C) * sizeof(float);
+  const size_t smem = Csvm * sizeof(double) + (2 * D + 3 * C) * sizeof(float);
   const int ncols = 2 * D + 2 * C;                            // one thread per column sum when it fits a block
   const int threads = std::min(1024, std::max(128, (ncols + 31) / 32 * 32));
   count_launch();
-  fuse_kernel<<<V, threads, smem, st>>>(desc_s, desc_t, score_s, score_t, offs, D, C, svm_w, svm_b, w_s, w_t, video_desc,
+  fuse_kernel<<<V, threads, smem, st>>>(desc_s, desc_t, score_s, score_t, offs, D, C, Csvm, svm_w, svm_b, w_s, w_t, video_desc,
                                     video_scores, score_pred, svm_scores, svm_pred);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ F2 on fp64 rows
+// LinearSVC.predict on already-fused fp64 descriptors (the values pandas reads from the descriptor CSVs,
+// combinedModel.py:19-25,38): scores[v][c] = X[v] . W[c] + b[c] in fp64, pred = first maximum.  One CTA per video, one
+// warp per class (lanes stride the F-long dot product, xor-butterfly reduction: the summation order is fixed).
+__global__ void __launch_bounds__(256) svm_decision_kernel(const double* __restrict__ X, int F, const double* __restrict__ W,
+                                                           const double* __restrict__ b, int P, double* __restrict__ scores,
+                                                           int32_t* __restrict__ pred) {
+  extern __shared__ double sdec[];      // F + P
+  double* sxv = sdec;
+  double* ssc = sdec + F;
+  const int v = blockIdx.x;
+  for (int j = threadIdx.x; j < F; j += blockDim.x) sxv[j] = X[(size_t)v * F + j];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < P; c += nwarps) {
+    double acc = 0.0;
+    for (int j = lane; j < F; j += 32) acc += sxv[j] * W[(size_t)c * F + j];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      acc += b[c];
+      ssc[c] = acc;
+      if (scores) scores[(size_t)v * P + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && pred) {
+    double bv = ssc[0]; int bi = 0;
+    for (int c = 1; c < P; ++c) if (ssc[c] > bv) { bv = ssc[c]; bi = c; }
+    pred[v] = bi;
+  }
+}
+cudaError_t launch_svm_decision(const double* X, int V, int F, const double* W, const double* b, int P, double* scores,
+                                int32_t* pred, cudaStream_t st) {
+  if (V == 0) return cudaSuccess;
+  count_launch();
+  svm_decision_kernel<<<V, 256, (size_t)(F + P) * sizeof(double), st>>>(X, F, W, b, P, scores, pred);
   return cudaGetLastError();
 }
 

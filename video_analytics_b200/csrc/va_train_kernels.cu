@@ -360,13 +360,18 @@ __global__ void __launch_bounds__(128) ce_fwd_bwd_kernel(const float* __restrict
   if (lane == 0) red[warp] = s;
   __syncthreads();
   s = red[0] + red[1] + red[2] + red[3];
-  const int lab = (int)labels[i];
+  // A label outside [0, C) (torch's CrossEntropyLoss raises "Target out of bounds"; the reference's 1-based class ids
+  // reach C when all 101 classes are in use) must not index shared memory: the loss becomes NaN -- loud, and it
+  // poisons nothing else -- and the sample contributes no gradient.  The host layer validates labels before upload.
+  const long long lab64 = labels[i];
+  const bool lab_ok = lab64 >= 0 && lab64 < (long long)C;
+  const int lab = lab_ok ? (int)lab64 : 0;
   const float inv_n = 1.0f / (float)n;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float pr = expf(sl[c] - mx) / s;
-    dlogits[(size_t)i * C + c] = (pr - (c == lab ? 1.f : 0.f)) * inv_n;
+    dlogits[(size_t)i * C + c] = lab_ok ? (pr - (c == lab ? 1.f : 0.f)) * inv_n : 0.f;
   }
-  if (threadIdx.x == 0) atomicAdd(loss_sum, (logf(s) + mx - sl[lab]) * inv_n);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, lab_ok ? (logf(s) + mx - sl[lab]) * inv_n : __int_as_float(0x7fc00000));
 }
 // dW4[c][d] = sum_i dlogits[i][c] * x[i][d]; db4[c] = sum_i dlogits[i][c]   (grid = C, block = D threads)
 __global__ void logit_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ x, int n, int D, int C,

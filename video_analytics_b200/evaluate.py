@@ -104,6 +104,8 @@ class TwoStreamEvaluator:
                "video_scores": torch.zeros((n_rows, C), dtype=torch.float32, device=dev),
                "score_pred": torch.full((n_rows,), -1, dtype=torch.int32, device=dev)}
         if with_svm:
-            out["svm_scores"] = torch.zeros((n_rows, C), dtype=torch.float64, device=dev)
+            # one column per class the SVM was fitted on (LinearSVC: len(np.unique(y))), not per network class
+            c_svm = int(self.combined.coef_.shape[0]) if self.combined.coef_ is not None else C
+            out["svm_scores"] = torch.zeros((n_rows, c_svm), dtype=torch.float64, device=dev)
             out["svm_pred"] = torch.full((n_rows,), -1, dtype=torch.int32, device=dev)
         return out

@@ -138,7 +138,16 @@ def fuse(desc_s, desc_t, score_s, score_t, video_offsets: torch.Tensor, *, svm_w
     ref = desc_s if desc_s is not None else score_s
     dev = ref.device
     D = desc_s.shape[1] if desc_s is not None else 1
-    Cn = score_s.shape[1] if score_s is not None else (svm_w.shape[0] if svm_w is not None else 1)
+    Cn = score_s.shape[1] if score_s is not None else 1
+    Csvm = 0
+    if svm_w is not None:
+        # the SVM has one row per class it was FITTED on (LinearSVC: len(np.unique(y))), independent of the score width
+        if desc_s is None or desc_t is None:
+            raise VAError("ops.fuse: SVM scoring needs both descriptor arrays")
+        Csvm = int(svm_w.shape[0])
+        if svm_w.dim() != 2 or svm_w.shape[1] != 2 * D or svm_b is None or svm_b.numel() != Csvm:
+            raise VAError(f"ops.fuse: svm_w {tuple(svm_w.shape)} / svm_b {None if svm_b is None else tuple(svm_b.shape)} "
+                          f"do not match descriptors of width 2*{D}")
     res = out if out is not None else {}
     if desc_s is not None and "video_desc" not in res:
         res["video_desc"] = torch.empty((V, 2 * D), dtype=torch.float32, device=dev)
@@ -147,13 +156,30 @@ def fuse(desc_s, desc_t, score_s, score_t, video_offsets: torch.Tensor, *, svm_w
         res["score_pred"] = torch.empty((V,), dtype=torch.int32, device=dev)
     if svm_w is not None and "svm_scores" not in res:
         assert svm_w.dtype == torch.float64 and svm_b.dtype == torch.float64
-        res["svm_scores"] = torch.empty((V, Cn), dtype=torch.float64, device=dev)
+        res["svm_scores"] = torch.empty((V, Csvm), dtype=torch.float64, device=dev)
         res["svm_pred"] = torch.empty((V,), dtype=torch.int32, device=dev)
-    check(_lib.load().va_fuse(ptr(desc_s), ptr(desc_t), ptr(score_s), ptr(score_t), ptr(video_offsets), V, D, Cn,
+    if svm_w is not None and res.get("svm_scores") is not None and tuple(res["svm_scores"].shape[1:]) != (Csvm,):
+        raise VAError(f"ops.fuse: svm_scores buffer {tuple(res['svm_scores'].shape)} does not have {Csvm} SVM classes")
+    check(_lib.load().va_fuse(ptr(desc_s), ptr(desc_t), ptr(score_s), ptr(score_t), ptr(video_offsets), V, D, Cn, Csvm,
                               ptr(svm_w), ptr(svm_b), float(w_s), float(w_t), ptr(res.get("video_desc")),
                               ptr(res.get("video_scores")), ptr(res.get("score_pred")), ptr(res.get("svm_scores")),
                               ptr(res.get("svm_pred")), stream_ptr()), "va_fuse")
     return res
+
+
+def svm_decision(X: torch.Tensor, W: torch.Tensor, b: torch.Tensor):
+    """LinearSVC decision function + predict on fp64 rows: X [V,F] f64, W [P,F] f64, b [P] f64 -> (scores [V,P] f64,
+    pred [V] i32 = first maximum)."""
+    _need_cuda(X, W, b)
+    assert X.dtype == torch.float64 and W.dtype == torch.float64 and b.dtype == torch.float64
+    V, F = X.shape
+    P = W.shape[0]
+    if W.shape[1] != F or b.numel() != P:
+        raise VAError(f"svm_decision: X {tuple(X.shape)}, W {tuple(W.shape)}, b {tuple(b.shape)} do not match")
+    scores = torch.empty((V, P), dtype=torch.float64, device=X.device)
+    pred = torch.empty((V,), dtype=torch.int32, device=X.device)
+    check(_lib.load().va_svm_decision(ptr(X), V, F, ptr(W), ptr(b), P, ptr(scores), ptr(pred), stream_ptr()), "va_svm_decision")
+    return scores, pred
 
 
 def synth_fill(images: torch.Tensor, image_shape: Sequence[int], n_images: int, *, seed: int, first_id: int = 0,

@@ -2,11 +2,12 @@
 (`SpatialDataset` :21-81, `SpatialNetwork` :85-283), driving the hand-written sm_100a path in libva_b200.so.
 
 Differences a reference user will notice:
-  * frames come from a device-resident `DeviceStore` (decoded images in HBM) instead of JPEG folders;
+  * the JPEG folders under `rootDir` are decoded ONCE, on the GPU, into a device-resident `DeviceStore` when the dataset
+    is constructed (`DeviceStore.from_directories`); a prebuilt store can be passed with `store=` instead;
   * `__getitem__` still returns the reference's fp32 [3,224,224] tensor (bit-exact), produced by the CUDA
     preprocess kernel; batched use goes through `utils.getDataLoader`, which yields NHWC bf16 batches;
   * the forward pass inlined in the reference's train()/validate() is the explicit method `forward(ip)`;
-  * `train()` (backward/SGD) is not built and raises -- no silent fallback.
+  * `train()` runs the K5 kernels (training.py): no torch autograd, no cuDNN.
 """
 from __future__ import annotations
 
@@ -55,8 +56,13 @@ class SpatialDataset(torch.utils.data.Dataset):
             raise ValueError("Action label dictionary required!")          # reference :45-46
         self.actionLabelDict = _read_action_labels(actionLabelLoc)
         if store is None:
-            raise VAError("SpatialDataset needs a device-resident frame store (video_analytics_b200.store.DeviceStore); "
-                          "decoding JPEG folders on the GPU is not built (SURVEY.md 8f row 2)")
+            # the reference's own call: SpatialDataset(videoListLoc, rootDir, transforms, actionLabelLoc=...) (:286-298).
+            # Walk rootDir/<Category>/<video>/<i>.jpg like __getitem__ :72-77 does and decode every frame on the GPU.
+            if self.rootDir is None:
+                raise VAError("SpatialDataset needs rootDir (a tree of JPEG frame folders) or a prebuilt store=DeviceStore")
+            from .store import DeviceStore
+            store = DeviceStore.from_directories(self.videoList, mode, frames_root=self.rootDir,
+                                                 label_of=lambda cat: self.actionLabelDict[cat])
         self.store = store
         self._meta = {m.name: m for m in store.layout.videos}
         self.last_indices = None
@@ -237,7 +243,13 @@ class _StreamNetwork(object):
             if precision > self.highestPrecision:
                 self.highestPrecision = precision
                 self.isBest = True
-            self.scheduler.step()
+            # reference :278 `self.scheduler.step(loss)`: the summed validation loss is passed where MultiStepLR expects
+            # the epoch index, so the learning rate is lr * 0.1 ** bisect_right(milestones, loss) -- a function of the
+            # loss VALUE.  Reproduced as written; torch's closed form gives the same number.
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.scheduler.step(float(loss))
             self.save()
             savePerformance(precision, float(loss), self._perf_loc)
             saveVideoDescriptors(self.trainDict, self._train_csv, self.gpu)

@@ -124,6 +124,77 @@ class DeviceStore:
         return self
 
     @classmethod
+    def from_directories(cls, video_lines, mode: str, frames_root=None, flow_root=None, label_of=None, device=None):
+        """Build the store from the reference's ON-DISK TREE, the way its datasets walk it:
+        `<frames_root>/<Category>/<video>/<i>.jpg`, i = 0..n-1 with n = len(os.listdir(dir)) (spatialModel.py:72-77; the
+        files convertVideosToFrames writes, utils.py:95-121) and `<flow_root>/<Category>/<video>/flow_x_%04d.jpg` /
+        `flow_y_%04d.jpg`, 1..len(os.listdir(dir))/2 (temporalModel.py:76-81, parameters.py:38-39).  `video_lines` are the
+        lines of demoTrain.txt / demoTest.txt; either root may be None (that stream's store stays empty).  All JPEGs are
+        decoded ONCE on the GPU (va_jpeg_decode; pixels = Pillow's) into HBM; every frame of a tree must have the same
+        size (UCF101: 320x240 frames, 340x256 flow images) -- a mixed tree raises ValueError.
+        `label_of(category) -> int` supplies labels for test-mode lines (the reference's actionLabelDict)."""
+        import os
+
+        import torch
+
+        from . import jpeg
+        from .utils import videoInfo
+
+        self = cls.__new__(cls)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lay = StoreLayout(videos=[], seed=0)
+        rgb_files, flow_files, seen = [], [], set()
+        for line in video_lines:
+            if not line.strip():
+                continue
+            _, name, label, category, _, _ = videoInfo(line, mode)
+            if name in seen:
+                continue
+            seen.add(name)
+            if label is None:
+                label = label_of(category) if label_of is not None else 0
+            n_frames = n_flows = 0
+            rgb_first, fx_first = len(rgb_files), len(flow_files)
+            if frames_root is not None:
+                d = os.path.join(frames_root, category, name)
+                n_frames = len(os.listdir(d))                                     # reference spatialModel.py:74
+                for i in range(n_frames):
+                    with open(os.path.join(d, "%d.jpg" % i), "rb") as f:
+                        rgb_files.append(f.read())
+            if flow_root is not None:
+                d = os.path.join(flow_root, category, name)
+                n_flows = len(os.listdir(d)) // 2                                 # reference temporalModel.py:78
+                for prefix in ("flow_x_", "flow_y_"):
+                    for i in range(1, n_flows + 1):
+                        with open(os.path.join(d, "%s%04d.jpg" % (prefix, i)), "rb") as f:
+                            flow_files.append(f.read())
+            lay.videos.append(VideoMeta(name, category, int(label), n_frames, rgb_first, n_flows, fx_first, fx_first + n_flows))
+        lay.n_rgb_images, lay.n_flow_images = len(rgb_files), len(flow_files)
+        self.layout = lay
+        self.rgb = torch.empty(1, dtype=torch.uint8, device=dev)
+        self.flow = torch.empty(1, dtype=torch.uint8, device=dev)
+        for files, attr, comps in ((rgb_files, "rgb", 3), (flow_files, "flow", 1)):
+            if not files:
+                continue
+            fs = jpeg.JpegFileSet(files)
+            h, w, c = (int(v) for v in fs.sizes[0])
+            if c != comps:
+                raise ValueError("%s tree: expected %d-component JPEGs, file 0 has %d" % (attr, comps, c))
+            bad = [k for k, sz in enumerate(fs.sizes) if tuple(int(v) for v in sz) != (h, w, c)]
+            if bad:
+                raise ValueError("%s tree: image %d is %r, image 0 is %r (one size per tree)" % (attr, bad[0], tuple(fs.sizes[bad[0]]), (h, w, c)))
+            nb = h * w * c
+            buf = torch.empty(len(files) * nb, dtype=torch.uint8, device=dev)
+            fs.decode_into(buf, [k * nb for k in range(len(files))])
+            setattr(self, attr, buf)
+            if attr == "rgb":
+                lay.rgb_shape = (h, w, c)
+            else:
+                lay.flow_shape = (h, w, c)
+        torch.cuda.current_stream().synchronize()
+        return self
+
+    @classmethod
     def from_host(cls, layout: StoreLayout, rgb_u8, flow_u8, device=None):
         """Upload host-decoded frames (numpy u8) instead of generating them."""
         import torch

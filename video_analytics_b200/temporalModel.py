@@ -37,7 +37,13 @@ class TemporalDataset(torch.utils.data.Dataset):
             raise ValueError("Action label dictionary required!")          # reference :47-48
         self.actionLabelDict = _read_action_labels(actionLabelLoc)
         if store is None:
-            raise VAError("TemporalDataset needs a device-resident flow store (video_analytics_b200.store.DeviceStore)")
+            # the reference's own call (:315-324): walk rootDir/<Category>/<video>/flow_{x,y}_%04d.jpg (:76-81) and decode
+            # every flow image on the GPU, once
+            if self.rootDir is None:
+                raise VAError("TemporalDataset needs rootDir (a tree of flow-image folders) or a prebuilt store=DeviceStore")
+            from .store import DeviceStore
+            store = DeviceStore.from_directories(self.videoList, mode, flow_root=self.rootDir,
+                                                 label_of=lambda cat: self.actionLabelDict[cat])
         self.store = store
         self._meta = {m.name: m for m in store.layout.videos}
         # The reference applies its random transform to each of the 2L images separately (:86), so every channel

@@ -163,7 +163,11 @@ def test_frame_indices(nFrames: int, n: int = _P.N_TEST_SNIPPETS) -> List[int]:
 
 
 def test_flow_starts(nFlows: int, L: int = VIDEO_INPUT_FLOW_COUNT, n: int = _P.N_TEST_SNIPPETS) -> List[int]:
-    """25 equally spaced stack starts in the reference's range [1, nFlows-L] (temporalModel.py:79)."""
+    """25 equally spaced stack starts in the reference's range [1, nFlows-L] (temporalModel.py:79).  A video with fewer
+    than L+1 flow pairs has no valid start: the reference's `random.randint(1, nFlows - L)` raises ValueError there, and a
+    start < 1 would address an image before the video's first flow image in the store."""
+    if nFlows - L < 1:
+        raise ValueError("video has %d flow pairs; a stack of %d needs at least %d" % (nFlows, L, L + 1))
     return [1 + (k * (nFlows - L - 1)) // (n - 1) for k in range(n)]
 
 
