@@ -68,3 +68,39 @@ def test_bench_reference_arm_contract_under_torchrun():
             assert key in d, key
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
         assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def _sampler_worker(rank, world, port, n_items, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from video_analytics_b200.utils import RankShardSampler
+    torch.manual_seed(100 + rank)                      # ranks are seeded DIFFERENTLY (own crops / dropout masks)
+    s = RankShardSampler(n_items, True, rank, world)
+    epochs = [list(iter(s)) for _ in range(2)]
+    plain = list(iter(RankShardSampler(n_items, False, rank, world)))
+    q.put((rank, epochs, plain, len(s)))
+    dist.destroy_process_group()
+
+
+def test_rank_shard_sampler_partitions_every_epoch():
+    """Data-parallel loaders (utils.getDataLoader under a process group): the ranks' index lists partition each epoch's
+    permutation -- no repeated batches across ranks, even with different per-rank seeds -- and have equal lengths."""
+    world, n_items = 2, 11
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, world, port, n_items, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, e0, p0, l0), (_, e1, p1, l1) = results
+    assert l0 == l1 == 6
+    for a, b in zip(e0, e1):
+        assert len(a) == len(b) == 6
+        assert sorted(set(a + b)) == list(range(n_items))          # union covers the data set (one wrapped duplicate)
+        assert len(set(a) & set(b)) <= 1
+    assert e0[0] != e0[1] or e1[0] != e1[1]                          # a new permutation per epoch
+    assert p0 == [0, 2, 4, 6, 8, 10] and p1 == [1, 3, 5, 7, 9, 0]

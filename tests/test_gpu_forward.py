@@ -267,3 +267,99 @@ def test_result_independent_of_chunk_size():
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert torch.equal(a, b)
+
+
+def margin_histogram(scores: torch.Tensor):
+    """Counts of the reference's top1-top2 margin per decade (the statistic SURVEY.md section 7 asks to report next to
+    top-1 agreement: under random init the margins are tiny, so flips are a property of the data, not of the kernels)."""
+    srt = scores.sort(dim=1, descending=True).values
+    m = (srt[:, 0] - srt[:, 1]).double()
+    edges = [0.0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1.0]
+    return {f"[{edges[i]:g},{edges[i + 1]:g})": int(((m >= edges[i]) & (m < edges[i + 1])).sum()) for i in range(len(edges) - 1)}
+
+
+def test_whole_video_configs2_vs_oracle_full_size(nets, world):
+    """BASELINE configs[2] at FULL size: every one of the 250 + 250 snippets of one video through TwoStreamEvaluator
+    (fused front end off and on) against the CPU oracle run on the same 500 snippets (~25 s of CPU forwards)."""
+    from oracle import two_stream as ts
+    from video_analytics_b200.combinedModel import CombinedModel
+    from video_analytics_b200.evaluate import TwoStreamEvaluator
+    ms, mt, ns, nt = nets
+    lay, store, ost = world
+    m = lay.videos[0]
+    snips_s, _ = ts.video_snippets_spatial(ost, m.name)
+    snips_t, _ = ts.video_snippets_temporal(ost, m.name)
+    ods, oss, fv_s, lg_s = ts.video_consensus(ms, snips_s)
+    odt, ost_, fv_t, lg_t = ts.video_consensus(mt, snips_t)
+    ofused = ts.fuse_scores(oss, ost_)
+    dref = torch.cat([ods, odt])
+    ev = TwoStreamEvaluator(ns, nt, store, CombinedModel())
+    for fused_front in (False, True):
+        ev.fused_front_end = fused_front
+        res = ev.run_videos([0])
+        torch.cuda.synchronize()
+        got_sc, got_d = res["video_scores"][0].cpu(), res["video_desc"][0].cpu()
+        rel = float(((got_sc - ofused).abs() / ofused).max())
+        derr = float((got_d - dref).abs().max() / dref.abs().max())
+        srt = ofused.sort(descending=True).values
+        margin, err = float(srt[0] - srt[1]), float((got_sc - ofused).abs().max())
+        agree = int(res["score_pred"][0]) == int(ofused.argmax())
+        print(f"[configs2 full video, fused_front_end={fused_front}] fused-score rel err {rel:.3e}, descriptor err {derr:.3e}, "
+              f"video top-1 {'agrees' if agree else 'differs'} (oracle margin {margin:.3e}, our abs err {err:.3e})")
+        assert rel < SCORE_RTOL, rel
+        assert derr < DESC_RTOL, derr
+        if margin > 2 * err:
+            assert agree
+    # per-snippet statistics over all 500 forwards (reported; asserted margin-aware)
+    from video_analytics_b200 import ops
+    from video_analytics_b200.evaluate import spatial_table, temporal_table
+    for name, net, tab, images, shape, mean, std, lg in (
+            ("spatial", ns, spatial_table(m, lay.rgb_shape), store.rgb, lay.rgb_shape, ev.mean_s, ev.std_s, lg_s),
+            ("temporal", nt, temporal_table(m, lay.flow_shape), store.flow, lay.flow_shape, ev.mean_t, ev.std_t, lg_t)):
+        x = ops.preprocess(images, shape, torch.from_numpy(tab).cuda(), mean, std, c_pad=net.c_pad)
+        _, logits, probs, pred = net.forward(x)
+        p_ref = torch.softmax(lg, 1)
+        perr = float(((probs.cpu() - p_ref).abs() / p_ref).max())
+        lerr = float((logits.cpu() - lg).abs().max())
+        agree, decidable = _margin_aware_agree(pred, lg, lerr)
+        print(f"[configs2 {name}: 250 snippets] class-score rel err {perr:.3e}; top-1 agreement {float(agree.float().mean()):.3f} "
+              f"({int(decidable.sum())} decidable, all agree: {bool(agree[decidable].all())}); oracle logit margins {margin_histogram(lg)}")
+        assert perr < SCORE_RTOL, perr
+        assert bool(agree[decidable].all())
+
+
+def test_temporal_batch64_configs1_vs_oracle(world):
+    """BASELINE configs[1]: one temporal batch of 64 stacks (20 x 224 x 224) in ONE chunk, bf16, against the oracle."""
+    from oracle import two_stream as ts
+    from video_analytics_b200 import ops
+    from video_analytics_b200.evaluate import temporal_table
+    lay, store, ost = world
+    model = ts.build_temporal_model(seed=0)
+    net = ops.StreamNet(ops.STREAM_TEMPORAL, 20, max_batch=64)
+    net.load_state_dict(model.state_dict())
+    sel = list(range(0, 250, 4))[:32]
+    tabs, snips = [], []
+    for v in (0, 1):                                             # 32 stacks of each of the two store videos
+        m = lay.videos[v]
+        tabs.append(temporal_table(m, lay.flow_shape)[sel])
+        snips.append(ts.video_snippets_temporal(ost, m.name)[0][sel])
+    table = torch.from_numpy(np.concatenate(tabs)).cuda()
+    snips = torch.cat(snips)
+    assert table.shape[0] == 64
+    fv, lg, opred = ts.forward_eval(model, snips)
+    p_ref = torch.softmax(lg, 1)
+    x = ops.preprocess(store.flow, lay.flow_shape, table, [0.485] * 20, [0.229] * 20, c_pad=net.c_pad)
+    for how in ("k1+forward", "fused front end"):
+        if how == "k1+forward":
+            desc, logits, probs, pred = net.forward(x)
+        else:
+            desc, logits, probs, pred = net.forward_store(store.flow, lay.flow_shape, table, [0.485] * 20, [0.229] * 20)
+        perr = float(((probs.cpu() - p_ref).abs() / p_ref).max())
+        derr = float((desc.cpu() - fv).abs().max() / fv.abs().max())
+        lerr = float((logits.cpu() - lg).abs().max())
+        agree, decidable = _margin_aware_agree(pred, lg, lerr)
+        print(f"[configs1 temporal B=64, {how}] class-score rel err {perr:.3e}, descriptor err {derr:.3e}; top-1 agreement "
+              f"{float(agree.float().mean()):.3f} ({int(decidable.sum())} decidable); oracle logit margins {margin_histogram(lg)}")
+        assert perr < SCORE_RTOL and derr < DESC_RTOL, (perr, derr)
+        assert bool(agree[decidable].all())
+    net.close()

@@ -204,8 +204,16 @@ class _StreamNetwork(object):
             loss += self.criterion(op, labelVar)                            # scalar bookkeeping on the logits
             correct += int((pred.to(torch.int64) == labelVar).sum().item())
             self.testDict.update_batch(videoNames, labels, featureVectors)
-        print("Validation for epoch %d: total = %d, correct = %d, loss = %f" % (self.epoch, self.totalTest, correct, float(loss)))
-        return (correct / self.totalTest), loss
+        total = self.totalTest
+        world, _ = self._world_rank()
+        if world > 1:
+            # each rank validated its shard of the test list (utils.RankShardSampler): sum the counts and the losses
+            acc = torch.tensor([float(correct), float(loss)], dtype=torch.float64, device="cuda")
+            torch.distributed.all_reduce(acc)
+            correct, loss = int(acc[0].item()), acc[1].to(torch.float32)
+            total = world * ((self.totalTest + world - 1) // world)       # shards are padded to equal length
+        print("Validation for epoch %d: total = %d, correct = %d, loss = %f" % (self.epoch, total, correct, float(loss)))
+        return (correct / total), loss
 
     def resume(self):
         """reference :234-249."""
@@ -226,8 +234,17 @@ class _StreamNetwork(object):
         print("Loaded checkpoint: starting from epoch: %d" % (self.startEpoch))
         return True
 
+    @staticmethod
+    def _world_rank():
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(), torch.distributed.get_rank()
+        return 1, 0
+
     def save(self):
-        """reference :252-262 -- same checkpoint dict, same file names."""
+        """reference :252-262 -- same checkpoint dict, same file names.  One process per GPU: replicas are identical
+        (StreamTrainer.sync_replicas + all-reduced gradients), rank 0 alone writes."""
+        if self._world_rank()[1] != 0:
+            return
         makeCheckpoint({"epoch": self.epoch, "model": self.model.state_dict(), "highestPrecision": self.highestPrecision,
                         "optimizer": self.optimizer.state_dict()}, self.isBest, self.ckpLoc + self._ckp_file,
                        self.ckpLoc + self._best_file)
@@ -251,9 +268,26 @@ class _StreamNetwork(object):
                 warnings.simplefilter("ignore")
                 self.scheduler.step(float(loss))
             self.save()
-            savePerformance(precision, float(loss), self._perf_loc)
-            saveVideoDescriptors(self.trainDict, self._train_csv, self.gpu)
-            saveVideoDescriptors(self.testDict, self._test_csv, self.gpu)
+            world, rank = self._world_rank()
+            if world == 1:
+                savePerformance(precision, float(loss), self._perf_loc)
+                saveVideoDescriptors(self.trainDict, self._train_csv, self.gpu)
+                saveVideoDescriptors(self.testDict, self._test_csv, self.gpu)
+            else:
+                # every rank holds the descriptors of ITS shard of the videos: each writes a part file, rank 0 joins them
+                # into the reference's CSVs (one writer per file: no write race)
+                for d, path in ((self.trainDict, self._train_csv), (self.testDict, self._test_csv)):
+                    saveVideoDescriptors(d, path + ".rank%d" % rank, self.gpu)
+                torch.distributed.barrier()
+                if rank == 0:
+                    savePerformance(precision, float(loss), self._perf_loc)
+                    for path in (self._train_csv, self._test_csv):
+                        with open(path, "w") as out:
+                            for r in range(world):
+                                with open(path + ".rank%d" % r) as part:
+                                    out.write(part.read())
+                                os.remove(path + ".rank%d" % r)
+                torch.distributed.barrier()
 
 
 def swap_classifier(model, descriptorDim, nActionClasses):

@@ -76,6 +76,25 @@ class StreamTrainer:
             self.bufs.append(self.flat_buf[off:off + p.numel()].view(p.shape))
         self.steps_done = 0
         self._adopt_optimizer_state()
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Data-parallel replicas must start from the SAME parameters and momentum: the torch module each rank built is
+        initialised from its own RNG (and a resumed checkpoint may exist on one rank only), and nothing downstream would
+        notice a divergence -- the all-reduce only averages gradients.  Rank 0's arenas are broadcast, as
+        nn.DataParallel's replicate() (reference spatialModel.py:133) would copy them from device 0."""
+        if self.group is None:
+            return
+        import torch.distributed as dist
+        if dist.get_world_size(self.group) < 2:
+            return
+        flag = torch.tensor([self.steps_done], device=self.flat_param.device)
+        dist.broadcast(flag, src=0, group=self.group)
+        dist.broadcast(self.flat_param, src=0, group=self.group)
+        dist.broadcast(self.flat_buf, src=0, group=self.group)
+        if int(flag.item()) and self.steps_done == 0:
+            self._publish_optimizer_state()          # rank 0 resumed with momentum buffers: adopt them here too
+        self.steps_done = int(flag.item())
 
     # ---- optimizer state <-> arena (checkpoint compatibility, reference :240-246,255-260)
     def _adopt_optimizer_state(self):
@@ -135,6 +154,13 @@ class StreamTrainer:
         desc_dim = W[30].shape[0]
         if masks is None:
             masks = self.draw_masks(n, desc_dim)
+        if not labels.is_cuda:
+            # validated while still on the host (no device sync): torch's CrossEntropyLoss raises "Target out of bounds";
+            # the kernel itself answers an out-of-range label with a NaN loss instead of reading past its buffers
+            n_classes = W[32].shape[0]
+            if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= n_classes):
+                raise VAError(f"labels must lie in [0, {n_classes}): got [{int(labels.min())}, {int(labels.max())}] "
+                              "(the reference's class ids are 1-based and are used as-is, spatialModel.py:178)")
         labels = labels.to(device=x_nhwc.device, dtype=torch.int64).contiguous()
 
         # ---------------- forward (train mode), activations kept

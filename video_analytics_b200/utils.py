@@ -207,9 +207,54 @@ def getDataLoader(dataset, batchSize=TEMPORAL_BATCH_SIZE, nWorkers=NWORKERS_LOAD
         table = torch.from_numpy(rows).pin_memory().cuda(non_blocking=True)
         return SnippetBatch(dataset.preprocess_table(table), table), labels, names
 
-    loader = DataLoader(dataset=_IndexView(), batch_size=batchSize, shuffle=shuffle, num_workers=0, collate_fn=_collate)
+    world, rank = _dist_world_rank()
+    if world > 1:
+        # one process per GPU: every rank walks its own 1/world of each epoch's permutation (the reference is
+        # single-process; its DataParallel wrapper would split each batch across devices, spatialModel.py:133)
+        sampler = RankShardSampler(len(dataset), shuffle, rank, world)
+        loader = DataLoader(dataset=_IndexView(), batch_size=batchSize, sampler=sampler, num_workers=0, collate_fn=_collate)
+    else:
+        loader = DataLoader(dataset=_IndexView(), batch_size=batchSize, shuffle=shuffle, num_workers=0, collate_fn=_collate)
     loader.snippet_dataset = dataset
     return loader
+
+
+def _dist_world_rank():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+class RankShardSampler(torch.utils.data.Sampler):
+    """Rank r of R takes positions r, r+R, r+2R, ... of the epoch's permutation (padded by wrapping so every rank sees
+    the same number of batches: the gradient all-reduce is a collective).  The permutation is drawn by rank 0 from the
+    global torch RNG -- one draw per epoch, like torch's RandomSampler -- and broadcast, so ranks seeded differently
+    (different crops and dropout masks, as they should be) still partition the data instead of repeating it."""
+
+    def __init__(self, n_items: int, shuffle: bool, rank: int, world: int):
+        self.n, self.shuffle, self.rank, self.world = n_items, bool(shuffle), rank, world
+        self.per_rank = (n_items + world - 1) // world
+
+    def __len__(self):
+        return self.per_rank
+
+    def __iter__(self):
+        import torch.distributed as dist
+        if self.shuffle:
+            perm = torch.randperm(self.n) if self.rank == 0 else torch.empty(self.n, dtype=torch.int64)
+            if dist.get_backend() == "nccl":
+                dev_perm = perm.cuda()
+                dist.broadcast(dev_perm, src=0)
+                perm = dev_perm.cpu()
+            else:
+                dist.broadcast(perm, src=0)
+        else:
+            perm = torch.arange(self.n)
+        total = self.per_rank * self.world
+        if total > self.n:
+            perm = torch.cat([perm, perm[:total - self.n]])
+        return iter(perm[self.rank:total:self.world].tolist())
 
 
 # ------------------------------------------------------------------------------------------------ consensus
