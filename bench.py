@@ -118,7 +118,7 @@ def cpu_reference_pass(n_spatial, n_temporal, batch=10, threads=None):
     img_recs = [(f, c) for f in ts.test_frame_indices(st.n_frame_files(name)) for c in ts.ten_crop_params(*synth.RGB_SHAPE[:2])]
     xs = torch.stack([ts.apply_transform(st.frame(name, f), i, j, fl, ts.NORM_MEANS_TF, ts.NORM_STDS_TF)
                       for (f, (i, j, fl)) in img_recs[:n_spatial]])
-    ds, ss, _, _ = ts.video_consensus(state["ms"], xs, batch=batch)
+    ds, ss, _, lg_s = ts.video_consensus(state["ms"], xs, batch=batch)
     mean, std = ts.flow_norm_constants(1)
     stk = [(s, c) for s in ts.test_flow_starts(st.n_flow_files(name) // 2) for c in ts.ten_crop_params(*synth.FLOW_SHAPE[:2])]
     xt = []
@@ -128,7 +128,8 @@ def cpu_reference_pass(n_spatial, n_temporal, batch=10, threads=None):
             planes.append(ts.apply_transform(st.flow_x(name, idx), i, j, fl, mean, std))
             planes.append(ts.apply_transform(st.flow_y(name, idx), i, j, fl, mean, std))
         xt.append(torch.cat(planes, 0))
-    dt_, st_, _, _ = ts.video_consensus(state["mt"], torch.stack(xt), batch=batch)
+    dt_, st_, _, lg_t = ts.video_consensus(state["mt"], torch.stack(xt), batch=batch)
+    state["last_logits"] = (lg_s, lg_t)        # per-snippet logits of this pass: the parity leg's oracle sample
     fused = ts.fuse_scores(ss, st_)
     _ = torch.cat([ds, dt_]), int(fused.argmax())
     return time.perf_counter() - t0, torch.get_num_threads()
@@ -270,6 +271,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256,
                     help="--workload train: snippets per stream per GPU per step (BASELINE configs[4]: 256)")
     ap.add_argument("--lr", type=float, default=0.001, help="--workload train: SGD learning rate")
+    ap.add_argument("--no-legs", dest="legs", action="store_false",
+                    help="skip the extra legs of the line (configs0_b1, configs1_b64, parity, strong_3783, train)")
+    ap.add_argument("--strong-videos", type=int, default=3783, help="videos of the configs[3] strong-scaling leg")
     args = ap.parse_args()
     if args.workload == "train":
         import bench_train
@@ -588,6 +592,43 @@ def main():
         del fd, fs, fout, fout2
         jpeg_line = jpeg_decode_measurement(store, layout, dev)
 
+    # ---- the reference's CPU path beside it (rank 0, N = 1): the oracle port on the box's host cores, bounded sample
+    cpu_line, oracle_logits = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = args.ref_snippets
+        cpu_reference_pass(n, n)                                   # warm-up
+        t, reps, cores = 0.0, 0, 0
+        while t < 12.0 and reps < 6:
+            dt, cores = cpu_reference_pass(n, n)
+            t += dt
+            reps += 1
+        cpu_line = {"value": reps * n / t, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{reps} x ({n} spatial + {n} temporal protocol snippets, batch 10) of one synthetic video: "
+                              "CPU preprocess + VGG16 fp32 forward + consensus + fusion (oracle/two_stream.py)"}
+        oracle_logits = cpu_reference_pass.__dict__["state"].get("last_logits")
+
+    # ---- the other BASELINE configs, in the same line (bench_legs.py): collective legs run on every rank
+    legs = {}
+    if args.legs:
+        import bench_legs
+        sd_s, sd_t = build_spatial_torch_model(C, D, seed=0).state_dict(), build_temporal_torch_model(C, 10, D, seed=0).state_dict()
+        for key, fn in (
+                ("small", (lambda: bench_legs.small_batch_legs(spatial, temporal, ev, store, layout)) if world == 1 else None),
+                ("parity", (lambda: bench_legs.parity_leg(spatial, temporal, ev, store, layout, sd_s, sd_t,
+                                                          oracle_logits=oracle_logits)) if world == 1 else None),
+                ("strong_3783", lambda: bench_legs.strong_leg(ev, lambda rows: ev.alloc_outputs(rows, D, C, with_svm=True), rank, world,
+                                                              dev, n_videos=args.strong_videos, vps=vps)),
+                ("train", lambda: bench_legs.train_leg(args))):
+            if fn is None:
+                continue
+            try:
+                legs[key] = fn()
+            except Exception as e:                 # a failing leg must not take the contract line down with it
+                if world > 1:
+                    raise                           # ...except under torchrun, where a rank that skips a collective hangs the rest
+                legs[key] = {"unavailable": repr(e)[:300]}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         peaks = read_peaks()
         achieved = (t_f.value / 1e12) / (t_ms.value * 1e-3) if t_ms.value > 0 else 0.0
@@ -623,17 +664,17 @@ def main():
             "e2e_jpeg": e2e_jpeg,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            n = args.ref_snippets
-            cpu_reference_pass(n, n)                                   # warm-up
-            t, reps, cores = 0.0, 0, 0
-            while t < 12.0 and reps < 6:
-                dt, cores = cpu_reference_pass(n, n)
-                t += dt
-                reps += 1
-            line["cpu_baseline"] = {"value": reps * n / t, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{reps} x ({n} spatial + {n} temporal protocol snippets, batch 10) of one synthetic video: "
-                                              "CPU preprocess + VGG16 fp32 forward + consensus + fusion (oracle/two_stream.py)"}
+        if legs:
+            small = legs.get("small")
+            if isinstance(small, tuple):
+                line["configs0_b1"], line["configs1_b64"] = small
+            elif small is not None:
+                line["configs0_b1"] = line["configs1_b64"] = small
+            for key in ("parity", "strong_3783", "train"):
+                if legs.get(key) is not None:
+                    line[key] = legs[key]
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

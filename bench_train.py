@@ -80,7 +80,8 @@ def run_reference(args, rank):
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def main(args):
+def main(args, embedded=False):
+    """embedded=True (bench_legs.train_leg): return the line on rank 0 instead of printing it, keep the process group."""
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
@@ -337,6 +338,8 @@ def main(args):
             "roofline": roof,
             "clocks": clocks,
         }
+        if embedded:
+            return line
         if world == 1 and not args.no_cpu_baseline:
             n = args.ref_snippets
             cpu_train_pass(n)
@@ -349,5 +352,7 @@ def main(args):
                                     "sample": f"{reps} x one two-stream SGD step on {n} snippets per stream "
                                               "(oracle/two_stream.py train_step: torch CPU fp32 forward + backward + SGD)"}
         print(json.dumps(line))
+    if embedded:
+        return None
     if world > 1:
         dist.destroy_process_group()
