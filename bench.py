@@ -392,36 +392,27 @@ def main():
                 "svm_pred": torch.empty((vps,), dtype=torch.int32).pin_memory()}
     h2d = d2h = 0
 
-    def e2e_step(i, count=False):
-        nonlocal h2d, d2h
-        vids = my[i * vps:(i + 1) * vps]
-        tabs_s, tabs_t, nb = [], [], 0
-        for slot, v in enumerate(vids):
-            k = v % len(layout.videos)
-            m = layout.videos[k]
-            a, b = m.rgb_first * rgb_img, (m.rgb_first + m.n_frames) * rgb_img
-            stage.rgb[slot * max_fr * rgb_img: slot * max_fr * rgb_img + (b - a)].copy_(rgb_host[a:b], non_blocking=True)
-            a, b = m.flowx_first * flow_img, (m.flowx_first + 2 * m.n_flows) * flow_img
-            stage.flow[slot * 2 * max_fl * flow_img: slot * 2 * max_fl * flow_img + (b - a)].copy_(flow_host[a:b], non_blocking=True)
-            nb += m.n_frames * rgb_img + 2 * m.n_flows * flow_img
-            hs, ht = staged_tables(k, slot)
-            tabs_s.append(hs.to(dev, non_blocking=True)); tabs_t.append(ht.to(dev, non_blocking=True))
-            nb += hs.numel() * 4 + ht.numel() * 4
-        r = ev.run_tables(torch.cat(tabs_s), torch.cat(tabs_t), len(vids), store=stage)
-        nd = 0
-        for kname, hbuf in res_host.items():
-            hbuf[:len(vids)].copy_(r[kname], non_blocking=True)
-            nd += r[kname].numel() * r[kname].element_size()
-        torch.cuda.current_stream().synchronize()      # the step's result is on the host
-        if count:
-            h2d, d2h = nb, nd
+    # The evaluator's own host pipeline (TwoStreamEvaluator.host_pipeline): per group it copies the images the protocol
+    # touches (25 frames + 2 x 250 flow images per video) and the index tables from pinned host memory on a copy stream,
+    # double-buffered, so the H2D of step i+1 runs under the networks of step i; every step ends with its scores on the host.
+    from video_analytics_b200.evaluate import HostStore
+    host = HostStore(layout, rgb_host, flow_host)
 
-    for i in range(W):
-        e2e_step(i)
+    def e2e_run(first, last):
+        nonlocal h2d, d2h
+        groups = [my[i * vps:(i + 1) * vps] for i in range(first, last)]
+        for r in ev.host_pipeline(host, groups):
+            nd = 0
+            for kname, hbuf in res_host.items():
+                hbuf[:r[kname].shape[0]].copy_(r[kname], non_blocking=True)
+                nd += r[kname].numel() * r[kname].element_size()
+            torch.cuda.current_stream().synchronize()      # the step's result is on the host
+            h2d, d2h = ev.last_h2d_bytes, nd
+
+    e2e_run(0, W)
     barrier()
     t0 = time.perf_counter()
-    for i in range(W, W + K):
-        e2e_step(i, count=(i == W))
+    e2e_run(W, W + K)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

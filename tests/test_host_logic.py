@@ -187,7 +187,7 @@ def test_layout_is_deterministic_and_valid():
     a, b = make_layout(8), make_layout(8)
     assert a.videos == b.videos
     for m in a.videos:
-        assert m.n_frames >= 12 and m.n_flows >= 10 + 1 and 1 <= m.label <= 25
+        assert m.n_frames >= 25 and m.n_flows == 10 * m.n_frames and 1 <= m.label <= 25
         assert m.flowy_first == m.flowx_first + m.n_flows
     line = a.list_line(3, "train")
     assert U.videoInfo(line, "train")[1] == a.videos[3].name

@@ -82,6 +82,7 @@ struct va_handle {
   void* act[2];     // ping-pong activation workspace
   size_t act_bytes;
   float* desc_ws;   // [max_batch][desc_dim] when the caller does not want descriptors
+  float* splitk_ws; // [kSplitK][max_batch][4096] fp32 partial sums of the split-K fully-connected layers
 };
 
 extern "C" {
@@ -175,7 +176,8 @@ va_status va_create_ex(va_handle** out, int stream_kind, int in_channels, int n_
   if (cudaMalloc(&h->w4t, (size_t)desc_dim * n_classes * 4) != cudaSuccess ||
       cudaMalloc(&h->b4, n_classes * 4) != cudaSuccess || cudaMalloc(&h->act[0], h->act_bytes) != cudaSuccess ||
       cudaMalloc(&h->act[1], h->act_bytes) != cudaSuccess ||
-      cudaMalloc(&h->desc_ws, (size_t)max_batch * desc_dim * 4) != cudaSuccess) {
+      cudaMalloc(&h->desc_ws, (size_t)max_batch * desc_dim * 4) != cudaSuccess ||
+      (!precision && cudaMalloc(&h->splitk_ws, (size_t)va::kSplitK * max_batch * kFcHidden * 4) != cudaSuccess)) {
     va_destroy(h);
     return fail(VA_ERR_CUDA, "cudaMalloc workspace failed (max_batch %d needs 2 x %zu bytes)", max_batch, h->act_bytes);
   }
@@ -188,7 +190,7 @@ va_status va_destroy(va_handle* h) {
   for (int i = 0; i < 13; ++i) { cudaFree(h->wconv[i]); cudaFree(h->bconv[i]); }
   cudaFree(h->wconv1_fused);
   for (int i = 0; i < 3; ++i) { cudaFree(h->wfc[i]); cudaFree(h->bfc[i]); }
-  cudaFree(h->w4t); cudaFree(h->b4); cudaFree(h->act[0]); cudaFree(h->act[1]); cudaFree(h->desc_ws);
+  cudaFree(h->w4t); cudaFree(h->b4); cudaFree(h->act[0]); cudaFree(h->act[1]); cudaFree(h->desc_ws); cudaFree(h->splitk_ws);
   delete h;
   return VA_OK;
 }
@@ -294,6 +296,7 @@ va_status forward_impl(va_handle* h, const void* in_nhwc, const StoreInput* src,
       d.split6 = h->precision;
       d.w_packed = h->wfc[i]; d.bias = h->bfc[i]; d.Cout = fout[i]; d.ks = 1;
       d.relu = 1; d.pool = 0; d.force_bn = 0; d.force_r = 0;
+      d.splitk_ws = h->splitk_ws;
       d.y = (i < 2) ? h->act[cur] : nullptr;
       d.y_f32 = (i < 2) ? nullptr : desc_out;
       if (const char* e = va::conv_layer_run(d, st)) return fail(VA_ERR_CUDA, "fc layer %d: %s", i + 1, e);
@@ -389,6 +392,11 @@ va_status va_linear(const void* x, int n, int in_features, const float* w, const
   va::ConvLayerDesc d;
   d.x = x; d.n = n; d.H = 1; d.W = 1; d.cin_pad = in_features; d.w_packed = wp; d.bias = bias; d.Cout = out_features;
   d.ks = 1; d.relu = relu; d.pool = 0; d.y = y_bf16; d.y_f32 = y_f32; d.force_bn = force_bn; d.force_r = 0; d.split6 = 0;
+  void* ws = nullptr;
+  if (in_features / 64 >= 32 && (in_features / 64) % va::kSplitK == 0 && force_bn == 0) {
+    VA_CUDA(scratch.alloc(&ws, (size_t)va::kSplitK * n * out_features * 4));
+    d.splitk_ws = static_cast<float*>(ws);
+  }
   const char* e = va::conv_layer_run(d, st);
   if (e) return fail(VA_ERR_CUDA, "va_linear: %s", e);
   return VA_OK;

@@ -97,6 +97,28 @@ const char* launch_variant(const CUtensorMap& tA, const CUtensorMap& tW, const C
   return nullptr;
 }
 
+// Second pass of the split-K fully-connected layers: y[i][c] = act(sum_s part[s][i][c] + bias[c]), slices added in the fixed
+// order s = 0..S-1 (so the result does not depend on which CTA finished first, nor on the batch size).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ part, int S, long long n4, int cout4,
+                                                            const float4* __restrict__ bias, int relu,
+                                                            uint2* __restrict__ y_bf16, float4* __restrict__ y_f32) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = __ldg(part + i);
+    for (int s = 1; s < S; ++s) {
+      const float4 v = __ldg(part + (size_t)s * n4 + i);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    const float4 b = __ldg(bias + (int)(i % cout4));
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    if (y_f32) y_f32[i] = acc;
+    if (y_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+      y_bf16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
 }  // namespace
 
 static long long* g_dbg_counters = nullptr;
@@ -111,6 +133,10 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   if (d.Cout % 64 != 0) return errf("Cout %d must be a multiple of 64", d.Cout);
   if (d.pool && ((d.H | d.W) & 1)) return "fused 2x2 pool needs even H and W";
   if (d.y_f32 && (d.H != 1 || d.W != 1 || d.pool)) return "fp32 output only for fully-connected (H=W=1) layers";
+  // split-K for the fully-connected layers (weight-bandwidth bound: FC1 streams 205 MB through 16..64 CTAs otherwise).
+  // The slice count depends on K alone, never on the batch: the summation order is the same for every chunk size.
+  const bool splitk = d.splitk_ws != nullptr && d.H == 1 && d.W == 1 && d.ks == 1 && !d.split6 && CK == 64 &&
+                      (d.cin_pad / 64) >= 32 && (d.cin_pad / 64) % kSplitK == 0;
 
   ConvKernelParams p;
   p.n_img = d.n; p.H = d.H; p.W = d.W;
@@ -245,18 +271,21 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
 
   // CTA-pair kernel (cta_group::2, UMMA M=256) for the wide 3x3 layers: 6 x 32 KB stages instead of 4 x 48 KB.
   const bool pair = BN == 256 && CK == 64 && R == 1 && S == 1 && d.ks == 3 && !d.y_f32 && d.force_r != 1 && !d.split6 &&
-                    getenv("VA_CONV_NO_PAIR") == nullptr;
+                    true;
   p.n_tiles_cout = d.Cout / BN;
-  p.total_tiles = tiles_m * p.n_tiles_cout;
+  p.total_tiles = tiles_m * p.n_tiles_cout * (splitk ? kSplitK : 1);
+  p.ksplit = splitk ? kSplitK : 1;
+  p.kb_per_split = splitk ? (d.cin_pad / 64) / kSplitK : 0;
+  p.tiles_m = tiles_m;
   p.div_cout = FastDiv::make((uint32_t)p.n_tiles_cout);
   p.div_w = FastDiv::make((uint32_t)p.tiles_w);
   p.div_h = FastDiv::make((uint32_t)p.tiles_h);
   p.ks = d.ks; p.pad = (d.ks - 1) / 2;
   p.cin_chunks = d.cin_pad / CK;
-  p.pool = d.pool; p.relu = d.relu; p.out_f32 = d.y_f32 ? 1 : 0;
+  p.pool = d.pool; p.relu = d.relu; p.out_f32 = (d.y_f32 || splitk) ? 1 : 0;
   p.split6 = (d.split6 && !d.y_f32) ? 1 : 0;
   p.Cout = d.Cout;
-  p.bias = d.bias; p.out_f32_ptr = d.y_f32; p.dbg = g_dbg_counters;
+  p.bias = d.bias; p.out_f32_ptr = splitk ? d.splitk_ws : d.y_f32; p.dbg = g_dbg_counters;
   const int rowb = CK * 2;
   const int a_rows = p.n_t * (p.h_t + (R - 1)) * (halo ? p.hb_pitch : p.w_t);
   p.a_tx_bytes = (uint32_t)a_rows * rowb;
@@ -264,7 +293,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   p.staging_bytes = d.pool ? 4096u : 16384u;
   // Resident weights: the layer's whole weight set stays in smem (one Cout tile, one channel chunk, R=3 variants)
   const int groups = (d.ks * d.ks) / (R * S);
-  const bool wres = !d.split6 && R == 3 && p.n_tiles_cout == 1 && p.cin_chunks == 1 && BN == 64 && getenv("VA_CONV_NO_WRES") == nullptr &&
+  const bool wres = !d.split6 && R == 3 && p.n_tiles_cout == 1 && p.cin_chunks == 1 && BN == 64 && true &&
                     (size_t)groups * conv_b_stage_bytes(BN, CK, R, S) <= 80 * 1024;
   if (halo && !wres) return "HALO variant needs resident weights";
   const int a_boxes = halo ? 1 : S;
@@ -287,7 +316,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     const uint32_t box[3] = {(uint32_t)CK, (uint32_t)BN, (uint32_t)(R * S)};
     if (const char* e = encode_bf16(&tW, d.w_packed, 3, dims, box, rowb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
   }
-  if (!d.y_f32) {
+  if (!d.y_f32 && !splitk) {
     const int sh = d.pool ? 1 : 0;
     const uint64_t dims[4] = {(uint64_t)d.Cout * (d.split6 ? 6 : 1), (uint64_t)(d.W >> sh), (uint64_t)(d.H >> sh), (uint64_t)d.n};
     const uint32_t box[4] = {64u, (uint32_t)(p.w_t >> sh), (uint32_t)(p.h_t >> sh), (uint32_t)p.n_t};
@@ -329,6 +358,23 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     return errf("fp32-accuracy mode: no kernel for BN=%d CK=%d", BN, CK);
   }
   if (halo) return launch_variant<64, 64, 3, 3, true, false, true>(tA, tW, tO, p, grid, smem, st);
+  if (splitk) {
+    const char* e = nullptr;
+    if (BN == 256) e = launch_variant<256, 64, 1, 1, false>(tA, tW, tO, p, grid, smem, st);
+    else if (BN == 128) e = launch_variant<128, 64, 1, 1, false>(tA, tW, tO, p, grid, smem, st);
+    else e = launch_variant<64, 64, 1, 1, false>(tA, tW, tO, p, grid, smem, st);
+    if (e) return e;
+    const long long n4 = (long long)d.n * d.Cout / 4;
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)sms * 8);
+    count_launch();
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d.splitk_ws), kSplitK, n4, d.Cout / 4,
+                                                 reinterpret_cast<const float4*>(d.bias), d.relu,
+                                                 d.y_f32 ? nullptr : reinterpret_cast<uint2*>(d.y),
+                                                 d.y_f32 ? reinterpret_cast<float4*>(d.y_f32) : nullptr);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return errf("splitk_reduce_kernel launch: %s", cudaGetErrorString(ce));
+    return nullptr;
+  }
 #define VA_CASE(bn, ck, r, sv, wr) \
   if (BN == bn && CK == ck && R == r && S == sv && wres == wr) \
     return launch_variant<bn, ck, r, sv, wr>(tA, tW, tO, p, grid, smem, st);

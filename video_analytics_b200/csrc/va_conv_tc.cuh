@@ -77,7 +77,24 @@ struct ConvKernelParams {
   float* out_f32_ptr;              // [n_img, Cout] when out_f32 (fully-connected only)
   long long* dbg;                  // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
   int hb_pitch;                    // HALO variant: pixels per row of the haloed A box (w_t + 2)
+  int ksplit;                      // fully-connected split-K: number of K slices (1 = off); a tile index then decodes as
+  int kb_per_split;                //   ((slice * n_tiles_cout + nt) * tiles_m + mt) and covers kb_per_split K blocks
+  int tiles_m;                     // M tiles (split-K decode)
 };
+
+// tile index -> (K slice, M tile, N tile).  Without split-K the N tile is fastest (concurrent CTAs share the A patch in
+// L2); with split-K (fully-connected layers, weight-bandwidth bound) the M tile is fastest, so the CTAs that run at the
+// same time read the SAME weight block and HBM sees every weight byte once.
+__device__ __forceinline__ void decode_tile(const ConvKernelParams& p, uint32_t tile, uint32_t& ks_i, uint32_t& mt, uint32_t& nt) {
+  if (p.ksplit > 1) {
+    const uint32_t rest = tile / (uint32_t)p.tiles_m;
+    mt = tile - rest * (uint32_t)p.tiles_m;
+    p.div_cout.divmod(rest, ks_i, nt);
+  } else {
+    ks_i = 0;
+    p.div_cout.divmod(tile, mt, nt);
+  }
+}
 
 // wait on an mbarrier, charging the stalled cycles to *acc when diagnostics are on
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int tag, bool on, long long& acc) {
@@ -133,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int groups = (p.ks * p.ks) / (R * S);    // stages per channel chunk: 9 (per tap), 3 (per filter column) or 1
-  const int num_kb = groups * p.cin_chunks;      // pipeline stages consumed per tile
+  const int num_kb = p.ksplit > 1 ? p.kb_per_split : groups * p.cin_chunks;      // pipeline stages consumed per tile
   const uint32_t wres_bytes = WRES ? (uint32_t)groups * B_STAGE : 0u;   // resident weights sit in front of the ring
   const uint32_t a_stage_bytes = (HALO ? 1 : S) * p.a_box_bytes;
   const uint32_t stage_bytes = a_stage_bytes + (WRES ? 0u : B_STAGE);
@@ -191,16 +208,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      uint32_t nt, mt, tw, th, tn;
-      p.div_cout.divmod((uint32_t)tile, mt, nt);
+      uint32_t nt, mt, tw, th, tn, ksl;
+      decode_tile(p, (uint32_t)tile, ksl, mt, nt);
       p.div_w.divmod(mt, mt, tw);
       p.div_h.divmod(mt, tn, th);
       const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
+      const int cc_begin = p.ksplit > 1 ? (int)ksl * p.kb_per_split : 0;
+      const int cc_end = p.ksplit > 1 ? cc_begin + p.kb_per_split : p.cin_chunks;
       // taps are walked with counters.  R=1: g = s*ks + r; R=3: g = s; S=3: g = 0 covers the whole filter.
       int s = 0, r = 0;
       for (int g = 0; g < groups; ++g) {
         const int wx = w0 + s - p.pad, hy = h0 + r - p.pad;
-        for (int cc = 0; cc < p.cin_chunks; ++cc) {
+        for (int cc = cc_begin; cc < cc_end; ++cc) {
           mbar_wait_t(&empty_bar[stage], phase ^ 1, 100 + stage, dbg, t_wait);
           if (elect_one()) {
             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
@@ -307,8 +326,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       if (DRAIN ? (eg != 0) : ((it & 1) != eg)) continue;       // the other group's tile (DRAIN: group 0 does all)
       uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
-      uint32_t nt, mt, tw, th, tn;
-      p.div_cout.divmod((uint32_t)tile, mt, nt);
+      uint32_t nt, mt, tw, th, tn, ksl;
+      decode_tile(p, (uint32_t)tile, ksl, mt, nt);
       p.div_w.divmod(mt, mt, tw);
       p.div_h.divmod(mt, tn, th);
       const int n0 = tn * p.n_t, h0 = th * p.h_t, w0 = tw * p.w_t, c0 = nt * BN;
@@ -368,6 +387,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.out_f32) {
           // fully-connected tail (H=W=1, tile = 128 images): fp32 rows straight to global.
           const int img = n0 + m;
+          if (p.ksplit > 1) {
+            // split-K partial sums: raw fp32 accumulators of this K slice; bias / ReLU / rounding happen in the reduction
+            if (img < p.n_img) {
+              float* dst = p.out_f32_ptr + ((size_t)ksl * p.n_img + img) * p.Cout + c0 + chunk * 64;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1]),
+                                                                  __uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+                *reinterpret_cast<float4*>(dst + 32 + i) = make_float4(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1]),
+                                                                       __uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+              }
+            }
+            continue;
+          }
           if (img < p.n_img) {
             float* dst = p.out_f32_ptr + (size_t)img * p.Cout + c0 + chunk * 64;
 #pragma unroll

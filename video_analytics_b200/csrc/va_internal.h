@@ -78,7 +78,10 @@ struct ConvLayerDesc {
   float* y_f32;         // fp32 [n][Cout] (H=W=1 only)
   int force_bn, force_r;
   int split6;           // fp32-accuracy mode: y has 6*Cout channels (slice blocks), x/w_packed already carry 6x channels
+  float* splitk_ws = nullptr;   // fully-connected layers: fp32 [kSplitK][n][Cout] scratch; when given (and K is long
+                                // enough) the K loop is cut into kSplitK slices reduced in a fixed order by a second kernel
 };
+constexpr int kSplitK = 8;
 // Plans (tile shape, kernel variant, tensor maps) and launches one layer.  Returns nullptr on success or a
 // static/thread-local error string.
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st);

@@ -42,6 +42,51 @@ def temporal_table(meta: VideoMeta, flow_shape, L: int = VIDEO_INPUT_FLOW_COUNT)
     return np.asarray(rows, dtype=np.int32).reshape(-1, 2 * L, 4)
 
 
+class HostStore:
+    """The loader side of the end-to-end path: the pool videos' decoded u8 images in PINNED host memory (same flat
+    layout and image ids as the DeviceStore they mirror).  `TwoStreamEvaluator.host_pipeline` copies, per video, only the
+    images the 25 x 10 protocol reads -- the files the reference would `Image.open` (spatialModel.py:76, temporalModel.py:85)."""
+
+    def __init__(self, layout, rgb: torch.Tensor, flow: torch.Tensor):
+        self.layout = layout
+        self.rgb = rgb if rgb.is_pinned() else rgb.pin_memory()
+        self.flow = flow if flow.is_pinned() else flow.pin_memory()
+
+    @classmethod
+    def from_device(cls, store: DeviceStore):
+        return cls(store.layout, store.rgb.cpu(), store.flow.cpu())
+
+
+class _VideoPlan:
+    """What one pool video contributes to a staged group: source image runs to copy and index tables whose image ids are
+    LOCAL to the video's stage slot (frames 0..24, flow images 0..499)."""
+
+    def __init__(self, meta: VideoMeta, layout, L: int):
+        frames = sorted(set(test_frame_indices(meta.n_frames)))
+        f_local = {f: i for i, f in enumerate(frames)}
+        flows = sorted({s + d for s in test_flow_starts(meta.n_flows, L) for d in range(L)})         # 1-based flow indices
+        x_local = {idx: i for i, idx in enumerate(flows)}
+        nfl = len(flows)
+        self.n_rgb, self.n_flow = len(frames), 2 * nfl
+        self.rgb_src = [meta.rgb_first + f for f in frames]                                           # one copy per frame
+        runs, start = [], 0                                                                          # consecutive flow indices
+        for i in range(1, nfl + 1):
+            if i == nfl or flows[i] != flows[i - 1] + 1:
+                runs.append((flows[start], start, i - start))                                         # (first index, local, count)
+                start = i
+        self.flow_runs = [(meta.flowx_first + a - 1, loc, cnt) for a, loc, cnt in runs] + \
+                         [(meta.flowy_first + a - 1, nfl + loc, cnt) for a, loc, cnt in runs]
+        lm = VideoMeta(meta.name, meta.category, meta.label, meta.n_frames, 0, meta.n_flows, 0, 0)
+        ts = spatial_table(lm, layout.rgb_shape)
+        ts[:, :, 0] = np.vectorize(f_local.get)(ts[:, :, 0])
+        tt = temporal_table(VideoMeta(meta.name, meta.category, meta.label, meta.n_frames, 0, meta.n_flows, 1, 1 + 10 ** 6), layout.flow_shape, L)
+        ids = tt[:, :, 0]
+        is_y = ids >= 10 ** 6                                                                         # x ids = idx, y ids = 1e6 + idx
+        idx = np.where(is_y, ids - 10 ** 6, ids)
+        tt[:, :, 0] = np.vectorize(x_local.get)(idx) + np.where(is_y, nfl, 0)
+        self.ts, self.tt = ts.astype(np.int32), tt.astype(np.int32)
+
+
 class TwoStreamEvaluator:
     """Runs groups of videos through preprocess -> both streams -> consensus/fusion on the current device."""
 
@@ -87,6 +132,96 @@ class TwoStreamEvaluator:
         if out is not None:
             sub = {k: t[out_row:out_row + V] for k, t in out.items()}
         return self.combined.fuse(desc_s, desc_t, prob_s, prob_t, offs, out=sub)
+
+    # ---- end-to-end from host memory: double-buffered staging, H2D of group i+1 under the networks of group i
+    MAX_RGB_PER_VIDEO = N_TEST_SNIPPETS
+    MAX_FLOW_PER_VIDEO = 2 * N_TEST_SNIPPETS * VIDEO_INPUT_FLOW_COUNT
+
+    def host_pipeline(self, host: HostStore, groups: Sequence[Sequence[int]], depth: int = 2):
+        """Generator: evaluates each group of video ids from PINNED HOST images and yields its fusion result dict.
+        The images a group touches (25 frames + 2 x 250 flow images per video) and its index tables are copied into one
+        of `depth` device stage stores on a copy stream while the previous group's networks run; `self.last_h2d_bytes` is
+        the byte count of the most recent group's copies.  Results are stream-ordered on the CURRENT stream."""
+        lay = host.layout
+        dev = self.store.rgb.device
+        vmax = max((len(g) for g in groups), default=0)
+        if vmax == 0:
+            return
+        rgb_img = lay.rgb_shape[0] * lay.rgb_shape[1] * lay.rgb_shape[2]
+        flow_img = lay.flow_shape[0] * lay.flow_shape[1] * lay.flow_shape[2]
+        key = (vmax, depth, rgb_img, flow_img)
+        if getattr(self, "_stage_key", None) != key:
+            self._stages = []
+            for _ in range(depth):
+                st = DeviceStore.__new__(DeviceStore)
+                st.layout = lay
+                st.rgb = torch.empty(vmax * self.MAX_RGB_PER_VIDEO * rgb_img, dtype=torch.uint8, device=dev)
+                st.flow = torch.empty(vmax * self.MAX_FLOW_PER_VIDEO * flow_img, dtype=torch.uint8, device=dev)
+                self._stages.append(st)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copied = [torch.cuda.Event() for _ in range(depth)]
+            self._consumed = [torch.cuda.Event() for _ in range(depth)]
+            self._stage_key = key
+            self._plans, self._host_tables = {}, {}
+        cur = torch.cuda.current_stream()
+        for ev_ in self._consumed:
+            ev_.record(cur)
+        pending = {}
+
+        def plan_for(k):
+            if k not in self._plans:
+                self._plans[k] = _VideoPlan(lay.videos[k], lay, self.L)
+            return self._plans[k]
+
+        def tables_for_slot(k, pos):
+            if (k, pos) not in self._host_tables:
+                pl = plan_for(k)
+                ts, tt = pl.ts.copy(), pl.tt.copy()
+                ts[:, :, 0] += pos * self.MAX_RGB_PER_VIDEO
+                tt[:, :, 0] += pos * self.MAX_FLOW_PER_VIDEO
+                self._host_tables[(k, pos)] = (torch.from_numpy(ts).pin_memory(), torch.from_numpy(tt).pin_memory())
+            return self._host_tables[(k, pos)]
+
+        def issue(gi):
+            slot = gi % depth
+            st = self._stages[slot]
+            nb = 0
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._consumed[slot])
+                tabs_s, tabs_t = [], []
+                for pos, v in enumerate(groups[gi]):
+                    k = v % len(lay.videos)
+                    pl = plan_for(k)
+                    base = pos * self.MAX_RGB_PER_VIDEO
+                    for i, src in enumerate(pl.rgb_src):
+                        st.rgb[(base + i) * rgb_img:(base + i + 1) * rgb_img].copy_(host.rgb[src * rgb_img:(src + 1) * rgb_img], non_blocking=True)
+                    base = pos * self.MAX_FLOW_PER_VIDEO
+                    for src, loc, cnt in pl.flow_runs:
+                        st.flow[(base + loc) * flow_img:(base + loc + cnt) * flow_img].copy_(host.flow[src * flow_img:(src + cnt) * flow_img],
+                                                                                           non_blocking=True)
+                    hs, ht = tables_for_slot(k, pos)
+                    tabs_s.append(hs.to(dev, non_blocking=True))
+                    tabs_t.append(ht.to(dev, non_blocking=True))
+                    nb += pl.n_rgb * rgb_img + pl.n_flow * flow_img + hs.numel() * 4 + ht.numel() * 4
+                ts = torch.cat(tabs_s) if len(tabs_s) > 1 else tabs_s[0]
+                tt = torch.cat(tabs_t) if len(tabs_t) > 1 else tabs_t[0]
+                self._copied[slot].record(self._copy_stream)
+            pending[gi] = (ts, tt, nb)
+
+        for gi in range(min(depth - 1, len(groups))):
+            issue(gi)
+        for gi in range(len(groups)):
+            slot = gi % depth
+            if gi + depth - 1 < len(groups):
+                issue(gi + depth - 1)                 # its copies run under this group's networks
+            ts, tt, nb = pending.pop(gi)
+            cur.wait_event(self._copied[slot])
+            ts.record_stream(cur)
+            tt.record_stream(cur)
+            res = self.run_tables(ts, tt, len(groups[gi]), store=self._stages[slot])
+            self._consumed[slot].record(cur)
+            self.last_h2d_bytes = nb
+            yield res
 
     def _stream(self, net: ops.StreamNet, images, shape, table, mean, std):
         """One stream over a table of snippets -> (descriptors, softmax scores).  bf16 handles gather the crops inside the

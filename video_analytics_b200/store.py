@@ -11,6 +11,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import List
 
+VIDEO_FRAME_SAMPLE_RATE = 10  # parameters.py:2: frames are extracted every 10th video frame
 RGB_SHAPE = (240, 320, 3)     # UCF101 native; the reference never resizes (utils.py:116-120)
 FLOW_SHAPE = (256, 340, 1)    # TSN tvl1 tool convention for parameters.py:27's directory -- an assumption, a parameter
 STORE_SEED = 1234
@@ -59,15 +60,18 @@ class StoreLayout:
         return f"{base} {m.label}\n" if mode == "train" else base + "\n"
 
 
-def make_layout(pool: int, *, seed: int = STORE_SEED, min_frames: int = 12, frame_span: int = 19, n_classes: int = 25,
-                rgb_shape=RGB_SHAPE, flow_shape=FLOW_SHAPE) -> StoreLayout:
-    """n_frames_v = min_frames + hash(seed, v) % frame_span stored frames; n_flows_v = 2 * n_frames_v + 10."""
+def make_layout(pool: int, *, seed: int = STORE_SEED, min_frames: int = 25, frame_span: int = 19, n_classes: int = 25,
+                flows_per_frame: int = VIDEO_FRAME_SAMPLE_RATE, rgb_shape=RGB_SHAPE, flow_shape=FLOW_SHAPE) -> StoreLayout:
+    """UCF101-shaped clips: a video of 250..430 frames has n_frames_v = min_frames + hash(seed, v) %
+    frame_span STORED frames -- the reference keeps every 10th frame (utils.py:65, parameters.py:2) -- and a flow image
+    pair per video frame, n_flows_v = flows_per_frame * n_frames_v.  With >= 25 stored frames the protocol's 25 equally
+    spaced snippets are 25 DISTINCT frames and 25 disjoint stacks of 10 flow pairs."""
     lay = StoreLayout(seed=seed, rgb_shape=tuple(rgb_shape), flow_shape=tuple(flow_shape))
     rgb = flow = 0
     for v in range(pool):
         hv = _mix32(seed * 0x9E3779B1 + v * 0x85EBCA6B + 0x27D4EB2F)
         nf = min_frames + hv % frame_span
-        nfl = 2 * nf + 10
+        nfl = flows_per_frame * nf
         label = 1 + v % n_classes
         cat = f"Class{label:03d}"
         name = f"v_{cat}_g{1 + (v // n_classes) % 25:02d}_c{1 + v % 7:02d}"
