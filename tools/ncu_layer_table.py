@@ -53,12 +53,23 @@ def main():
         return v
 
     data = [r for r in data if len(r) > col["Kernel Name"]]
+    # the capture window may start a few launches before the step's first layer: align on the first-layer kernel (the
+    # only instances with CK = 16 / 32: conv_tc_kernel<64, 16, ..> spatial, <64, 32, ..> temporal, or the fused gather kernel)
+    import re
+    first = next((i for i, r in enumerate(data) if re.search(r"conv_tc_kernel<64, (16|32),|conv1_fused", r[col["Kernel Name"]])), 0)
+    lead = data[:first]
+    data = data[first:]
+    for r in lead:
+        print(f"(before the step's first layer: {r[col['Kernel Name']].split('(')[0]}, {scaled(r, 'gpu__time_duration.sum', 'us'):.1f} us -- tail of the previous stream)")
+    print()
     print("| # | stream | layer | kernel | grid | duration us | algorithmic TFLOP/s | tensor pipe active % | executed TFLOP (tensor path) | DRAM read MB | "
           "DRAM write MB | UTCMMA A wavefronts | UTCMMA B wavefronts (1cta / 2cta) | SM clock MHz |")
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     tot = {}
     for k, r in enumerate(data):
         stream = "spatial" if k < 16 else "temporal"      # launch 16 (if present) is the temporal stream's conv1_1
+        if k >= 17:
+            break
         layer = LAYERS[k % 16]
         kname = r[col["Kernel Name"]].split("(")[0].replace("va::", "")
         dur = scaled(r, "gpu__time_duration.sum", "us")

@@ -255,7 +255,7 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
       if (d.Cout % bn) continue;
       if (CK != 64 && bn != 64) continue;
       if (R == 3 && bn == 256) continue;
-      const long long tiles = (long long)tiles_m * (d.Cout / bn);
+      const long long tiles = (long long)tiles_m * (d.Cout / bn) * (splitk ? kSplitK : 1);
       const long long waves = (tiles + sms - 1) / sms;
       // relative cost per output column, measured on B200 (profiles/r01_diag_forward_call1.log): narrower N tiles
       // re-read the A patch from L2 more often and are L2->SM bandwidth bound.
