@@ -68,8 +68,8 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
   static_assert(NSEG * SEG == kF1Pitch, "SEG must divide the patch width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem;                                               // 2 x 16 KB, 1024-aligned (128B swizzle)
-  uint8_t* w_s = staging + 2 * kF1StagingBytes;                          // n_mma x 2 KB
+  uint8_t* staging = smem;                                               // 2 groups x 2 x 16 KB, 1024-aligned (128B swizzle)
+  uint8_t* w_s = staging + 4 * kF1StagingBytes;                          // n_mma x 2 KB
   const uint32_t a_stage_bytes = (uint32_t)p.n_chunks * kF1PlaneBytes;
   uint8_t* a_ring = w_s + (size_t)p.n_mma * 2048;
   uint16_t* lut_s = reinterpret_cast<uint16_t*>(a_ring + (size_t)kF1Stages * a_stage_bytes);
@@ -114,6 +114,12 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Every CTA walks a CONTIGUOUS range of tiles (row-major inside a snippet): consecutive tiles read neighbouring 8-pixel
+  // column blocks of the same source rows and the same index-table row, so the gather's loads hit L1 (a strided
+  // assignment made every tile a fresh L2 round trip for the table row AND the pixels: 1650 clk per tile measured).
+  const int tiles_per = p.total_tiles / (int)gridDim.x, tiles_rem = p.total_tiles % (int)gridDim.x;
+  const int tile_begin = (int)blockIdx.x * tiles_per + min((int)blockIdx.x, tiles_rem);
+  const int tile_end = tile_begin + tiles_per + ((int)blockIdx.x < tiles_rem ? 1 : 0);
 
   if (warp >= kGatherWarp0 && warp < kGatherWarp0 + 4) {
     // ===================================================== gather + normalise -> A operand (4 warps)
@@ -213,13 +219,13 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
     };
 
     uint32_t stage = 0, phase = 0;
-    int tile = blockIdx.x;
-    if (tile < p.total_tiles) load_tile(tile, ua, ma);
+    int tile = tile_begin;
+    if (tile < tile_end) load_tile(tile, ua, ma);
     // two tiles per iteration so that the register sets alternate without copies
-    while (tile < p.total_tiles) {
+    while (tile < tile_end) {
       {
-        const int next = tile + (int)gridDim.x;
-        if (next < p.total_tiles) load_tile(next, ub, mb);
+        const int next = tile + 1;
+        if (next < tile_end) load_tile(next, ub, mb);
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
         convert_tile(a_ring + (size_t)stage * a_stage_bytes, ua, ma);
         fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -228,10 +234,10 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
         if (++stage == kF1Stages) { stage = 0; phase ^= 1; }
         tile = next;
       }
-      if (tile >= p.total_tiles) break;
+      if (tile >= tile_end) break;
       {
-        const int next = tile + (int)gridDim.x;
-        if (next < p.total_tiles) load_tile(next, ua, ma);
+        const int next = tile + 1;
+        if (next < tile_end) load_tile(next, ua, ma);
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
         convert_tile(a_ring + (size_t)stage * a_stage_bytes, ub, mb);
         fence_proxy_async_smem();
@@ -250,7 +256,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
     const uint64_t da_base = desc_noswizzle_base(kF1Pitch * 16);                         // 8-pixel groups 160 B apart
     const uint64_t db_base = desc_noswizzle_base(128) | ((uint64_t)(1024 >> 4) << 16);   // [k-chunk][n][8]: SBO 128, LBO 1024
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
       mbar_wait(&full_bar[stage], phase, 300 + stage);
       tc_fence_after();
@@ -273,10 +279,13 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
     const int q = warp & 3;
     const int m = q * 32 + lane;                  // accumulator row == pixel h_i*8 + w_i of the tile
     const int et = threadIdx.x - eg * 128;
-    uint8_t* stage_out = staging + eg * kF1StagingBytes;
+    // TWO staging buffers per group: the layer writes 16 KB per tile, and a TMA store holds its buffer until the store
+    // engine has read it (~1 us under HBM write pressure) -- with one buffer per group that turnaround, not bandwidth,
+    // set the tile rate (0.98 us per tile = 2.4 TB/s of writes measured).
+    uint8_t* stage_base = staging + eg * 2 * kF1StagingBytes;
     const uint32_t as = (uint32_t)eg;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       if ((it & 1) != eg) continue;
       const uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
       uint32_t mt, tw, th, tn;
@@ -304,8 +313,9 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
         pk[i] = *reinterpret_cast<uint32_t*>(&lo);
         pk[16 + i] = *reinterpret_cast<uint32_t*>(&hi);
       }
-      if (et < 32) {                       // the group's staging buffer was last read by its previous TMA store
-        if (elect_one()) tma_store_wait_read<0>();
+      uint8_t* stage_out = stage_base + ((it >> 1) & 1) * kF1StagingBytes;
+      if (et < 32) {                       // this buffer was last read by the group's store of two tiles ago
+        if (elect_one()) tma_store_wait_read<1>();
         __syncwarp();
       }
       named_bar_sync(1 + eg, 128);
@@ -483,7 +493,7 @@ const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h
   }
   const bool rep32 = img_c == 1 && p.n_luts == 1;
   const int rep = rep32 ? 32 : 1;
-  const size_t smem = 1024 + 2 * kF1StagingBytes + (size_t)p.n_mma * 2048 + (size_t)kF1Stages * p.n_chunks * kF1PlaneBytes +
+  const size_t smem = 1024 + 4 * kF1StagingBytes + (size_t)p.n_mma * 2048 + (size_t)kF1Stages * p.n_chunks * kF1PlaneBytes +
                       (size_t)p.n_luts * 256 * rep * 2 + 64 * 4 + (2 * kF1Stages + 4) * 8 + 16;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
