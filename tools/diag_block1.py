@@ -118,6 +118,19 @@ def run_fused(kind, batch):
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         res[name] = ts[len(ts) // 2]
+    # per-role cycle counters of CTA 0 (gather thread 0, MMA warp, epilogue group 0)
+    from video_analytics_b200 import _lib
+    cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
+    _lib.load().va_debug_conv_counters(_lib.ptr(cnt))
+    fused()
+    torch.cuda.synchronize()
+    _lib.load().va_debug_conv_counters(None)
+    c = cnt.cpu().tolist()
+    tiles = max(1, c[11])
+    res["roles"] = {"tiles_per_cta": tiles, "clk_per_tile": c[0] / tiles,
+                    "gather_pct": {"load_next": 100 * c[1] / max(1, c[0]), "wait_empty": 100 * c[2] / max(1, c[0]), "convert+fence": 100 * c[3] / max(1, c[0])},
+                    "mma_pct": {"wait_tmem_empty": 100 * c[5] / max(1, c[4]), "wait_full": 100 * c[6] / max(1, c[4])},
+                    "epilogue0_pct": {"wait_tmem_full": 100 * c[8] / max(1, c[7]), "wait_staging": 100 * c[9] / max(1, c[7])}}
     out_bytes = batch * 224 * 224 * 64 * 2
     res["fused_write_GBs"] = out_bytes / (res["fused_ms"] * 1e-3) / 1e9
     res["ok"] = res["max_abs_diff"] <= 0.05 * max(res["ref_absmean"], 1e-3) + 0.05

@@ -29,12 +29,13 @@ namespace va {
 
 namespace {
 
-constexpr int kF1Threads = 416;
+constexpr int kF1GatherWarps = 6;                      // 192 threads >= the 180 pixels of a haloed patch
+constexpr int kF1Threads = (8 + kF1GatherWarps + 1) * 32;
 constexpr int kF1TileH = 16, kF1TileW = 8, kF1Pitch = kF1TileW + 2, kF1Rows = kF1TileH + 2;
 constexpr int kF1Pix = kF1Pitch * kF1Rows;            // 180 haloed pixels
-constexpr int kF1PlaneBytes = kF1Pix * 16;            // one 8-channel plane of a stage
+constexpr int kF1PlaneBytes = kF1Pix * 32;            // one plane of a stage: [pixel][16 bf16]
 constexpr int kF1Crop = 224;
-constexpr int kF1MaxMma = 18;
+constexpr int kF1MaxMma = 24;
 constexpr int kF1Stages = 4;
 constexpr int kF1StagingBytes = 128 * 128;            // 128 pixels x 64 bf16
 
@@ -44,37 +45,62 @@ struct Conv1FusedParams {
   int img_w;
   const int32_t* table;          // [n][planes][4] = image id, crop top, crop left, flip
   int n_img, planes;
-  FastDiv div_planes;
-  int n_chunks;                  // ceil(planes * IMG_C / 8)
+  int n_full;                    // 16-channel planes of a stage
+  int has_pair;                  // + one "pair" plane holding the remaining <= 8 channels of pixel p and of pixel p+1
   int n_luts;
   float lut_mean[3], lut_std[3];
   unsigned char lut_of[32];
-  const __nv_bfloat16* w_packed; // [n_mma][2][64][8]
+  const __nv_bfloat16* w_packed; // [n_mma][64][16], 32B-swizzled
   const float* bias;             // [64]
   int total_tiles;
   FastDiv div_w, div_h;          // by 28, 14
   int n_mma;
-  unsigned long long a_delta[kF1MaxMma];   // per MMA: (first-chunk byte offset >> 4) | (LBO >> 4) << 16
+  unsigned int a_off16[kF1MaxMma];   // per MMA: byte offset of its A window inside a stage, >> 4
+  long long* dbg;                    // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
 };
 
-__device__ __forceinline__ uint64_t desc_noswizzle_base(uint32_t sbo_bytes) {
-  return ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);       // layout type 0, descriptor version 1
+// 32-byte swizzle (Swizzle<1,4,3>): the 16-byte half of a 32-byte row is XORed with address bit 7.  Both TMA and UMMA apply
+// it to ABSOLUTE shared-memory address bits (measured: va_conv_tc.cuh HALO), so generic stores that do the same produce an
+// operand the tensor core reads from ANY 32-byte-aligned start address.
+__device__ __forceinline__ uint32_t swz32(uint32_t addr) { return addr ^ ((addr >> 3) & 0x10u); }
+
+// Explicit shared-state-space loads: pointers derived from the aligned dynamic-smem base are GENERIC to the compiler, and a
+// generic LD.E to shared memory (~150 clk dependent latency, measured through the role counters) made the 20 table lookups
+// of a flow pixel the kernel's critical path.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int IMG_C, int SEG, int REP, int ROUNDS>
+template <int IMG_C, int MAXCH, int REP>
 __global__ void __launch_bounds__(kF1Threads, 1)
 conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedParams p) {
-  constexpr int NSEG = kF1Pitch / SEG;
-  static_assert(NSEG * SEG == kF1Pitch, "SEG must divide the patch width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem;                                               // 2 groups x 2 x 16 KB, 1024-aligned (128B swizzle)
   uint8_t* w_s = staging + 4 * kF1StagingBytes;                          // n_mma x 2 KB
-  const uint32_t a_stage_bytes = (uint32_t)p.n_chunks * kF1PlaneBytes;
+  const int n_planes = p.n_full + p.has_pair;
+  const uint32_t a_stage_bytes = (uint32_t)n_planes * kF1PlaneBytes;
   uint8_t* a_ring = w_s + (size_t)p.n_mma * 2048;
   uint16_t* lut_s = reinterpret_cast<uint16_t*>(a_ring + (size_t)kF1Stages * a_stage_bytes);
   float* bias_s = reinterpret_cast<float*>(lut_s + (size_t)p.n_luts * 256 * REP);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 64);
+  unsigned long long* pl_base = reinterpret_cast<unsigned long long*>(bias_s + 64);      // [32] per-plane source base of the snippet
+  uint32_t* pl_flip = reinterpret_cast<uint32_t*>(pl_base + 32);                         // bit pl = flip; [1] = snippet id
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(pl_flip + 2);
   uint64_t* empty_bar = full_bar + kF1Stages;
   uint64_t* tfull_bar = empty_bar + kF1Stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -82,21 +108,22 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kGatherWarp0 = 8, kMmaWarp = 12;
+  constexpr int kGatherWarp0 = 8, kMmaWarp = 8 + kF1GatherWarps;
 
   // ---- prologue: barriers, TMEM, resident weights, normalisation table, zeroed stages
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmO);
-    for (int i = 0; i < kF1Stages; ++i) { mbar_init(&full_bar[i], 4); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kF1Stages; ++i) { mbar_init(&full_bar[i], kF1GatherWarps); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_mbar_init();
+    pl_flip[1] = 0xFFFFFFFFu;
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
   {
     const uint4* wg = reinterpret_cast<const uint4*>(p.w_packed);
     uint4* ws4 = reinterpret_cast<uint4*>(w_s);
     for (int i = threadIdx.x; i < p.n_mma * 128; i += kF1Threads) ws4[i] = __ldg(wg + i);
-    // pad channels of the last chunk (and everything else) start as zero and are never written again
+    // channel padding, the last pair row and everything else start as zero; only real channels are ever written again
     uint4* a4 = reinterpret_cast<uint4*>(a_ring);
     const int n16 = (int)(kF1Stages * a_stage_bytes / 16);
     for (int i = threadIdx.x; i < n16; i += kF1Threads) a4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -115,156 +142,156 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Every CTA walks a CONTIGUOUS range of tiles (row-major inside a snippet): consecutive tiles read neighbouring 8-pixel
-  // column blocks of the same source rows and the same index-table row, so the gather's loads hit L1 (a strided
-  // assignment made every tile a fresh L2 round trip for the table row AND the pixels: 1650 clk per tile measured).
+  // column blocks of the same source rows, so the gather's loads hit L1, and the per-plane source bases change once per snippet.
   const int tiles_per = p.total_tiles / (int)gridDim.x, tiles_rem = p.total_tiles % (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * tiles_per + min((int)blockIdx.x, tiles_rem);
   const int tile_end = tile_begin + tiles_per + ((int)blockIdx.x < tiles_rem ? 1 : 0);
 
-  if (warp >= kGatherWarp0 && warp < kGatherWarp0 + 4) {
-    // ===================================================== gather + normalise -> A operand (4 warps)
-    // Work item = SEG consecutive pixels of one patch row of one plane (flow: a whole 10-pixel row; RGB: 2 pixels x 3
-    // channels); thread t owns items t, t+128, ... so row / plane / destination offset are per-thread constants.  The
-    // source bytes of the NEXT tile are loaded into registers before the current tile is converted: the two dependent
-    // L2 round trips (index-table row, then pixels) are hidden behind the table lookups and stores of the current tile
-    // (first version, one tile at a time: 2.2 ms per 250 flow stacks, latency-bound).
+  if (warp >= kGatherWarp0 && warp < kGatherWarp0 + kF1GatherWarps) {
+    // ===================================================== gather + normalise -> A operand (6 warps, thread = patch pixel)
+    // Thread t < 180 owns pixel (row t/10, col t%10) of the haloed patch and loops over the planes: a warp-level byte load
+    // then touches ~4 cache lines (3 patch rows of one plane), not 32 as with one (plane, row) per lane.  The bytes of the
+    // NEXT tile are loaded before the current tile is converted (two register sets).
     const int gt = threadIdx.x - kGatherWarp0 * 32;
-    const int items = kF1Rows * p.planes * NSEG;
+    const bool has_px = gt < kF1Pix;
+    const int prow = has_px ? gt / kF1Pitch : 0, pcol = has_px ? gt % kF1Pitch : 0;
     const int4* table4 = reinterpret_cast<const int4*>(p.table);
-    constexpr int NB = SEG * IMG_C;                     // source bytes per item
-    constexpr uint32_t FULL = (1u << SEG) - 1u;
-    int it_row[ROUNDS], it_plane[ROUNDS], it_x[ROUNDS];
-    uint32_t it_off[ROUNDS];
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-      const int i = gt + 128 * r;
-      uint32_t seg = 0, rp = (uint32_t)i;
-      if (NSEG > 1) { rp = (uint32_t)i / NSEG; seg = (uint32_t)i - rp * NSEG; }
-      uint32_t row, plane;
-      p.div_planes.divmod(rp, row, plane);
-      const bool valid = i < items;
-      it_row[r] = valid ? (int)row : -1;
-      it_plane[r] = (int)plane;
-      it_x[r] = (int)seg * SEG;
-      const int ch0 = (int)plane * IMG_C;
-      it_off[r] = (uint32_t)(((int)row * kF1Pitch + (int)seg * SEG) * 16 + (ch0 >> 3) * kF1PlaneBytes + (ch0 & 7) * 2);
-    }
-    uint32_t ua[ROUNDS][NB], ub[ROUNDS][NB], ma[ROUNDS], mb[ROUNDS];
+    const int nch = p.planes * IMG_C;
+    uint32_t ua[MAXCH], ub[MAXCH];
+    bool va_ok = false, vb_ok = false;
+    const uint32_t lut_u32 = smem_u32(lut_s), plb_u32 = smem_u32(pl_base), plf_u32 = smem_u32(pl_flip);
 
-    auto load_tile = [&](int tile, uint32_t (&u)[ROUNDS][NB], uint32_t (&msk)[ROUNDS]) {
+    auto load_tile = [&](int tile, uint32_t (&u)[MAXCH], bool& ok) {
       uint32_t mt, tw, th, tn;
       p.div_w.divmod((uint32_t)tile, mt, tw);
       p.div_h.divmod(mt, tn, th);
-      const int h0 = (int)th * kF1TileH, w0 = (int)tw * kF1TileW;
-      // patch columns inside the crop (bit q <-> x = w0 - 1 + q): everything except the conv's zero-padding columns
-      const uint32_t colmask = 0x3FFu & ~(w0 == 0 ? 1u : 0u) & ~(w0 + kF1TileW == kF1Crop ? (1u << (kF1Pitch - 1)) : 0u);
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) {
-        msk[r] = 0;
-        if (it_row[r] < 0) continue;
-        const int y = h0 - 1 + it_row[r];
-        if ((unsigned)y >= (unsigned)kF1Crop) {                            // zero-padding row: no loads, table index 0
-#pragma unroll
-          for (int b = 0; b < NB; ++b) u[r][b] = 0u;
-          continue;
+      if (lds_u32(plf_u32 + 4) != tn) {                // first tile of a snippet (same decision in all gather threads)
+        named_bar_sync(5, kF1GatherWarps * 32);        // nobody still reads the previous snippet's entries
+        if (gt < p.planes) {
+          const int4 e = __ldg(table4 + (size_t)tn * p.planes + gt);   // image id, crop top, crop left, flip
+          pl_base[gt] = (unsigned long long)e.x * p.image_bytes + ((unsigned long long)e.y * p.img_w + e.z) * IMG_C;
+          if (e.w) atomicOr(&pl_flip[0], 1u << gt); else atomicAnd(&pl_flip[0], ~(1u << gt));
         }
-        const uint32_t m = (colmask >> it_x[r]) & FULL;
-        msk[r] = m;
-        const int4 e = __ldg(table4 + (size_t)tn * p.planes + it_plane[r]);   // image id, crop top, crop left, flip
-        const uint8_t* base = p.images + (unsigned long long)e.x * p.image_bytes +
-                              ((long long)(e.y + y) * p.img_w + e.z) * IMG_C;
-        const int x0 = w0 - 1 + it_x[r];
-        if (m == FULL) {
-          if (!e.w) {
-            const uint8_t* s0 = base + x0 * IMG_C;
+        if (gt == 0) pl_flip[1] = tn;
+        named_bar_sync(5, kF1GatherWarps * 32);
+      }
+      const int y = (int)th * kF1TileH - 1 + prow, x = (int)tw * kF1TileW - 1 + pcol;
+      ok = has_px && (unsigned)y < (unsigned)kF1Crop && (unsigned)x < (unsigned)kF1Crop;   // else: the conv's zero padding
+      if (!ok) return;
+      const uint32_t flips = lds_u32(plf_u32);
+      const uint32_t off_n = (uint32_t)(y * p.img_w + x) * IMG_C, off_f = (uint32_t)(y * p.img_w + (kF1Crop - 1 - x)) * IMG_C;
 #pragma unroll
-            for (int q = 0; q < SEG; ++q)
+      for (int pl = 0; pl < MAXCH / IMG_C; ++pl) {
+        if (pl < p.planes) {
+          const uint8_t* src = p.images + lds_u64(plb_u32 + 8 * pl) + (((flips >> pl) & 1u) ? off_f : off_n);   // hflip == reversed columns
 #pragma unroll
-              for (int k = 0; k < IMG_C; ++k) u[r][q * IMG_C + k] = __ldg(s0 + q * IMG_C + k);
-          } else {                                                         // hflip of the crop == reversed columns
-            const uint8_t* s0 = base + (kF1Crop - 1 - x0) * IMG_C;
-#pragma unroll
-            for (int q = 0; q < SEG; ++q)
-#pragma unroll
-              for (int k = 0; k < IMG_C; ++k) u[r][q * IMG_C + k] = __ldg(s0 - q * IMG_C + k);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < SEG; ++q) {
-            const int x = x0 + q;
-            const int xs = e.w ? (kF1Crop - 1 - x) : x;
-#pragma unroll
-            for (int k = 0; k < IMG_C; ++k) u[r][q * IMG_C + k] = ((m >> q) & 1u) ? (uint32_t)__ldg(base + xs * IMG_C + k) : 0u;
-          }
+          for (int k = 0; k < IMG_C; ++k) u[pl * IMG_C + k] = __ldg(src + k);
         }
       }
     };
-    auto convert_tile = [&](uint8_t* a_dst, const uint32_t (&u)[ROUNDS][NB], const uint32_t (&msk)[ROUNDS]) {
+    auto convert_tile = [&](uint32_t a_dst, const uint32_t (&u)[MAXCH], bool ok) {
+      if (!has_px) return;
+      uint32_t pk[MAXCH / 2];                          // bf16 pairs, channel order
 #pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) {
-        if (it_row[r] < 0) continue;
-        uint8_t* dst = a_dst + it_off[r];
-        const uint32_t m = msk[r];
-#pragma unroll
-        for (int q = 0; q < SEG; ++q) {
-#pragma unroll
-          for (int k = 0; k < IMG_C; ++k) {
-            const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[it_plane[r] * IMG_C + k];
-            uint16_t v = lut_s[(size_t)(li * 256 + (int)u[r][q * IMG_C + k]) * REP + (REP == 32 ? lane : 0)];
-            if (m != FULL && !((m >> q) & 1u)) v = 0;                      // outside the crop: the conv's zero padding
-            *reinterpret_cast<uint16_t*>(dst + q * 16 + k * 2) = v;
-          }
+      for (int c = 0; c < MAXCH; c += 2) {
+        uint32_t lo = 0, hi = 0;
+        if (ok && c < nch) {
+          const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c];
+          lo = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c]) * REP + (REP == 32 ? lane : 0)) * 2));
         }
+        if (ok && c + 1 < nch) {
+          const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c + 1];
+          hi = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c + 1]) * REP + (REP == 32 ? lane : 0)) * 2));
+        }
+        pk[c / 2] = lo | (hi << 16);
+      }
+      const uint32_t row_addr = a_dst + (uint32_t)gt * 32u;
+#pragma unroll
+      for (int f = 0; f < MAXCH / 16; ++f) {           // full 16-channel planes: row p = channels 16f .. 16f+15 of pixel p
+        if (f < p.n_full) {
+          const uint32_t a = row_addr + (uint32_t)f * kF1PlaneBytes;
+          sts128(swz32(a), make_uint4(pk[8 * f], pk[8 * f + 1], pk[8 * f + 2], pk[8 * f + 3]));
+          sts128(swz32(a + 16), make_uint4(pk[8 * f + 4], pk[8 * f + 5], pk[8 * f + 6], pk[8 * f + 7]));
+        }
+      }
+      if (p.has_pair) {                                // pair plane: row p = [remaining channels of pixel p | of pixel p+1]
+        uint4 g = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int f = 0; f < MAXCH / 16; ++f)
+          if (f == p.n_full) g = make_uint4(pk[8 * f], pk[8 * f + 1], pk[8 * f + 2], pk[8 * f + 3]);
+        const uint32_t a = row_addr + (uint32_t)p.n_full * kF1PlaneBytes;
+        sts128(swz32(a), g);
+        if (gt > 0) sts128(swz32(a - 32 + 16), g);
       }
     };
 
+    const uint32_t ring_u32 = smem_u32(a_ring);
     uint32_t stage = 0, phase = 0;
     int tile = tile_begin;
-    if (tile < tile_end) load_tile(tile, ua, ma);
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && gt == 0;
+    long long t_load = 0, t_wait = 0, t_conv = 0, t_begin = clock64(), tq = 0;
+    if (tile < tile_end) load_tile(tile, ua, va_ok);
     // two tiles per iteration so that the register sets alternate without copies
     while (tile < tile_end) {
       {
         const int next = tile + 1;
-        if (next < tile_end) load_tile(next, ub, mb);
+        if (dbg) tq = clock64();
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-        convert_tile(a_ring + (size_t)stage * a_stage_bytes, ua, ma);
-        fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        if (dbg) { const long long t = clock64(); t_wait += t - tq; tq = t; }
+        convert_tile(ring_u32 + stage * a_stage_bytes, ua, va_ok);
+        // generic-proxy stores -> visible to the tensor core's async-proxy reads.  ptxas implements this fence with a
+        // MEMBAR.ALL.CTA, which also waits for every global load in flight: the next tile's loads are therefore issued
+        // AFTER it (issued before, the fence exposed their whole L2 latency on every tile).
+        fence_proxy_async_smem();
+        if (dbg) { const long long t = clock64(); t_conv += t - tq; tq = t; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == kF1Stages) { stage = 0; phase ^= 1; }
+        if (next < tile_end) load_tile(next, ub, vb_ok);
+        if (dbg) { const long long t = clock64(); t_load += t - tq; tq = t; }
         tile = next;
       }
       if (tile >= tile_end) break;
       {
         const int next = tile + 1;
-        if (next < tile_end) load_tile(next, ua, ma);
+        if (dbg) tq = clock64();
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-        convert_tile(a_ring + (size_t)stage * a_stage_bytes, ub, mb);
+        if (dbg) { const long long t = clock64(); t_wait += t - tq; tq = t; }
+        convert_tile(ring_u32 + stage * a_stage_bytes, ub, vb_ok);
         fence_proxy_async_smem();
+        if (dbg) { const long long t = clock64(); t_conv += t - tq; tq = t; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == kF1Stages) { stage = 0; phase ^= 1; }
+        if (next < tile_end) load_tile(next, ua, va_ok);
+        if (dbg) { const long long t = clock64(); t_load += t - tq; tq = t; }
         tile = next;
       }
     }
+    if (dbg) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = t_load; p.dbg[2] = t_wait; p.dbg[3] = t_conv; p.dbg[11] = tile_end - tile_begin; }
   } else if (warp == kMmaWarp) {
     // ===================================================== MMA issuer (convergent warp, one elected lane issues)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64);
     const uint32_t a_ring_u32 = smem_u32(a_ring);
     const uint32_t w_u32 = smem_u32(w_s);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint64_t da_base = desc_noswizzle_base(kF1Pitch * 16);                         // 8-pixel groups 160 B apart
-    const uint64_t db_base = desc_noswizzle_base(128) | ((uint64_t)(1024 >> 4) << 16);   // [k-chunk][n][8]: SBO 128, LBO 1024
+    // A: 32-byte rows (one pixel x 16 channels), 8-pixel groups (one output row of the tile) 10 pixels = 320 B apart
+    const uint64_t a_sbo_fix = ((uint64_t)((kF1Pitch * 32) >> 4) << 32) - ((uint64_t)((32 * 8) >> 4) << 32);
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+    long long t_te = 0, t_full = 0, t_begin = clock64();
     for (int tile = tile_begin; tile < tile_end; ++tile) {
+      long long tq = dbg ? clock64() : 0;
       mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
+      if (dbg) { const long long t = clock64(); t_te += t - tq; tq = t; }
       mbar_wait(&full_bar[stage], phase, 300 + stage);
+      if (dbg) t_full += clock64() - tq;
       tc_fence_after();
-      const uint64_t da0 = da_base + ((a_ring_u32 + stage * a_stage_bytes) >> 4);
-      const uint64_t db0 = db_base + (w_u32 >> 4);
+      const uint64_t da0 = make_smem_desc<32>(a_ring_u32 + stage * a_stage_bytes) + a_sbo_fix;
+      const uint64_t db0 = make_smem_desc<32>(w_u32);
       const uint32_t d_tmem = tmem_u + as * 64;
       if (elect_one()) {
-        for (int i = 0; i < p.n_mma; ++i) umma_bf16(d_tmem, da0 + p.a_delta[i], db0 + (uint64_t)(i * (2048 >> 4)), idesc, i ? 1u : 0u);
+        for (int i = 0; i < p.n_mma; ++i) umma_bf16(d_tmem, da0 + p.a_off16[i], db0 + (uint64_t)(i * (2048 >> 4)), idesc, i ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         umma_commit(&tfull_bar[as]);
       }
@@ -273,25 +300,28 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
       as ^= 1;
       if (as == 0) as_phase ^= 1;
     }
+    if (dbg && lane == 0) { p.dbg[4] = clock64() - t_begin; p.dbg[5] = t_te; p.dbg[6] = t_full; }
   } else if (warp < 8) {
     // ===================================================== epilogue (2 groups x 4 warps)
     const int eg = warp >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;                  // accumulator row == pixel h_i*8 + w_i of the tile
     const int et = threadIdx.x - eg * 128;
-    // TWO staging buffers per group: the layer writes 16 KB per tile, and a TMA store holds its buffer until the store
-    // engine has read it (~1 us under HBM write pressure) -- with one buffer per group that turnaround, not bandwidth,
-    // set the tile rate (0.98 us per tile = 2.4 TB/s of writes measured).
+    // two staging buffers per group: a TMA store holds its buffer until the store engine has read it
     uint8_t* stage_base = staging + eg * 2 * kF1StagingBytes;
     const uint32_t as = (uint32_t)eg;
     int it = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && et == 0 && eg == 0;
+    long long t_tf = 0, t_st = 0, t_begin = clock64();
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       if ((it & 1) != eg) continue;
       const uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
       uint32_t mt, tw, th, tn;
       p.div_w.divmod((uint32_t)tile, mt, tw);
       p.div_h.divmod(mt, tn, th);
+      long long tq = dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[as], as_phase, 400 + as);
+      if (dbg) t_tf += clock64() - tq;
       tc_fence_after();
       uint32_t v0[32], v1[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 64;
@@ -314,11 +344,13 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
         pk[16 + i] = *reinterpret_cast<uint32_t*>(&hi);
       }
       uint8_t* stage_out = stage_base + ((it >> 1) & 1) * kF1StagingBytes;
+      tq = dbg ? clock64() : 0;
       if (et < 32) {                       // this buffer was last read by the group's store of two tiles ago
         if (elect_one()) tma_store_wait_read<1>();
         __syncwarp();
       }
       named_bar_sync(1 + eg, 128);
+      if (dbg) t_st += clock64() - tq;
       uint8_t* rowp = stage_out + m * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -339,6 +371,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
       if (elect_one()) tma_store_wait_all();
       __syncwarp();
     }
+    if (dbg) { p.dbg[7] = clock64() - t_begin; p.dbg[8] = t_tf; p.dbg[9] = t_st; }
   }
 
   tc_fence_before();
@@ -346,49 +379,56 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 128);
 }
 
-// ---- weight packing for the dense-K schedule -------------------------------------------------------------------
+// ---- weight packing for the K schedule ---------------------------------------------------------------------------
 struct Conv1PackPlan {
   int n_mma;
-  signed char tap[kF1MaxMma][2];     // r*3+s, or -1 = zero weights
-  signed char chunk[kF1MaxMma][2];
+  signed char tap[kF1MaxMma][2];     // per 8-channel half of the MMA's K = 16: tap r*3+s, or -1 = zero weights
+  signed char ch0[kF1MaxMma][2];     // first input channel of that half
 };
 
 __global__ void pack_conv1_fused_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin,
                                           const Conv1PackPlan plan) {
-  // out [n_mma][2][64][8]; w OIHW [64][cin][3][3]
+  // out [n_mma][64 rows n][16 k] in the 32B-swizzled layout the tensor core reads; w OIHW [64][cin][3][3]
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= plan.n_mma * 2 * 64 * 8) return;
-  const int e = idx & 7, n = (idx >> 3) & 63, kc = (idx >> 9) & 1, i = idx >> 10;
-  const int tap = plan.tap[i][kc], ch = plan.chunk[i][kc] * 8 + e;
+  if (idx >= plan.n_mma * 64 * 16) return;
+  const int k = idx & 15, n = (idx >> 4) & 63, i = idx >> 10;
+  const int half = k >> 3, e = k & 7;
+  const int tap = plan.tap[i][half], ch = plan.ch0[i][half] + e;
   float v = 0.f;
   if (tap >= 0 && ch < cin) v = w[((size_t)n * cin + ch) * 9 + tap];
-  out[idx] = __float2bfloat16_rn(v);
+  uint32_t off = (uint32_t)(n * 32 + half * 16);           // bytes inside the MMA's 2 KB block (2 KB-aligned in smem)
+  off ^= (off >> 3) & 0x10u;
+  out[(size_t)i * 1024 + off / 2 + e] = __float2bfloat16_rn(v);
 }
 
 struct Conv1Schedule {
   Conv1PackPlan plan;
-  unsigned long long a_delta[kF1MaxMma];
+  unsigned int a_off16[kF1MaxMma];
+  int n_full, has_pair;
 };
 
-Conv1Schedule make_schedule(int n_chunks) {
+Conv1Schedule make_schedule(int cin) {
   Conv1Schedule s;
   s.plan.n_mma = 0;
-  auto shift = [](int tap) { return (tap / 3) * kF1Pitch + (tap % 3); };
-  auto add = [&](int tap0, int chunk0, bool zero0, int tap1, int chunk1) {
+  const int rem = cin % 16;
+  s.n_full = cin / 16 + (rem > 8 ? 1 : 0);
+  s.has_pair = (rem > 0 && rem <= 8) ? 1 : 0;
+  auto shift = [](int r, int c) { return r * kF1Pitch + c; };
+  auto add = [&](int plane, int px_shift, int tap0, int ch0, int tap1, int ch1) {
     const int i = s.plan.n_mma++;
-    const long long off0 = (long long)chunk0 * kF1PlaneBytes + shift(tap0) * 16;
-    const long long off1 = (long long)chunk1 * kF1PlaneBytes + shift(tap1) * 16;
-    s.plan.tap[i][0] = (signed char)(zero0 ? -1 : tap0); s.plan.chunk[i][0] = (signed char)chunk0;
-    s.plan.tap[i][1] = (signed char)tap1; s.plan.chunk[i][1] = (signed char)chunk1;
-    s.a_delta[i] = (unsigned long long)(off0 >> 4) | ((unsigned long long)((off1 - off0) >> 4) << 16);
+    s.plan.tap[i][0] = (signed char)tap0; s.plan.ch0[i][0] = (signed char)ch0;
+    s.plan.tap[i][1] = (signed char)tap1; s.plan.ch0[i][1] = (signed char)ch1;
+    s.a_off16[i] = (unsigned int)((plane * kF1PlaneBytes + px_shift * 32) >> 4);
   };
-  for (int tap = 0; tap < 9; ++tap)
-    for (int q = 0; q + 1 < n_chunks; q += 2) add(tap, q, false, tap, q + 1);
-  if (n_chunks & 1) {
-    const int j = n_chunks - 1;
-    for (int r = 0; r < 3; ++r) add(r * 3 + 0, j, false, r * 3 + 1, j);    // (r,0) + (r,1): second half = pixel to the right
-    add(0 * 3 + 2, j, false, 1 * 3 + 2, j);                                // (0,2) + (1,2): second half = pixel below
-    add(2 * 3 + 1, j, true, 2 * 3 + 2, j);                                 // zero-weighted (2,1) + (2,2)
+  for (int f = 0; f < s.n_full; ++f)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) add(f, shift(r, c), r * 3 + c, 16 * f, r * 3 + c, 16 * f + 8);
+  if (s.has_pair) {
+    const int c0 = 16 * s.n_full;
+    for (int r = 0; r < 3; ++r) {
+      add(s.n_full, shift(r, 0), r * 3 + 0, c0, r * 3 + 1, c0);      // [pixel p | pixel p+1] x taps (r,0), (r,1)
+      add(s.n_full, shift(r, 2), r * 3 + 2, c0, -1, c0);             // [pixel p+2 | pixel p+3] x tap (r,2), zero weights
+    }
   }
   return s;
 }
@@ -411,9 +451,9 @@ EncodeTiledFn encode_fn() {
 
 thread_local char g_err1[256];
 
-template <int IMG_C, int SEG, int REP, int ROUNDS>
+template <int IMG_C, int MAXCH, int REP>
 const char* launch_fused(const CUtensorMap& tO, const Conv1FusedParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = conv1_fused_kernel<IMG_C, SEG, REP, ROUNDS>;
+  auto kfn = conv1_fused_kernel<IMG_C, MAXCH, REP>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -429,18 +469,15 @@ const char* launch_fused(const CUtensorMap& tO, const Conv1FusedParams& p, int g
 
 }  // namespace
 
-int conv1_fused_packed_bytes(int cin) {
-  const int n_chunks = (cin + 7) / 8;
-  return make_schedule(n_chunks).plan.n_mma * 2048;
-}
+int conv1_fused_packed_bytes(int cin) { return make_schedule(cin).plan.n_mma * 2048; }
 
 bool conv1_fused_supported(int planes, int img_c, int crop) {
   return crop == kF1Crop && ((planes == 1 && img_c == 3) || (img_c == 1 && planes >= 1 && planes <= 32));
 }
 
 cudaError_t launch_pack_conv1_fused_w(const float* w, void* out, int cin, cudaStream_t st) {
-  const Conv1Schedule s = make_schedule((cin + 7) / 8);
-  const int total = s.plan.n_mma * 2 * 64 * 8;
+  const Conv1Schedule s = make_schedule(cin);
+  const int total = s.plan.n_mma * 64 * 16;
   count_launch();
   pack_conv1_fused_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), cin, s.plan);
   return cudaGetLastError();
@@ -455,8 +492,6 @@ const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h
   const int cin = planes * img_c;
   Conv1FusedParams p;
   p.images = images; p.image_bytes = image_bytes; p.img_w = img_w; p.table = table; p.n_img = n; p.planes = planes;
-  p.div_planes = FastDiv::make((uint32_t)planes);
-  p.n_chunks = (cin + 7) / 8;
   p.n_luts = 0;
   for (int i = 0; i < 3; ++i) { p.lut_mean[i] = 0.f; p.lut_std[i] = 1.f; }
   for (int i = 0; i < 32; ++i) p.lut_of[i] = 0;
@@ -469,11 +504,13 @@ const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h
     }
     p.lut_of[c] = (unsigned char)k;
   }
-  const Conv1Schedule s = make_schedule(p.n_chunks);
+  const Conv1Schedule s = make_schedule(cin);
   p.n_mma = s.plan.n_mma;
-  for (int i = 0; i < kF1MaxMma; ++i) p.a_delta[i] = i < p.n_mma ? s.a_delta[i] : 0ull;
+  p.n_full = s.n_full; p.has_pair = s.has_pair;
+  for (int i = 0; i < kF1MaxMma; ++i) p.a_off16[i] = i < p.n_mma ? s.a_off16[i] : 0u;
   p.w_packed = static_cast<const __nv_bfloat16*>(w_fused);
   p.bias = bias;
+  p.dbg = conv_get_debug_counters();
   const int tiles_w = kF1Crop / kF1TileW, tiles_h = kF1Crop / kF1TileH;
   p.total_tiles = n * tiles_w * tiles_h;
   p.div_w = FastDiv::make((uint32_t)tiles_w);
@@ -493,16 +530,16 @@ const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h
   }
   const bool rep32 = img_c == 1 && p.n_luts == 1;
   const int rep = rep32 ? 32 : 1;
-  const size_t smem = 1024 + 4 * kF1StagingBytes + (size_t)p.n_mma * 2048 + (size_t)kF1Stages * p.n_chunks * kF1PlaneBytes +
-                      (size_t)p.n_luts * 256 * rep * 2 + 64 * 4 + (2 * kF1Stages + 4) * 8 + 16;
+  const size_t smem = 1024 + 4 * kF1StagingBytes + (size_t)p.n_mma * 2048 + (size_t)kF1Stages * (p.n_full + p.has_pair) * kF1PlaneBytes +
+                      (size_t)p.n_luts * 256 * rep * 2 + 64 * 4 + 32 * 8 + 8 + (2 * kF1Stages + 4) * 8 + 16;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  // ROUNDS = items per gather thread: 18 rows x planes (x 5 two-pixel segments for RGB) over 128 threads
-  if (img_c == 3) return launch_fused<3, 2, 1, 1>(tO, p, grid, smem, st);
-  if (planes <= 21) return rep32 ? launch_fused<1, 10, 32, 3>(tO, p, grid, smem, st) : launch_fused<1, 10, 1, 3>(tO, p, grid, smem, st);
-  return rep32 ? launch_fused<1, 10, 32, 5>(tO, p, grid, smem, st) : launch_fused<1, 10, 1, 5>(tO, p, grid, smem, st);
+  // MAXCH = channel registers per gather thread (multiple of 16)
+  if (img_c == 3) return launch_fused<3, 16, 1>(tO, p, grid, smem, st);
+  if (planes <= 16) return rep32 ? launch_fused<1, 16, 32>(tO, p, grid, smem, st) : launch_fused<1, 16, 1>(tO, p, grid, smem, st);
+  return rep32 ? launch_fused<1, 32, 32>(tO, p, grid, smem, st) : launch_fused<1, 32, 1>(tO, p, grid, smem, st);
 }
 
 }  // namespace va

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __rest
 
 static long long* g_dbg_counters = nullptr;
 void conv_set_debug_counters(long long* dev_buf) { g_dbg_counters = dev_buf; }
+long long* conv_get_debug_counters() { return g_dbg_counters; }
 
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   cudaStream_t st_ = st;

@@ -86,6 +86,7 @@ constexpr int kSplitK = 8;
 // static/thread-local error string.
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st);
 void conv_set_debug_counters(long long* dev_buf);
+long long* conv_get_debug_counters();
 
 // ---- fused snippet gather + conv1_1 (va_conv1_fused.cu)
 bool conv1_fused_supported(int planes, int img_c, int crop);
