@@ -328,8 +328,10 @@ def main(args, embedded=False):
                        "lr": args.lr, "lr_note": "the reference's 0.1 diverges within a few steps on random-init weights and noise "
                                                  "frames (its runs start from ImageNet weights); the arithmetic per step does not depend on lr",
                        "batch_per_gpu_per_stream": B, "global_batch": world * B,
-                       "parallelism": f"data parallel x{world}: one NCCL all-reduce per stream per step over the flat gradient arena "
-                                      f"({tr_s.flat_grad.numel() * 4 / 1e6:.0f} + {tr_t.flat_grad.numel() * 4 / 1e6:.0f} MB)",
+                       "parallelism": f"data parallel x{world}: NCCL all-reduce of the flat gradient arena per stream per step, "
+                                      f"{tr_s.grad_allreduce_dtype} payload ({tr_s.flat_grad.numel() * (2 if tr_s.grad_allreduce_dtype == 'bf16' else 4) / 1e6:.0f}"
+                                      f" + {tr_t.flat_grad.numel() * (2 if tr_t.grad_allreduce_dtype == 'bf16' else 4) / 1e6:.0f} MB), classifier slice "
+                                      "launched as soon as its gradients exist",
                        "l2_policy": "inputs larger than L2: activations of one step are several GB",
                        "weights": "random init (seed 0) of the reference architecture, fp32 master copies",
                        "loss_first_step": loss_first, "loss_last_step": loss_last},

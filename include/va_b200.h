@@ -179,7 +179,8 @@ va_status va_pack_input_nchw_split6(const float* x_nchw, int n, int channels, in
  *   va_transpose_bf16    : [n][A][B] -> [n][B][A] (NHWC <-> the reference's NCHW flatten order in front of FC1)
  *   va_relu_bwd_f32_to_bf16, va_f32_to_bf16 : glue between the fp32 descriptor layer and the bf16 stack
  *   va_sgd_momentum      : buf = g (first step) | momentum*buf + g;  p -= lr*buf   (grad_scale multiplies g first,
- *                          e.g. 1/world_size after a gradient all-reduce)
+ *                          e.g. 1/world_size after a gradient all-reduce); va_sgd_momentum_bf16g reads the gradient as
+ *                          bf16 (the compressed all-reduce payload of the data-parallel step, 270 MB instead of 541 MB)
  * --------------------------------------------------------------------------------------------------------- */
 va_status va_maxpool2x2_nhwc(const void* x, int n, int H, int W, int C, void* y, void* codes, va_stream_t stream);
 va_status va_pool_bwd_codes(const void* dout, const void* codes, int n, int H, int W, int C, void* dZ, float* db,
@@ -200,6 +201,8 @@ va_status va_ce_train(const float* x, const float* w4, const float* b4, const in
 va_status va_relu_bwd_f32_to_bf16(const float* dy, const float* y, long long n, void* dz, va_stream_t stream);
 va_status va_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                           int first_step, float grad_scale, va_stream_t stream);
+va_status va_sgd_momentum_bf16g(float* param, const void* grad_bf16, float* momentum_buf, long long n, float lr, float momentum,
+                                int first_step, float grad_scale, va_stream_t stream);
 va_status va_transpose_bf16(const void* x, int n, int A, int B, void* y, va_stream_t stream);
 va_status va_f32_to_bf16(const float* x, long long n, void* y, va_stream_t stream);
 

@@ -47,8 +47,27 @@ def main():
     same = bool(torch.equal(mine, tr.flat_param))
     flag = torch.tensor([1 if same else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    # replicas built from DIFFERENT seeds per rank must come out identical (StreamTrainer.sync_replicas broadcasts rank 0's)
+    tr2 = StreamTrainer(build_spatial_torch_model(101, 256, seed=100 + rank), None, lr=0.01, momentum=0.9, c_pad=16,
+                        process_group=dist.group.WORLD, grad_allreduce_dtype="fp32")
+    p0 = tr2.flat_param.clone()
+    dist.broadcast(p0, src=0)
+    synced = torch.tensor([1 if torch.equal(p0, tr2.flat_param) else 0], device="cuda")
+    dist.all_reduce(synced, op=dist.ReduceOp.MIN)
+    # the bf16 gradient payload (default) against the exact fp32 payload: same data, same start -> the parameter UPDATE differs
+    # by bf16 rounding of the summed gradients only
+    tr3 = StreamTrainer(build_spatial_torch_model(101, 256, seed=100), None, lr=0.01, momentum=0.9, c_pad=16,
+                        process_group=dist.group.WORLD, grad_allreduce_dtype="bf16")
+    before = tr2.flat_param.clone()
+    args = (x_all[sl].cuda(), labels_all[sl].cuda(), [m[sl].contiguous().cuda() for m in masks_all])
+    tr2.step(*args)
+    tr3.step(*args)
+    d32, d16 = tr2.flat_param - before, tr3.flat_param - before
+    rel16 = float((d16 - d32).norm() / d32.norm())
     if rank == 0:
-        print(("DDP_OK" if ok and int(flag) == 1 else "DDP_FAIL"), f"world={world} params_identical={bool(int(flag))}")
+        good = ok and int(flag) == 1 and int(synced) == 1 and rel16 < 1e-2
+        print(("DDP_OK" if good else "DDP_FAIL"), f"world={world} params_identical={bool(int(flag))} replicas_synced={bool(int(synced))} "
+              f"bf16_vs_fp32_update_rel={rel16:.3e}")
     dist.destroy_process_group()
 
 

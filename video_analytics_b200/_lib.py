@@ -49,6 +49,7 @@ SIGNATURES = {
     "va_ce_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "va_relu_bwd_f32_to_bf16": (_i, [_vp, _vp, C.c_longlong, _vp, _vp]),
     "va_sgd_momentum": (_i, [_vp, _vp, _vp, C.c_longlong, _f, _f, _i, _f, _vp]),
+    "va_sgd_momentum_bf16g": (_i, [_vp, _vp, _vp, C.c_longlong, _f, _f, _i, _f, _vp]),
     "va_transpose_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "va_f32_to_bf16": (_i, [_vp, C.c_longlong, _vp, _vp]),
     "va_jpeg_decode": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),

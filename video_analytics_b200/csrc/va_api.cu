@@ -601,6 +601,14 @@ va_status va_sgd_momentum(float* param, const float* grad, float* momentum_buf, 
                                   static_cast<cudaStream_t>(stream)));
   return VA_OK;
 }
+va_status va_sgd_momentum_bf16g(float* param, const void* grad_bf16, float* momentum_buf, long long n, float lr, float momentum,
+                                int first_step, float grad_scale, va_stream_t stream) {
+  if (!param || !grad_bf16 || !momentum_buf) return fail(VA_ERR_INVALID, "va_sgd_momentum_bf16g: NULL argument");
+  if (va_status s = require_sm100()) return s;
+  VA_CUDA(va::launch_sgd_momentum_bf16g(param, grad_bf16, momentum_buf, n, lr, momentum, first_step, grad_scale,
+                                        static_cast<cudaStream_t>(stream)));
+  return VA_OK;
+}
 va_status va_transpose_bf16(const void* x, int n, int A, int B, void* y, va_stream_t stream) {
   if (!x || !y) return fail(VA_ERR_INVALID, "va_transpose_bf16: NULL argument");
   if (n > 65535) return fail(VA_ERR_INVALID, "va_transpose_bf16: n must be <= 65535");

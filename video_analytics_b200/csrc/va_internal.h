@@ -48,6 +48,8 @@ cudaError_t launch_nhwc_to_nchw_bf16(const void* x, void* y, int n, int H, int W
 cudaError_t launch_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t st);
 cudaError_t launch_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, int first_step,
                                 float grad_scale, cudaStream_t st);
+cudaError_t launch_sgd_momentum_bf16g(float* p, const void* g_bf16, float* buf, long long n, float lr, float momentum,
+                                      int first_step, float grad_scale, cudaStream_t st);
 cudaError_t launch_ce_train(const float* x, const float* w4, const float* b4, const int64_t* labels, int n, int D, int C,
                             float* logits, float* dlogits, float* loss, float* dw4, float* db4, float* dx, cudaStream_t st);
 cudaError_t launch_relu_bwd_f32_to_bf16(const float* dy, const float* y, void* dz, long long n, cudaStream_t st);

@@ -294,13 +294,28 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------ SGD with momentum
 // torch.optim.SGD(lr, momentum, dampening=0, nesterov=False, weight_decay=0): buf = g (first step) or m*buf + g;
 // p -= lr * buf   (reference spatialModel.py:116,181)
-__global__ void __launch_bounds__(256) sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g,
+// GT = float (exact gradients) or __nv_bfloat16 (the all-reduced bf16 payload of the data-parallel step).
+template <typename GT>
+__device__ __forceinline__ float4 load_grad4(const GT* g, long long i4);
+template <>
+__device__ __forceinline__ float4 load_grad4<float>(const float* g, long long i4) { return *reinterpret_cast<const float4*>(g + i4); }
+template <>
+__device__ __forceinline__ float4 load_grad4<__nv_bfloat16>(const __nv_bfloat16* g, long long i4) {
+  const uint2 r = *reinterpret_cast<const uint2*>(g + i4);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x), b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ float grad1(const float* g, long long i) { return g[i]; }
+__device__ __forceinline__ float grad1(const __nv_bfloat16* g, long long i) { return __bfloat162float(g[i]); }
+
+template <typename GT>
+__global__ void __launch_bounds__(256) sgd_momentum_kernel(float* __restrict__ p, const GT* __restrict__ g,
                                                            float* __restrict__ buf, long long n, float lr, float momentum,
                                                            int first_step, float grad_scale) {
   // four elements per thread (16-byte accesses: the arenas are 256-byte aligned); scalar tail
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 + 3 < n) {
-    const float4 gv = *reinterpret_cast<const float4*>(g + i4);
+    const float4 gv = load_grad4<GT>(g, i4);
     float4 pv = *reinterpret_cast<float4*>(p + i4);
     float4 bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(buf + i4);
     const float ge[4] = {gv.x * grad_scale, gv.y * grad_scale, gv.z * grad_scale, gv.w * grad_scale};
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(256) sgd_momentum_kernel(float* __restrict__ p
     *reinterpret_cast<float4*>(p + i4) = make_float4(pe[0], pe[1], pe[2], pe[3]);
   } else {
     for (long long i = i4; i < n; ++i) {
-      const float gi = g[i] * grad_scale;
+      const float gi = grad1(g, i) * grad_scale;
       const float b = first_step ? gi : fmaf(momentum, buf[i], gi);
       buf[i] = b;
       p[i] = fmaf(-lr, b, p[i]);
@@ -533,7 +548,15 @@ cudaError_t launch_sgd_momentum(float* p, const float* g, float* buf, long long 
                                 float grad_scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   count_launch();
-  sgd_momentum_kernel<<<nblk((n + 3) / 4), 256, 0, st>>>(p, g, buf, n, lr, momentum, first_step, grad_scale);
+  sgd_momentum_kernel<float><<<nblk((n + 3) / 4), 256, 0, st>>>(p, g, buf, n, lr, momentum, first_step, grad_scale);
+  return cudaGetLastError();
+}
+cudaError_t launch_sgd_momentum_bf16g(float* p, const void* g_bf16, float* buf, long long n, float lr, float momentum,
+                                      int first_step, float grad_scale, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  count_launch();
+  sgd_momentum_kernel<__nv_bfloat16><<<nblk((n + 3) / 4), 256, 0, st>>>(p, static_cast<const __nv_bfloat16*>(g_bf16), buf, n, lr,
+                                                                        momentum, first_step, grad_scale);
   return cudaGetLastError();
 }
 cudaError_t launch_ce_train(const float* x, const float* w4, const float* b4, const int64_t* labels, int n, int D, int C,

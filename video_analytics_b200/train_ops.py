@@ -181,6 +181,19 @@ def sgd_momentum_(param: torch.Tensor, grad: torch.Tensor, buf: torch.Tensor, *,
     """In place torch.optim.SGD(lr, momentum) update (dampening 0, no nesterov, no weight decay;
     reference spatialModel.py:116)."""
     _need_cuda(param, grad, buf)
-    assert param.dtype == grad.dtype == buf.dtype == torch.float32 and param.numel() == grad.numel() == buf.numel()
+    assert param.dtype == buf.dtype == torch.float32 and param.numel() == grad.numel() == buf.numel()
+    if grad.dtype == torch.bfloat16:         # the compressed payload of a data-parallel gradient all-reduce
+        check(_lib.load().va_sgd_momentum_bf16g(ptr(param), ptr(grad), ptr(buf), param.numel(), lr, momentum, int(first_step),
+                                                grad_scale, stream_ptr()), "va_sgd_momentum_bf16g")
+        return
+    assert grad.dtype == torch.float32
     check(_lib.load().va_sgd_momentum(ptr(param), ptr(grad), ptr(buf), param.numel(), lr, momentum, int(first_step),
                                       grad_scale, stream_ptr()), "va_sgd_momentum")
+
+
+def f32_to_bf16_(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Cast into a caller-owned bf16 buffer of the same numel."""
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.numel() == out.numel()
+    check(_lib.load().va_f32_to_bf16(ptr(x), x.numel(), ptr(out), stream_ptr()), "va_f32_to_bf16")
+    return out
