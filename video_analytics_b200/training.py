@@ -41,7 +41,8 @@ class StreamTrainer:
     """Owns the flat parameter / gradient / momentum arenas of one stream and runs training steps on them."""
 
     def __init__(self, module: torch.nn.Module, optimizer: Optional[torch.optim.SGD] = None, *, lr: float = 0.1,
-                 momentum: float = 0.9, c_pad: int = 16, process_group=None, grad_allreduce_dtype: str = "bf16"):
+                 momentum: float = 0.9, c_pad: int = 16, process_group=None, grad_allreduce_dtype: str = "bf16",
+                 overlap_allreduce: Optional[bool] = None):
         """module: the (unwrapped) torchvision-layout VGG16 with the swapped classifier (parameter container only).
         optimizer: the torch.optim.SGD over module.parameters(); its lr / momentum are read at every step (so a
         MultiStepLR scheduler keeps working) and its momentum buffers are re-pointed at the arena."""
@@ -58,6 +59,15 @@ class StreamTrainer:
         if grad_allreduce_dtype not in ("bf16", "fp32"):
             raise VAError("grad_allreduce_dtype must be 'bf16' or 'fp32'")
         self.grad_allreduce_dtype = grad_allreduce_dtype
+        # overlap_allreduce=True launches the classifier slice's collective in the middle of the backward pass.  The layer
+        # kernels are PERSISTENT with one CTA per SM: while NCCL's CTAs hold some SMs, a layer kernel's last CTAs start only
+        # after others finish and that layer takes up to twice as long -- measured at N = 2: 50.1-50.4 ms per step against
+        # 48.1 ms at N = 1, whatever the payload size.  Default (None -> VA_OVERLAP_ALLREDUCE env, else False): ONE collective
+        # over the whole arena after the backward pass -- exposed, but only for the time the bytes take.
+        if overlap_allreduce is None:
+            import os
+            overlap_allreduce = os.environ.get("VA_OVERLAP_ALLREDUCE", "0") == "1"
+        self.overlap_allreduce = bool(overlap_allreduce)
         sd = dict(self.module.named_parameters())
         missing = [k for k in STATE_DICT_KEYS if k not in sd]
         if missing:
@@ -258,12 +268,12 @@ class StreamTrainer:
         pending = []
         split = self.offsets[26]               # first classifier tensor (state_dict order: 13 conv pairs, then 4 FC pairs)
         hook = None
-        if self.group is not None:
+        if self.group is not None and self.overlap_allreduce:
             def hook():
                 pending.append(self._allreduce_async(split, self.flat_grad.numel()))
         loss, feat, logits = self.forward_backward(x_nhwc, labels, masks, on_classifier_grads=hook)
         if self.group is not None:
-            pending.append(self._allreduce_async(0, split))
+            pending.append(self._allreduce_async(0, split if self.overlap_allreduce else self.flat_grad.numel()))
         self.apply_update(pending)
         return loss, feat, logits
 
