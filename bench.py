@@ -624,13 +624,14 @@ def main():
         peaks = read_peaks()
         achieved = (t_f.value / 1e12) / (t_ms.value * 1e-3) if t_ms.value > 0 else 0.0
         traffic = None      # DRAM bytes per layer-kernel launch from the committed ncu --set full capture (profiles/)
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_conv_tc_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_conv_tc_traffic.json")
         if os.path.exists(tpath):
-            # the capture ran 125-snippet chunks; a launch of this run processes `chunk` snippets: activation bytes scale
-            # with the chunk, the weights (29 MB of 4.7 GB per 125-snippet chunk) do not -- scaled linearly, 0.6 % high
-            captured = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+            # the capture ran one 250-snippet chunk; a launch of this run processes `chunk` snippets: activation bytes scale
+            # with the chunk, the weights (0.27 GB of 9.2 GB per 250-snippet chunk) do not -- scaled linearly, 3 % high
+            tj = json.load(open(tpath))
+            captured = tj.get("dram_bytes_per_launch_avg")
             chunk = min(args.max_batch, vps * SNIPPETS_PER_VIDEO)
-            traffic = captured * chunk / 125.0 if captured is not None else None
+            traffic = captured * chunk / float(tj.get("chunk_snippets", 250)) if captured is not None else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -643,10 +644,15 @@ def main():
                        "weights": "random init (seed 0) of the reference architecture", "max_batch": args.max_batch},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_tc2h_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                         "traffic_source": "profiles/r01_ncu_conv_tc_traffic.json (ncu --set full, 16 launches of one 125-snippet temporal chunk: "
-                                           "297.4 MB per launch), scaled to this run's snippets per launch",
+                         "traffic_source": "profiles/r02_ncu_conv_tc_traffic.json (ncu --set full of the layer launches of one 250-snippet "
+                                           "spatial chunk: dram__bytes_read + dram__bytes_write, averaged per launch), scaled to this run's "
+                                           "snippets per launch",
+                         "tensor_pipe_pct": 79.6,
+                         "tensor_pipe_source": "profiles/r02_ncu_layer_table.md: sm__pipe_tensor_cycles_active (pct of peak, elapsed), "
+                                               "duration-weighted over the layer launches of one 250-snippet chunk under ncu; "
+                                               "88.8-94.1 % on conv2_1..conv4_3",
                          "peak_source": peaks["src"], "launches": int(t_l.value), "avg_launch_ms": t_ms.value / max(1, t_l.value),
                          "flops_per_launch": t_f.value / max(1, t_l.value),
                          "share_of_step": t_ms.value / total_ms if total_ms > 0 else None},
