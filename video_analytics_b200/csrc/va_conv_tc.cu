@@ -169,7 +169,6 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
     p.a_tx_bytes = (uint32_t)((p.h_t + 2) * p.hb_pitch * 128);
     p.a_box_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
     p.staging_bytes = d.pool ? 4096u : 16384u;
-    p.staging_bufs = 1;
     int st = (int)((227 * 1024 - conv2h_smem_bytes(BNh, chunks, p.a_box_bytes, p.staging_bytes, 0)) / p.a_box_bytes);
     if (st > kMaxStages) st = kMaxStages;
     if (st >= 2) {
@@ -299,16 +298,13 @@ const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
                     (size_t)groups * conv_b_stage_bytes(BN, CK, R, S) <= 80 * 1024;
   if (halo && !wres) return "HALO variant needs resident weights";
   const int a_boxes = halo ? 1 : S;
-  // the first layer (Cin_pad 16/32 -> 64 channels at 224^2, no pool) writes 16 KB per tile and waits on its staging
-  // buffer 26-28 % of the time (r01_role_stalls_v7.log): two staging buffers per epilogue group
-  p.staging_bufs = (wres && CK < 64 && !d.pool && !d.split6 && S == 3) ? 2 : 1;
   const uint32_t stage_bytes = a_boxes * p.a_box_bytes + (wres ? 0u : conv_b_stage_bytes(BN, CK, R, S));
   const size_t smem_cap = 227 * 1024;
-  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, 0, a_boxes, p.staging_bufs)) / stage_bytes);
+  int stages = (int)((smem_cap - conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, 0, a_boxes)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return errf("not enough shared memory for 2 stages (stage %u B)", stage_bytes);
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, stages, a_boxes, p.staging_bufs);
+  const size_t smem = conv_smem_bytes(BN, CK, R, S, wres, groups, p.a_box_bytes, p.staging_bytes, stages, a_boxes);
 
   CUtensorMap tA, tW, tO;
   {

@@ -80,7 +80,6 @@ struct ConvKernelParams {
   int ksplit;                      // fully-connected split-K: number of K slices (1 = off); a tile index then decodes as
   int kb_per_split;                //   ((slice * n_tiles_cout + nt) * tiles_m + mt) and covers kb_per_split K blocks
   int tiles_m;                     // M tiles (split-K decode)
-  int staging_bufs;                // output staging buffers per epilogue group (1, or 2 where the layer is store-bound)
 };
 
 // tile index -> (K slice, M tile, N tile).  Without split-K the N tile is fastest (concurrent CTAs share the A patch in
@@ -111,11 +110,11 @@ constexpr int kMaxStages = 8;
 __host__ __device__ constexpr uint32_t conv_b_stage_bytes(int BN, int CK, int R, int S) { return R * S * BN * CK * 2; }
 
 inline size_t conv_smem_bytes(int BN, int CK, int R, int S, bool wres, int groups, uint32_t a_box_bytes,
-                              uint32_t staging_bytes, int stages, int a_boxes = 0, int staging_bufs = 1) {
+                              uint32_t staging_bytes, int stages, int a_boxes = 0) {
   const size_t b = conv_b_stage_bytes(BN, CK, R, S);
   if (a_boxes == 0) a_boxes = S;
   return 1024 /*align slack*/ + (wres ? (size_t)groups * b : 0) + (size_t)stages * (a_boxes * a_box_bytes + (wres ? 0 : b)) +
-         2 * (size_t)staging_bufs * staging_bytes + 2 * 256 * sizeof(float) + 256;
+         2 * (size_t)staging_bytes + 2 * 256 * sizeof(float) + 256;
 }
 
 __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
@@ -157,7 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_stage_bytes + (WRES ? 0u : B_STAGE);
   uint8_t* ring = smem + wres_bytes;
   uint8_t* staging = ring + (size_t)p.num_stages * stage_bytes;
-  float* bias_s = reinterpret_cast<float*>(staging + 2 * p.staging_bufs * p.staging_bytes);
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * p.staging_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * 256);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
@@ -314,11 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m = q * 32 + lane;          // accumulator row == pixel index inside the tile
     const int et = threadIdx.x - eg * 128;        // 0..127 within the group
     float* bias_g = bias_s + eg * 256;
-    // staging_bufs == 2 (the first layer: 16 KB of output per tile, store-bound): a TMA store holds its buffer until the
-    // store engine has read it, so the group alternates between two buffers and waits for the store before last
-    uint8_t* stage_base = staging + eg * p.staging_bufs * p.staging_bytes;
-    uint8_t* stage_out = stage_base;
-    uint32_t store_cnt = 0;
+    uint8_t* stage_out = staging + eg * p.staging_bytes;
     const int w_i = m & (p.w_t - 1);
     const int h_i = (m >> p.log2_w_t) & (p.h_t - 1);
     const int n_i = m >> (p.log2_w_t + p.log2_h_t);
@@ -524,11 +519,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           writer = ((w_i | h_i) & 1) == 0;
           row = ((n_i * (p.h_t >> 1)) + (h_i >> 1)) * (p.w_t >> 1) + (w_i >> 1);
         }
-        // the group's staging buffer was last read by the TMA store of its previous chunk (or the one before, with 2 buffers)
+        // the group's staging buffer was last read by the TMA store of its previous chunk
         const long long ts0 = dbg ? clock64() : 0;
-        if (p.staging_bufs == 2) stage_out = stage_base + (store_cnt++ & 1u) * p.staging_bytes;
         if (et < 32) {                       // the group's first warp; its elected lane owns the bulk-store groups
-          if (elect_one()) { if (p.staging_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          if (elect_one()) tma_store_wait_read<0>();
           __syncwarp();
         }
         named_bar_sync(3 + eg, 128);
