@@ -363,3 +363,39 @@ def test_temporal_batch64_configs1_vs_oracle(world):
         assert perr < SCORE_RTOL and derr < DESC_RTOL, (perr, derr)
         assert bool(agree[decidable].all())
     net.close()
+
+
+def test_fuse_with_svm_fitted_on_fewer_classes_than_scores():
+    """The SVM has one row per class it was FITTED on (LinearSVC: len(np.unique(y)), 25 on mini-UCF-101), the networks score
+    101 classes: va_fuse takes the two counts separately (round-1 ADVICE: it read svm_w out of bounds)."""
+    from video_analytics_b200 import ops
+    from video_analytics_b200._lib import VAError
+    g = torch.Generator().manual_seed(8)
+    V, n, D, C, Csvm = 3, 4, 256, 101, 25
+    ds, dt = torch.rand(V * n, D, generator=g).cuda(), torch.rand(V * n, D, generator=g).cuda()
+    ss, st = torch.softmax(torch.randn(V * n, C, generator=g), 1).cuda(), torch.softmax(torch.randn(V * n, C, generator=g), 1).cuda()
+    offs = torch.arange(0, (V + 1) * n, n, dtype=torch.int32).cuda()
+    W = torch.randn(Csvm, 2 * D, generator=g, dtype=torch.float64).cuda()
+    b = torch.randn(Csvm, generator=g, dtype=torch.float64).cuda()
+    res = ops.fuse(ds, dt, ss, st, offs, svm_w=W, svm_b=b)
+    assert res["svm_scores"].shape == (V, Csvm) and res["video_scores"].shape == (V, C)
+    X = res["video_desc"].double()
+    want = X @ W.t() + b
+    assert torch.allclose(res["svm_scores"], want, rtol=1e-12, atol=1e-12)
+    assert torch.equal(res["svm_pred"].long(), want.argmax(1)) and int(res["svm_pred"].max()) < Csvm
+    with pytest.raises(VAError):
+        ops.fuse(ds, dt, ss, st, offs, svm_w=W[:, :100].contiguous(), svm_b=b)          # wrong descriptor width
+    with pytest.raises(VAError):
+        ops.fuse(ds, dt, ss, st, offs, svm_w=W, svm_b=b[:3].contiguous())               # intercepts do not match the rows
+
+
+def test_combined_model_predict_scores_fp64_rows():
+    """CombinedModel.predict keeps the fp64 values pandas reads from the CSVs (round 1 cast them to fp32 first)."""
+    from video_analytics_b200.combinedModel import CombinedModel
+    rng = np.random.default_rng(4)
+    W, b = rng.normal(size=(5, 512)), rng.normal(size=5)
+    X = rng.normal(size=(7, 512)) * (1 + 1e-9 * rng.normal(size=(7, 512)))             # not representable in fp32
+    cm = CombinedModel().set_svm(W, b, np.arange(10, 15))
+    scores = cm.decision_function(X).cpu().numpy()
+    assert np.allclose(scores, X @ W.T + b, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(cm.predict(X), np.arange(10, 15)[(X @ W.T + b).argmax(1)])

@@ -212,3 +212,25 @@ def test_data_parallel_gradients_two_gpus():
                         "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_train_ddp.py")],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert "DDP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_labels_out_of_range_are_rejected():
+    """torch's CrossEntropyLoss raises on a target outside [0, C) (the reference's 1-based ids reach C = 101 with all
+    classes in use); the trainer validates host labels before upload and the kernel answers device labels with NaN."""
+    from video_analytics_b200 import train_ops as T
+    from video_analytics_b200._lib import VAError
+    from video_analytics_b200.spatialModel import build_spatial_torch_model
+    from video_analytics_b200.training import StreamTrainer
+    tr = StreamTrainer(build_spatial_torch_model(101, 256, seed=1), None, c_pad=16)
+    x = torch.zeros(2, 224, 224, 16, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(VAError):
+        tr.forward_backward(x, torch.tensor([3, 101]))
+    with pytest.raises(VAError):
+        tr.forward_backward(x, torch.tensor([-1, 5]))
+    g = torch.Generator().manual_seed(2)
+    feat = torch.rand(2, 256, generator=g).cuda()
+    w4, b4 = torch.randn(101, 256, generator=g).cuda() * 0.05, torch.zeros(101).cuda()
+    ce = T.ce_train(feat, w4, b4, torch.tensor([7, 101]).cuda())
+    torch.cuda.synchronize()
+    assert torch.isnan(ce["loss"]).all()
+    assert float(ce["dlogits"][1].abs().max()) == 0.0 and float(ce["dlogits"][0].abs().max()) > 0.0

@@ -261,3 +261,15 @@ def test_training_flop_accounting_matches_survey():
     assert int(ft) + 2 * 256 * 101 == 31_917_132_288
     first_s, first_t = 2.0 * 224 * 224 * 64 * 9 * 3, 2.0 * 224 * 224 * 64 * 9 * 20
     assert bs == 2 * fs - first_s and bt == 2 * ft - first_t
+
+
+def test_flow_starts_reject_videos_shorter_than_a_stack():
+    """reference temporalModel.py:79 `random.randint(1, nFlows - L)` raises ValueError for nFlows <= L; the protocol
+    helper does too instead of returning start 0 (an image id before the video's first flow image)."""
+    import pytest
+    from video_analytics_b200.utils import test_flow_starts as flow_starts
+    assert flow_starts(11, 10) == [1] * 25
+    assert flow_starts(35, 10)[0] == 1 and flow_starts(35, 10)[-1] == 25
+    for n in (10, 5, 0):
+        with pytest.raises(ValueError):
+            flow_starts(n, 10)
