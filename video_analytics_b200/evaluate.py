@@ -212,14 +212,16 @@ class TwoStreamEvaluator:
             issue(gi)
         for gi in range(len(groups)):
             slot = gi % depth
-            if gi + depth - 1 < len(groups):
-                issue(gi + depth - 1)                 # its copies run under this group's networks
             ts, tt, nb = pending.pop(gi)
             cur.wait_event(self._copied[slot])
             ts.record_stream(cur)
             tt.record_stream(cur)
             res = self.run_tables(ts, tt, len(groups[gi]), store=self._stages[slot])
             self._consumed[slot].record(cur)
+            # the next group's ~150 copy calls are issued AFTER this group's kernels are queued: the host spends ~0.5 ms on
+            # them, which would otherwise be GPU idle time right after the caller's per-step synchronisation
+            if gi + depth - 1 < len(groups):
+                issue(gi + depth - 1)                 # its copies run under this group's networks
             self.last_h2d_bytes = nb
             yield res
 
