@@ -254,6 +254,41 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
                      double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
                      va_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * TV-L1 optical-flow producer.  Produces the `flow_x_%04d` / `flow_y_%04d` images that
+ * TemporalDataset.__getitem__ opens (reference temporalModel.py:76-86; parameters.py:27,38-39 -- the reference only
+ * consumes them, the TSN `dense_flow` tool that wrote `..._flow_img_tvl1_gpu` is third-party): per frame pair, grey
+ * conversion (cv::cvtColor BGR2GRAY), Zach/Pock/Bischof TV-L1 with OpenCV's CUDA structure and defaults, then the 8-bit
+ * mapping of [-bound, bound] to [0, 255].  The arithmetic contract is oracle/tvl1.py (separately rounded fp32 operations;
+ * the kernel is bit-identical to it).  One 16-CTA thread-block cluster solves one pair entirely on chip.
+ *   images:     u8 store as for va_preprocess, image `id` at images + id*image_bytes, [img_h][img_w][img_c], img_c 1 or 3 (RGB)
+ *   pair_table: DEVICE int32 [n][4] = {id of frame t-1, id of frame t, OUTPUT id of the x image, OUTPUT id of the y image};
+ *               output image `k` is written as u8 [img_h][img_w] at out_images + k*out_image_bytes
+ *   params:     HOST struct, NULL = the defaults below
+ *   flow_f32:   optional fp32 [n][2][img_h][img_w] (x then y displacement); iterations: optional int32
+ *               [n][nscales_used*warps] inner iterations run per (level, warp) in processing order (coarsest level first)
+ *   workspace:  DEVICE scratch of va_tvl1_workspace_bytes(img_h, img_w, params) bytes
+ * Limits: img_w <= 704 and ceil(img_h/16) * img_w <= 5504 (the on-chip band capacity: 340x256 and 320x240 fit);
+ * anything larger returns VA_ERR_UNSUPPORTED.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct va_tvl1_params {
+  double tau;          /* 0.25 */
+  double lambda;       /* 0.15 */
+  double theta;        /* 0.3  */
+  double epsilon;      /* 0.01 */
+  double scale_step;   /* 0.8  */
+  double bound;        /* 20: dense_flow / TSN --bound */
+  int nscales;         /* 5 */
+  int warps;           /* 5 */
+  int iterations;      /* 300 */
+  int reserved;
+} va_tvl1_params;
+size_t va_tvl1_workspace_bytes(int img_h, int img_w, const va_tvl1_params* params);
+va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
+                       const int32_t* pair_table, int n, const va_tvl1_params* params, uint8_t* out_images,
+                       size_t out_image_bytes, float* flow_f32, int32_t* iterations, void* workspace,
+                       size_t workspace_bytes, va_stream_t stream);
+
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,

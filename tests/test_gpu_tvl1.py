@@ -1,0 +1,118 @@
+"""GPU parity of the TV-L1 flow producer (va_tvl1_flow) against oracle/tvl1.py: BIT-exact u8 images,
+fp32 flow and iteration counts (every fp32 operation of the kernel is the oracle's separately rounded IEEE operation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tvl1 as otv
+from video_analytics_b200 import flow
+from video_analytics_b200._lib import VAError
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pair(f0, f1, p):
+    g0 = otv.gray_from_rgb(f0) if f0.shape[-1] == 3 else f0[..., 0]
+    g1 = otv.gray_from_rgb(f1) if f1.shape[-1] == 3 else f1[..., 0]
+    op = otv.TVL1Params(p.tau, p.lambda_, p.theta, p.nscales, p.warps, p.epsilon, p.iterations, p.scale_step, p.bound)
+    u1, u2, st = otv.tvl1_flow(g0, g1, op, return_stats=True)
+    return u1, u2, st, otv.flow_to_u8(u1, p.bound), otv.flow_to_u8(u2, p.bound)
+
+
+def _run(clip, p, pairs=None):
+    dev = torch.device("cuda")
+    n, h, w, c = clip.shape
+    frames = torch.from_numpy(clip).to(dev)
+    if pairs is None:
+        pairs = [(k, k + 1) for k in range(n - 1)]
+    m = len(pairs)
+    table = torch.tensor([[a, b, k, k + m] for k, (a, b) in enumerate(pairs)], dtype=torch.int32, device=dev)
+    out = torch.full((2 * m, h, w), 7, dtype=torch.uint8, device=dev)
+    res = flow.tvl1(frames, (h, w, c), table, out, params=p, return_flow=True, return_iterations=True)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), res["flow"].cpu().numpy(), res["iterations"].cpu().numpy()
+
+
+@pytest.mark.parametrize("shape,channels,seed", [((48, 64), 3, 11), ((77, 100), 1, 12), ((33, 41), 3, 13), ((96, 128), 3, 14)])
+def test_bit_exact_vs_oracle_small(shape, channels, seed):
+    p = flow.TVL1Params()
+    clip = flow.synthetic_clip(3, shape[0], shape[1], seed=seed, channels=channels, velocity=(1.2, -0.6), object_velocity=(-1.5, 0.8))
+    out, fl, its = _run(clip, p)
+    for k in range(2):
+        u1, u2, st, qx, qy = _oracle_pair(clip[k], clip[k + 1], p)
+        assert list(its[k][:len(st)]) == st, (k, list(its[k]), st)
+        assert np.array_equal(fl[k, 0], u1) and np.array_equal(fl[k, 1], u2), float(np.abs(fl[k, 0] - u1).max())
+        assert np.array_equal(out[k], qx) and np.array_equal(out[2 + k], qy)
+
+
+def test_golden_fixture(golden):
+    g = golden("tvl1_small.npz")
+    p = flow.TVL1Params()
+    out, fl, its = _run(g["clip_a"], p)
+    for k in range(2):
+        assert np.array_equal(fl[k, 0], g[f"a{k}_u1"]) and np.array_equal(fl[k, 1], g[f"a{k}_u2"])
+        assert np.array_equal(out[k], g[f"a{k}_x"]) and np.array_equal(out[2 + k], g[f"a{k}_y"])
+        assert list(its[k]) == list(g[f"a{k}_iters"])
+    out, fl, its = _run(g["clip_b"], p)
+    assert np.array_equal(fl[0, 0], g["b0_u1"]) and np.array_equal(out[0], g["b0_x"]) and np.array_equal(out[1], g["b0_y"])
+
+
+def test_full_size_tsn_images_and_many_pairs():
+    """340 x 256 (the TSN flow-image size, the band capacity limit) with more pairs than clusters; two pairs are checked
+    against the oracle, all of them for determinism (same pair computed by different clusters)."""
+    p = flow.TVL1Params()
+    clip = flow.synthetic_clip(3, 256, 340, seed=21, channels=3)
+    pairs = [(0, 1), (1, 2)] * 9 + [(0, 1)]
+    out, fl, its = _run(clip, p, pairs)
+    m = len(pairs)
+    for k in (0, 1):
+        u1, u2, st, qx, qy = _oracle_pair(clip[pairs[k][0]], clip[pairs[k][1]], p)
+        assert list(its[k]) == st
+        assert np.array_equal(fl[k, 0], u1) and np.array_equal(fl[k, 1], u2)
+        assert np.array_equal(out[k], qx) and np.array_equal(out[m + k], qy)
+    for k in range(2, m):
+        assert np.array_equal(out[k], out[k % 2]) and np.array_equal(out[m + k], out[m + k % 2])
+        assert np.array_equal(fl[k], fl[k % 2])
+
+
+def test_parameters_and_saturation():
+    """Non-default parameters (fewer levels/warps, no early stop, small bound so that the 8-bit mapping saturates)."""
+    p = flow.TVL1Params(tau=0.2, lambda_=0.1, theta=0.25, nscales=3, warps=2, epsilon=0.0, iterations=40, scale_step=0.7, bound=1.0)
+    clip = flow.synthetic_clip(2, 60, 80, seed=31, channels=1, velocity=(2.5, -1.5))
+    out, fl, its = _run(clip, p)
+    u1, u2, st, qx, qy = _oracle_pair(clip[0], clip[1], p)
+    assert st == [40] * len(st) and list(its[0][:len(st)]) == st
+    assert np.array_equal(fl[0, 0], u1) and np.array_equal(fl[0, 1], u2)
+    assert np.array_equal(out[0], qx) and np.array_equal(out[1], qy)
+    assert (qx == 255).mean() > 0.5 and (qy == 0).mean() > 0.5
+
+
+def test_identical_frames():
+    clip = flow.synthetic_clip(1, 64, 64, seed=5, channels=3)
+    out, fl, its = _run(np.concatenate([clip, clip]), flow.TVL1Params())
+    assert float(np.abs(fl).max()) == 0.0 and np.all(out == 128) and np.all(its[0] == 2)
+
+
+def test_flow_store_feeds_the_temporal_stream():
+    """fill_flow_store writes the images where the temporal index tables read them (x images then y images of a video)."""
+    from video_analytics_b200.store import DeviceStore, make_layout
+    lay = make_layout(1, min_frames=3, frame_span=1, flows_per_frame=1, rgb_shape=(48, 64, 3), flow_shape=(48, 64, 1))
+    store = DeviceStore(lay)
+    m = lay.videos[0]
+    clip = flow.synthetic_clip(m.n_flows + 1, 48, 64, seed=41)
+    cnt = flow.fill_flow_store(store, 0, torch.from_numpy(clip).cuda())
+    assert cnt == m.n_flows
+    fx, fy = flow.flow_images(torch.from_numpy(clip).cuda())
+    imgs = store.flow.view(-1, 48, 64)
+    assert torch.equal(imgs[m.flowx_first:m.flowx_first + cnt], fx) and torch.equal(imgs[m.flowy_first:m.flowy_first + cnt], fy)
+    _, _, _, qx, qy = _oracle_pair(clip[0], clip[1], flow.TVL1Params())
+    assert np.array_equal(fx[0].cpu().numpy(), qx) and np.array_equal(fy[0].cpu().numpy(), qy)
+
+
+def test_rejects_what_does_not_fit_on_chip():
+    dev = torch.device("cuda")
+    frames = torch.zeros((2, 480, 640, 1), dtype=torch.uint8, device=dev)
+    with pytest.raises(VAError):
+        flow.flow_images(frames)
+    with pytest.raises(VAError):
+        flow.tvl1(torch.zeros(10, dtype=torch.uint8), (1, 1, 1), torch.zeros((1, 4), dtype=torch.int32), torch.zeros(10, dtype=torch.uint8))

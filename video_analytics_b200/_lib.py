@@ -54,6 +54,8 @@ SIGNATURES = {
     "va_f32_to_bf16": (_i, [_vp, C.c_longlong, _vp, _vp]),
     "va_jpeg_decode": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "va_svm_fit": (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.c_double, C.c_double, _i, _vp, _vp, _vp, _vp, _vp]),
+    "va_tvl1_workspace_bytes": (_sz, [_i, _i, _vp]),
+    "va_tvl1_flow": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "va_synth_fill": (_i, [_vp, _sz, _i, _i, _i, _i, _u32, _u32, _vp]),
     "va_debug_conv_counters": (_i, [_vp]),
     "va_profile_enable": (_i, [_i]),

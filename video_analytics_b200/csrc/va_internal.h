@@ -68,6 +68,13 @@ const char* svm_fit_run(const double* X, const int32_t* class_index, int V, int 
                         double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
                         cudaStream_t st);
 
+// ---- TV-L1 optical flow (va_tvl1.cu)
+size_t tvl1_workspace_bytes(int h, int w, int nscales, double scale_step);
+const char* tvl1_run(const uint8_t* images, size_t image_bytes, int h, int w, int c, const int32_t* pairs, int n,
+                     double tau, double lambda, double theta, int nscales, int warps, double epsilon, int iterations,
+                     double scale_step, double bound, uint8_t* out, size_t out_bytes, float* flow, int32_t* stats,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 // ---- tensor-core conv / linear layer (va_conv_tc.cu)
 struct ConvLayerDesc {
   const void* x;        // bf16 NHWC [n][H][W][cin_pad]
