@@ -272,7 +272,7 @@ def main():
                     help="--workload train: snippets per stream per GPU per step (BASELINE configs[4]: 256)")
     ap.add_argument("--lr", type=float, default=0.001, help="--workload train: SGD learning rate")
     ap.add_argument("--no-legs", dest="legs", action="store_false",
-                    help="skip the extra legs of the line (configs0_b1, configs1_b64, parity, strong_3783, train)")
+                    help="skip the extra legs of the line (configs0_b1, configs1_b64, parity, strong_3783, train, tvl1_flow)")
     ap.add_argument("--strong-videos", type=int, default=3783, help="videos of the configs[3] strong-scaling leg")
     args = ap.parse_args()
     if args.workload == "train":
@@ -609,7 +609,8 @@ def main():
                                                           oracle_logits=oracle_logits)) if world == 1 else None),
                 ("strong_3783", lambda: bench_legs.strong_leg(ev, lambda rows: ev.alloc_outputs(rows, D, C, with_svm=True), rank, world,
                                                               dev, n_videos=args.strong_videos, vps=vps)),
-                ("train", lambda: bench_legs.train_leg(args))):
+                ("train", lambda: bench_legs.train_leg(args)),
+                ("tvl1_flow", (lambda: bench_legs.flow_leg(cpu_baseline=not args.no_cpu_baseline)) if world == 1 else None)):
             if fn is None:
                 continue
             try:
@@ -667,7 +668,7 @@ def main():
                 line["configs0_b1"], line["configs1_b64"] = small
             elif small is not None:
                 line["configs0_b1"] = line["configs1_b64"] = small
-            for key in ("parity", "strong_3783", "train"):
+            for key in ("parity", "strong_3783", "train", "tvl1_flow"):
                 if legs.get(key) is not None:
                     line[key] = legs[key]
         if cpu_line is not None:

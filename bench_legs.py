@@ -7,6 +7,7 @@
                 oracle on a 10+10-snippet sample                                                                   (N = 1)
   strong_3783   configs[3]: the whole 3783-video evaluation job, videos sharded over the ranks, total seconds     (every N)
   train         configs[4]: two-stream training step, batch 256 per GPU and stream, gradient all-reduce           (every N)
+  tvl1_flow     SURVEY 8f row 4: TV-L1 production of the flow_x_/flow_y_ images at 340 x 256, frame pairs per second  (N = 1)
 Every function returns a plain dict on rank 0 (None elsewhere) and never prints.
 """
 import os
@@ -57,6 +58,52 @@ def small_batch_legs(spatial, temporal, ev, store, layout):
             {"workload": "temporal stream, batch 64 of 20x224x224 flow stacks, bf16, 1 GPU (BASELINE configs[1])",
              "ms_per_batch": ms64, "snippets_per_s": 64e3 / ms64, "tflops": 64 * TEMPORAL_FLOPS / (ms64 * 1e-3) / 1e12,
              "ms_per_batch_with_preprocess": ms64_e2e})
+
+
+def flow_leg(cpu_baseline=True, pairs=56, frames=9, h=256, w=340):
+    """va_tvl1_flow on a synthetic moving-texture clip (TSN's 340 x 256 flow-image size): device-timed pairs/s, the
+    data-dependent iteration counts, and how far the on-chip iteration is from the SMs' fp32 issue rate.  The CPU figure
+    beside it is oracle/tvl1.py (numpy, one core) on ONE pair of the same clip."""
+    import numpy as np
+    import torch
+    from video_analytics_b200 import flow, ops
+    dev = torch.device("cuda", torch.cuda.current_device())
+    clip = flow.synthetic_clip(frames, h, w, seed=7)
+    fr = torch.from_numpy(clip).to(dev)
+    base = torch.arange(pairs, dtype=torch.int32, device=dev) % (frames - 1)
+    k = torch.arange(pairs, dtype=torch.int32, device=dev)
+    table = torch.stack([base, base + 1, k, k + pairs], dim=1).contiguous()
+    out = torch.empty((2 * pairs, h, w), dtype=torch.uint8, device=dev)
+    p = flow.TVL1Params()
+    its = flow.tvl1(fr, (h, w, 3), table, out, params=p, return_iterations=True)["iterations"].cpu().numpy()
+    ms = _event_ms(lambda: flow.tvl1(fr, (h, w, 3), table, out, params=p), reps=3, warm=1)
+    levels = p.levels(h, w)
+    sizes = [(h, w)]
+    for _ in range(1, levels):
+        sizes.append((int(round(sizes[-1][0] * p.scale_step)), int(round(sizes[-1][1] * p.scale_step))))
+    px = np.array([a * b for a, b in sizes[::-1]], np.float64)
+    pix_iters = float((its.reshape(pairs, levels, p.warps).sum(2) * px[None, :]).sum())
+    sm = ops.device_info()["sm_count"]
+    clk_hz = 1.0e6 * torch.cuda.clock_rate()          # current SM clock (MHz) as the driver reports it
+    instr_min = 105.0           # fp32 + load/store instructions one primal + dual update of a pixel needs at least (DESIGN.md)
+    peak = sm * 128 * clk_hz / instr_min
+    leg = {"workload": f"TV-L1 optical flow (OpenCV CUDA defaults: 5 levels x 5 warps x <= 300 iterations, epsilon 0.01), {pairs} frame pairs of "
+                       f"{w}x{h} RGB, one 16-CTA cluster per pair, u8 flow_x/flow_y out (bound 20)",
+           "pairs_per_s": pairs / ms * 1e3, "ms": ms, "inner_iterations_per_pair": float(its.sum(1).mean()),
+           "pixel_iterations_per_s": pix_iters / ms * 1e3,
+           "roofline": {"bound": "fp32 issue (solver state resident in shared memory, no HBM traffic in the iteration)",
+                        "achieved": pix_iters / ms * 1e3, "peak": peak, "unit": "pixel-iterations/s", "frac": pix_iters / ms * 1e3 / peak,
+                        "peak_definition": f"{sm} SMs x 128 lanes x SM clock / {instr_min:.0f} instructions per pixel-iteration",
+                        "limiters": "7 clusters of 16 CTAs fit (112 of 148 SMs); neighbour synchronisation latency dominates the coarse levels"},
+           "parity": "bit-identical to oracle/tvl1.py (tests/test_gpu_tvl1.py); oracle unpinned: third-party tool absent"}
+    if cpu_baseline:
+        from oracle import tvl1 as otv
+        t0 = time.time()
+        otv.tvl1_flow(otv.gray_from_rgb(clip[0]), otv.gray_from_rgb(clip[1]))
+        dt = time.time() - t0
+        leg["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+                               "sample": "one 340x256 pair of the same clip through oracle/tvl1.py (numpy fp32)"}
+    return leg
 
 
 def margin_histogram(scores):

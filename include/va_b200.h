@@ -289,6 +289,11 @@ va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int
                        size_t out_image_bytes, float* flow_f32, int32_t* iterations, void* workspace,
                        size_t workspace_bytes, va_stream_t stream);
 
+/* Diagnostics: when set to a device buffer of 2 * nscales * warps int64, cluster 0 of every subsequent va_tvl1_flow launch
+ * writes, for its first pair and per (level, warp) in processing order, the SM cycles of the bicubic warp phase [2k] and of
+ * the inner iterations [2k+1].  NULL switches it off. */
+va_status va_tvl1_debug_cycles(long long* dev_cycles);
+
 /* Synthetic image store generator (bench/test data; integer hash identical to oracle/synth.py):
  * fills n_images images of image_bytes each, image id = first_id + i. */
 va_status va_synth_fill(uint8_t* images, size_t image_bytes, int n_images, int img_h, int img_w, int img_c,

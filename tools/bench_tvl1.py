@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--epsilon", type=float, default=0.01)
     ap.add_argument("--oracle", action="store_true")
+    ap.add_argument("--cycles", action="store_true", help="per (level, warp) cycle counters of cluster 0's first pair")
     a = ap.parse_args()
     clip = flow.synthetic_clip(a.frames, a.h, a.w, seed=7)
     dev = torch.device("cuda")
@@ -54,6 +55,18 @@ def main():
     line = {"what": "va_tvl1_flow", "image": [a.h, a.w], "pairs": n, "ms": ms, "pairs_per_s": n / ms * 1e3,
             "inner_iterations_per_pair": float(its.sum(1).mean()), "pixel_iterations_per_s": pix_iters / ms * 1e3,
             "epsilon": a.epsilon, "times_ms": times}
+    if a.cycles:
+        from video_analytics_b200 import _lib
+        dbg = torch.zeros(2 * levels * p.warps, dtype=torch.int64, device=dev)
+        _lib.check(_lib.load().va_tvl1_debug_cycles(_lib.ptr(dbg)))
+        flow.tvl1(frames, (a.h, a.w, 3), table, out, params=p)
+        torch.cuda.synchronize()
+        _lib.check(_lib.load().va_tvl1_debug_cycles(None))
+        d = dbg.cpu().numpy().reshape(levels, p.warps, 2)
+        it0 = its[0].reshape(levels, p.warps)
+        line["cycles_first_pair"] = {"level_sizes": sizes[::-1], "iterations": it0.tolist(), "warp_phase_cycles": d[:, :, 0].tolist(),
+                                     "inner_cycles": d[:, :, 1].tolist(),
+                                     "cycles_per_iteration": (d[:, :, 1] / np.maximum(it0, 1)).round(0).tolist()}
     if a.oracle:
         from oracle import tvl1 as otv
         t = time.time()

@@ -649,6 +649,11 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
   return VA_OK;
 }
 
+va_status va_tvl1_debug_cycles(long long* dev_cycles) {
+  va::tvl1_set_debug_cycles(dev_cycles);
+  return VA_OK;
+}
+
 static va_tvl1_params tvl1_defaults() {
   va_tvl1_params d;
   d.tau = 0.25; d.lambda = 0.15; d.theta = 0.3; d.epsilon = 0.01; d.scale_step = 0.8; d.bound = 20.0;
