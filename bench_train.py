@@ -109,8 +109,13 @@ def main(args, embedded=False):
     C, D, L = 101, 256, 10
     group = dist.group.WORLD if world > 1 else None
     # same initial weights on every rank (seeded init), as DataParallel's replicate would give
-    tr_s = StreamTrainer(build_spatial_torch_model(C, D, seed=0), None, lr=args.lr, momentum=0.9, c_pad=16, process_group=group)
-    tr_t = StreamTrainer(build_temporal_torch_model(C, L, D, seed=0), None, lr=args.lr, momentum=0.9, c_pad=32, process_group=group)
+    # data parallel: each stream's gradient all-reduce runs under the OTHER stream's forward pass (deferred update + SM
+    # reservation, training.py); VA_DEFER_UPDATE=0 gives the collective-after-backward schedule for A/B runs
+    defer = world > 1 and os.environ.get("VA_DEFER_UPDATE", "1") == "1"
+    tr_s = StreamTrainer(build_spatial_torch_model(C, D, seed=0), None, lr=args.lr, momentum=0.9, c_pad=16, process_group=group,
+                         defer_update=defer)
+    tr_t = StreamTrainer(build_temporal_torch_model(C, L, D, seed=0), None, lr=args.lr, momentum=0.9, c_pad=32, process_group=group,
+                         defer_update=defer)
     layout = make_layout(args.pool)
     store = DeviceStore(layout, dev)
     mean_s, std_s = list(NORM_MEANS_TF), list(NORM_STDS_TF)
@@ -160,6 +165,8 @@ def main(args, embedded=False):
         sampler.start()
     for i in range(W):
         step(i)
+    tr_s.flush()
+    tr_t.flush()
     barrier()
     sampler.mark()
     launches0 = _lib.launch_count()
@@ -167,6 +174,8 @@ def main(args, embedded=False):
     e0.record()
     for i in range(W, W + K):
         step(i)
+    tr_s.flush()                 # deferred updates of the last step belong to the timed region
+    tr_t.flush()
     e1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -261,11 +270,15 @@ def main(args, embedded=False):
         issue_copies(0)
         for i in range(n_warm):
             e2e_step(i, last=(i == n_warm - 1))
+        tr_s.flush()
+        tr_t.flush()
     barrier()
     t0 = time.perf_counter()
     issue_copies(W)
     for i in range(W, W + K):
         e2e_step(i, last=(i == W + K - 1), count=(i == W))
+    tr_s.flush()
+    tr_t.flush()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

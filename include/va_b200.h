@@ -289,6 +289,14 @@ va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int
                        size_t out_image_bytes, float* flow_f32, int32_t* iterations, void* workspace,
                        size_t workspace_bytes, va_stream_t stream);
 
+/* SM reservation for a collective that runs beside the layer kernels (data-parallel training: the gradient all-reduce of
+ * one stream under the other stream's forward pass).  The layer kernels are persistent, one CTA per SM with 210-227 KB of
+ * shared memory, so a collective's CTAs cannot co-reside with them: launched beside a full grid they hold some SMs and the
+ * layer's CTAs for those SMs start only when the collective ends.  After va_reserve_sms(sms, launches) the next `launches`
+ * layer launches (va_forward / va_conv2d_nhwc / va_linear / dgrad calls of THIS process) size their grids for
+ * sm_count - sms SMs; (0, 0) switches it off.  Results do not depend on the grid size. */
+va_status va_reserve_sms(int sms, int launches);
+
 /* Diagnostics: when set to a device buffer of 2 * nscales * warps int64, cluster 0 of every subsequent va_tvl1_flow launch
  * writes, for its first pair and per (level, warp) in processing order, the SM cycles of the bicubic warp phase [2k] and of
  * the inner iterations [2k+1].  NULL switches it off. */

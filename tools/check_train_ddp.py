@@ -64,6 +64,25 @@ def main():
     tr3.step(*args)
     d32, d16 = tr2.flat_param - before, tr3.flat_param - before
     rel16 = float((d16 - d32).norm() / d32.norm())
+    # deferred update (the all-reduce of step k waits at the start of step k+1, SM reservation for the collective): same
+    # updates as the immediate schedule, up to the summation order of the weight-gradient atomics
+    del tr2, tr3
+    torch.cuda.empty_cache()
+    trA = StreamTrainer(build_spatial_torch_model(101, 256, seed=7), None, lr=0.01, momentum=0.9, c_pad=16,
+                        process_group=dist.group.WORLD, defer_update=False)
+    trB = StreamTrainer(build_spatial_torch_model(101, 256, seed=7), None, lr=0.01, momentum=0.9, c_pad=16,
+                        process_group=dist.group.WORLD, defer_update=True)
+    start = trA.flat_param.clone()
+    for _ in range(2):
+        trA.step(*args)
+        trB.step(*args)
+    pending = trB._deferred is not None
+    trB.flush()
+    moved = float((trA.flat_param - start).norm())
+    rel_defer = float((trA.flat_param - trB.flat_param).norm()) / moved
+    if rank == 0:
+        print(f"deferred vs immediate update: rel diff of the 2-step parameter change {rel_defer:.3e} (pending before flush: {pending})")
+        ok = ok and pending and rel_defer < 1e-4
     if rank == 0:
         good = ok and int(flag) == 1 and int(synced) == 1 and rel16 < 1e-2
         print(("DDP_OK" if good else "DDP_FAIL"), f"world={world} params_identical={bool(int(flag))} replicas_synced={bool(int(synced))} "

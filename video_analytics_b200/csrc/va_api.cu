@@ -649,6 +649,12 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
   return VA_OK;
 }
 
+va_status va_reserve_sms(int sms, int launches) {
+  if (sms < 0 || launches < 0) return fail(VA_ERR_INVALID, "va_reserve_sms: negative argument");
+  va::conv_reserve_sms(sms, launches);
+  return VA_OK;
+}
+
 va_status va_tvl1_debug_cycles(long long* dev_cycles) {
   va::tvl1_set_debug_cycles(dev_cycles);
   return VA_OK;

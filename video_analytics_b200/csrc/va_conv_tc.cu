@@ -69,6 +69,12 @@ const char* encode_bf16(CUtensorMap* m, const void* addr, int rank, const uint64
 
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
+// SM reservation (va_reserve_sms): the next `g_reserve_launches` layer-kernel launches size their persistent grids for
+// `sm_total - g_reserve_sms` SMs, so that a collective launched just before (NCCL's CTAs cannot co-reside with a layer CTA
+// that holds 210-227 KB of shared memory) finds free SMs instead of stalling a whole layer behind it.
+int g_reserve_sms = 0;
+int g_reserve_launches = 0;
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -76,6 +82,11 @@ int sm_count() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+  }
+  if (g_reserve_launches > 0 && g_reserve_sms > 0) {
+    int m = n - g_reserve_sms;
+    m &= ~1;                                   // CTA pairs
+    if (m >= 16) return m;
   }
   return n;
 }
@@ -125,9 +136,15 @@ static long long* g_dbg_counters = nullptr;
 void conv_set_debug_counters(long long* dev_buf) { g_dbg_counters = dev_buf; }
 long long* conv_get_debug_counters() { return g_dbg_counters; }
 
+void conv_reserve_sms(int sms, int launches) {
+  g_reserve_sms = sms > 0 ? sms : 0;
+  g_reserve_launches = (sms > 0 && launches > 0) ? launches : 0;
+}
+
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st) {
   cudaStream_t st_ = st;
   if (d.n <= 0) return nullptr;
+  struct ReserveTick { ~ReserveTick() { if (g_reserve_launches > 0) --g_reserve_launches; } } reserve_tick;   // one layer = one tick
   if (d.ks != 1 && d.ks != 3) return "ks must be 1 or 3";
   const int CK = (d.cin_pad % 64 == 0) ? 64 : d.cin_pad;
   if (CK != 64 && CK != 32 && CK != 16) return errf("cin_pad %d unsupported (16, 32 or multiple of 64)", d.cin_pad);

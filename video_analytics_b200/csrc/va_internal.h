@@ -95,6 +95,7 @@ constexpr int kSplitK = 8;
 // Plans (tile shape, kernel variant, tensor maps) and launches one layer.  Returns nullptr on success or a
 // static/thread-local error string.
 const char* conv_layer_run(const ConvLayerDesc& d, cudaStream_t st);
+void conv_reserve_sms(int sms, int launches);   // the next `launches` layer launches leave `sms` SMs free (0 = off)
 void conv_set_debug_counters(long long* dev_buf);
 long long* conv_get_debug_counters();
 

@@ -34,6 +34,11 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            # The collectives of this path run BESIDE persistent one-CTA-per-SM layer kernels (training: a stream's gradient
+            # all-reduce under the other stream's forward, with va_reserve_sms leaving 8 SMs free for 5 layer launches): cap NCCL's
+            # CTAs to the SMs that are reserved for it (measured at N = 2, ms per step: 8 SMs x 5 launches 49.41, 16 x 3 49.84,
+            # 32 x 3 49.67, 24 x 5 50.11, collective after the backward pass 50.47; profiles/r02_train_defer_n2.json).
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("VA_ALLREDUCE_SMS", "8"))
             torch.cuda.set_device(local)
             dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
         else:

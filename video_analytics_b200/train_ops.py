@@ -197,3 +197,9 @@ def f32_to_bf16_(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.numel() == out.numel()
     check(_lib.load().va_f32_to_bf16(ptr(x), x.numel(), ptr(out), stream_ptr()), "va_f32_to_bf16")
     return out
+
+
+def reserve_sms(sms: int, launches: int) -> None:
+    """va_reserve_sms: the next `launches` layer-kernel launches of this process leave `sms` SMs free for a collective
+    that was just launched on another stream (0, 0 switches it off)."""
+    check(_lib.load().va_reserve_sms(int(sms), int(launches)), "va_reserve_sms")

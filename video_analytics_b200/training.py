@@ -42,7 +42,8 @@ class StreamTrainer:
 
     def __init__(self, module: torch.nn.Module, optimizer: Optional[torch.optim.SGD] = None, *, lr: float = 0.1,
                  momentum: float = 0.9, c_pad: int = 16, process_group=None, grad_allreduce_dtype: str = "bf16",
-                 overlap_allreduce: Optional[bool] = None):
+                 overlap_allreduce: Optional[bool] = None, defer_update: Optional[bool] = None,
+                 reserve_sms: Optional[int] = None, reserve_launches: Optional[int] = None):
         """module: the (unwrapped) torchvision-layout VGG16 with the swapped classifier (parameter container only).
         optimizer: the torch.optim.SGD over module.parameters(); its lr / momentum are read at every step (so a
         MultiStepLR scheduler keeps working) and its momentum buffers are re-pointed at the arena."""
@@ -68,6 +69,19 @@ class StreamTrainer:
             import os
             overlap_allreduce = os.environ.get("VA_OVERLAP_ALLREDUCE", "0") == "1"
         self.overlap_allreduce = bool(overlap_allreduce)
+        # defer_update=True (data parallel only): step() returns as soon as the gradient all-reduce is LAUNCHED; the wait and
+        # the SGD update run at the start of this trainer's next step() (or flush()).  The two streams' trainers alternate,
+        # so one stream's collective runs under the other stream's forward pass -- same arithmetic, same order of updates.
+        # For NCCL's CTAs to find room beside the persistent layer kernels, the next `reserve_launches` layer launches of
+        # the process leave `reserve_sms` SMs free (va_reserve_sms); the collective then costs those layers ~sms/148 of
+        # their time instead of its own duration.  Measured in DESIGN.md section 5.
+        import os as _os
+        if defer_update is None:
+            defer_update = _os.environ.get("VA_DEFER_UPDATE", "0") == "1"
+        self.defer_update = bool(defer_update) and process_group is not None
+        self.reserve_sms = int(_os.environ.get("VA_ALLREDUCE_SMS", "8")) if reserve_sms is None else int(reserve_sms)
+        self.reserve_launches = int(_os.environ.get("VA_ALLREDUCE_LAUNCHES", "5")) if reserve_launches is None else int(reserve_launches)
+        self._deferred = None
         sd = dict(self.module.named_parameters())
         missing = [k for k in STATE_DICT_KEYS if k not in sd]
         if missing:
@@ -144,6 +158,7 @@ class StreamTrainer:
         return self._lr, self._momentum
 
     def param(self, key: str) -> torch.Tensor:
+        self.flush()
         return self.params[STATE_DICT_KEYS.index(key)].data
 
     def grad(self, key: str) -> torch.Tensor:
@@ -271,11 +286,24 @@ class StreamTrainer:
         if self.group is not None and self.overlap_allreduce:
             def hook():
                 pending.append(self._allreduce_async(split, self.flat_grad.numel()))
+        self.flush()                           # a deferred update of the previous step: wait for its collective, then SGD
         loss, feat, logits = self.forward_backward(x_nhwc, labels, masks, on_classifier_grads=hook)
         if self.group is not None:
             pending.append(self._allreduce_async(0, split if self.overlap_allreduce else self.flat_grad.numel()))
+        if self.defer_update:
+            self._deferred = pending
+            if self.reserve_sms > 0 and self.reserve_launches > 0:
+                T.reserve_sms(self.reserve_sms, self.reserve_launches)     # the NEXT layer launches (the other stream's forward)
+            return loss, feat, logits
         self.apply_update(pending)
         return loss, feat, logits
 
+    def flush(self):
+        """Apply a deferred update (no-op otherwise).  Called by step(); call it before reading parameters."""
+        if self._deferred is not None:
+            pending, self._deferred = self._deferred, None
+            self.apply_update(pending)
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
+        self.flush()
         return {k: p.data for k, p in zip(STATE_DICT_KEYS, self.params)}
