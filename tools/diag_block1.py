@@ -128,7 +128,8 @@ def run_fused(kind, batch):
     c = cnt.cpu().tolist()
     tiles = max(1, c[11])
     res["roles"] = {"tiles_per_cta": tiles, "clk_per_tile": c[0] / tiles,
-                    "gather_pct": {"load_next": 100 * c[1] / max(1, c[0]), "wait_empty": 100 * c[2] / max(1, c[0]), "convert+fence": 100 * c[3] / max(1, c[0])},
+                    "gather_pct": {"wait_strip": 100 * c[1] / max(1, c[0]), "wait_empty": 100 * c[2] / max(1, c[0]), "convert": 100 * c[3] / max(1, c[0]),
+                                   "proxy_fence": 100 * c[12] / max(1, c[0])},
                     "mma_pct": {"wait_tmem_empty": 100 * c[5] / max(1, c[4]), "wait_full": 100 * c[6] / max(1, c[4])},
                     "epilogue0_pct": {"wait_tmem_full": 100 * c[8] / max(1, c[7]), "wait_staging": 100 * c[9] / max(1, c[7])}}
     out_bytes = batch * 224 * 224 * 64 * 2

@@ -6,19 +6,25 @@
 // The separate K1 kernel wrote a channel-padded bf16 NHWC tensor (1.6 / 3.2 MB per snippet) that conv1_1 read back;
 // here the u8 crop is the only HBM input of the layer.
 //
-// Tile = 16 x 8 output pixels of one snippet.  Four gather warps read the 18 x 10 haloed source patch of every plane
-// (index-table row = image id, crop top/left, flip), normalise by table lookup (bf16(((u8/255) - mean)/std), the same
-// IEEE operations as torchvision, built per CTA), and write it into a pipeline stage as PLANES of 8 channels:
-//     stage[chunk j][pixel p = row*10 + col][8 x bf16]        (16-byte granules, zero outside the crop = conv padding)
-// This is a NO-SWIZZLE K-major UMMA operand in which 8-pixel groups (one output row of the tile) are 160 B apart (SBO)
-// and the two 8-channel halves of a K=16 MMA are LBO apart -- and because LBO is free, the second half may be ANOTHER
-// TAP of the same chunk (LBO = 16 B: the pixel to the right; 160 B: the pixel below).  Filter tap (r,s) is a start
-// address shift of (r*10 + s)*16 B (verified on B200 by tools/microbench/desc_probe.cu).  K is therefore packed
-// densely: 3 input channels need 5 MMAs per tile (K = 9 taps x 8 channels, last slot zero-weighted) instead of 9 with
-// 16-channel padding; 20 channels need 14 instead of 18.  Weights are packed to match and stay resident in smem.
-//
-// Warp roles (416 threads, 1 CTA/SM, persistent): warps 0-3 / 4-7 two epilogue groups (TMEM -> +bias -> ReLU -> bf16 ->
-// 128B-swizzled staging -> TMA store), warps 8-11 gather, warp 12 MMA issuer + TMEM owner.
+// Work unit = a SEGMENT of 7 horizontally adjacent 16 x 8 output tiles of one snippet (a quarter of a tile row); every
+// CTA walks a contiguous range of segments.  Per segment:
+//   * LOADER warp: for every plane (index-table row = image id, crop top/left, flip) and each of the 18 haloed source
+//     rows, ONE bulk async copy (cp.async.bulk, completion on an mbarrier) brings the 16-byte blocks covering the 58 source
+//     pixels the segment touches into one of two raw strip buffers, and the byte offset of the segment's first pixel inside
+//     the copied row goes into a small table.  No registers, no proxy fence in this warp: its copies stay in flight across
+//     tiles (versions 1-4 loaded bytes into registers of the converting warps: ptxas implements fence.proxy.async with
+//     MEMBAR.ALL.CTA, which drained those loads at every tile and exposed ~1000 clk of load latency per tile,
+//     profiles/r02_conv1_fused_role_counters.log).
+//   * CONVERTER warps (thread = pixel of the 18 x 10 haloed patch of a tile): byte from the strip -> normalisation table
+//     (bf16(((u8/255) - mean)/std), the same IEEE operations as torchvision, built per CTA) -> operand rows
+//     [pixel][16 channels] in the 32-byte-swizzle layout (the XOR is applied to absolute shared-address bits, as TMA and
+//     UMMA do), zero outside the crop (= the convolution's padding).  Channel remainders <= 8 go to a "pair" plane
+//     [pixel p | pixel p+1] so that two taps share one K = 16 MMA: 3 channels need 6 MMAs per tile instead of 9, 20
+//     channels 15 instead of 18.  Filter tap (r,s) is a start-address shift of (r*10 + s)*32 B, 8-pixel groups are
+//     320 B apart (SBO).  Weights are packed to match and stay resident in smem.
+//   * MMA warp (one elected lane) and two epilogue groups (TMEM -> +bias -> ReLU -> bf16 -> 128B-swizzled staging -> TMA
+//     store) as in va_conv_tc.cuh.
+// Warp roles (512 threads, 1 CTA/SM, persistent): warps 0-7 epilogue, 8-13 converters, 14 loader, 15 MMA + TMEM owner.
 #include "va_internal.h"
 #include "va_conv_tc.cuh"
 
@@ -29,8 +35,14 @@ namespace va {
 
 namespace {
 
-constexpr int kF1GatherWarps = 6;                      // 192 threads >= the 180 pixels of a haloed patch
-constexpr int kF1Threads = (8 + kF1GatherWarps + 1) * 32;
+constexpr int kF1GatherWarps = 6;                      // converter warps: 192 threads >= the 180 pixels of a haloed patch
+constexpr int kF1Threads = (8 + kF1GatherWarps + 2) * 32;
+constexpr int kF1SegTiles = 7;                         // tiles per segment (28 tiles per tile row = 4 segments)
+constexpr int kF1SegPerSnip = 14 * 4;
+constexpr int kF1SegPix = kF1SegTiles * 8 + 2;         // 58 source pixels per row of a segment
+// one bulk copy per (plane, haloed row): the 16-byte blocks covering 58 pixels at any byte shift, rows bank-staggered
+__host__ __device__ constexpr int f1_copy_bytes(int img_c) { return (15 + kF1SegPix * img_c + 15) / 16 * 16; }   // 80 / 192
+__host__ __device__ constexpr int f1_row_pitch(int img_c) { return img_c == 1 ? 80 : 208; }
 constexpr int kF1TileH = 16, kF1TileW = 8, kF1Pitch = kF1TileW + 2, kF1Rows = kF1TileH + 2;
 constexpr int kF1Pix = kF1Pitch * kF1Rows;            // 180 haloed pixels
 constexpr int kF1PlaneBytes = kF1Pix * 32;            // one plane of a stage: [pixel][16 bf16]
@@ -52,8 +64,7 @@ struct Conv1FusedParams {
   unsigned char lut_of[32];
   const __nv_bfloat16* w_packed; // [n_mma][64][16], 32B-swizzled
   const float* bias;             // [64]
-  int total_tiles;
-  FastDiv div_w, div_h;          // by 28, 14
+  int total_segments;            // n_img * 14 * 4
   int n_mma;
   unsigned int a_off16[kF1MaxMma];   // per MMA: byte offset of its A window inside a stage, >> 4
   long long* dbg;                    // optional [16] per-role cycle counters written by CTA 0 (diagnostics only)
@@ -86,37 +97,68 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int IMG_C, int MAXCH, int REP>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void f1_bulk_copy(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// NCH_CT: the channel count as a compile-time constant (3 = RGB frame, 20 = the 10-pair flow stack; 0 = read it from the
+// parameters).  With it the converter's per-channel slots beyond the real channels disappear instead of being issued
+// predicated-off: 190 -> ~60 instructions per RGB pixel, and the tile time of a converter warp is its dependent latency.
+template <int IMG_C, int MAXCH, int REP, int NCH_CT>
 __global__ void __launch_bounds__(kF1Threads, 1)
 conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedParams p) {
+  constexpr int kPitch = f1_row_pitch(IMG_C);
+  constexpr int kCopy = f1_copy_bytes(IMG_C);
+  constexpr int kMaxPlanes = MAXCH / IMG_C;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem;                                               // 2 groups x 2 x 16 KB, 1024-aligned (128B swizzle)
   uint8_t* w_s = staging + 4 * kF1StagingBytes;                          // n_mma x 2 KB
-  const int n_planes = p.n_full + p.has_pair;
+  const int n_full = NCH_CT ? (NCH_CT / 16 + ((NCH_CT % 16) > 8 ? 1 : 0)) : p.n_full;
+  const int has_pair = NCH_CT ? (((NCH_CT % 16) > 0 && (NCH_CT % 16) <= 8) ? 1 : 0) : p.has_pair;
+  const int n_planes = n_full + has_pair;
   const uint32_t a_stage_bytes = (uint32_t)n_planes * kF1PlaneBytes;
   uint8_t* a_ring = w_s + (size_t)p.n_mma * 2048;
   uint16_t* lut_s = reinterpret_cast<uint16_t*>(a_ring + (size_t)kF1Stages * a_stage_bytes);
   float* bias_s = reinterpret_cast<float*>(lut_s + (size_t)p.n_luts * 256 * REP);
-  unsigned long long* pl_base = reinterpret_cast<unsigned long long*>(bias_s + 64);      // [32] per-plane source base of the snippet
-  uint32_t* pl_flip = reinterpret_cast<uint32_t*>(pl_base + 32);                         // bit pl = flip; [1] = snippet id
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(pl_flip + 2);
+  const int units = p.planes * kF1Rows;                                  // (plane, haloed row) copies per segment
+  const uint32_t strip_bytes = (uint32_t)units * kPitch;
+  uint8_t* strips = reinterpret_cast<uint8_t*>(bias_s + 64);             // 2 raw strip buffers (16-byte aligned)
+  int* rowoff = reinterpret_cast<int*>(strips + 2 * (size_t)strip_bytes);   // [2][units]: byte of the segment's first pixel in its row
+  uint32_t* flipmask = reinterpret_cast<uint32_t*>(rowoff + 2 * units);  // [2]: bit pl = plane pl is flipped
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(flipmask + 2);
   uint64_t* empty_bar = full_bar + kF1Stages;
   uint64_t* tfull_bar = empty_bar + kF1Stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sfull_bar = tempty_bar + 2;                                   // strip loaded (tx bytes + one arrival per unit)
+  uint64_t* sempty_bar = sfull_bar + 2;                                   // strip consumed by the 6 converter warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kGatherWarp0 = 8, kMmaWarp = 8 + kF1GatherWarps;
+  constexpr int kGatherWarp0 = 8, kLoaderWarp = 8 + kF1GatherWarps, kMmaWarp = kLoaderWarp + 1;
 
   // ---- prologue: barriers, TMEM, resident weights, normalisation table, zeroed stages
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < kF1Stages; ++i) { mbar_init(&full_bar[i], kF1GatherWarps); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4);
+      mbar_init(&sfull_bar[i], 32 + 1); mbar_init(&sempty_bar[i], kF1GatherWarps);
+    }
     fence_mbar_init();
-    pl_flip[1] = 0xFFFFFFFFu;
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
   {
@@ -141,134 +183,170 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // Every CTA walks a CONTIGUOUS range of tiles (row-major inside a snippet): consecutive tiles read neighbouring 8-pixel
-  // column blocks of the same source rows, so the gather's loads hit L1, and the per-plane source bases change once per snippet.
-  const int tiles_per = p.total_tiles / (int)gridDim.x, tiles_rem = p.total_tiles % (int)gridDim.x;
-  const int tile_begin = (int)blockIdx.x * tiles_per + min((int)blockIdx.x, tiles_rem);
-  const int tile_end = tile_begin + tiles_per + ((int)blockIdx.x < tiles_rem ? 1 : 0);
+  // Every CTA walks a CONTIGUOUS range of segments (row-major inside a snippet).
+  const int seg_per = p.total_segments / (int)gridDim.x, seg_rem = p.total_segments % (int)gridDim.x;
+  const int seg_begin = (int)blockIdx.x * seg_per + min((int)blockIdx.x, seg_rem);
+  const int seg_end = seg_begin + seg_per + ((int)blockIdx.x < seg_rem ? 1 : 0);
+  const int n_tiles = (seg_end - seg_begin) * kF1SegTiles;
 
-  if (warp >= kGatherWarp0 && warp < kGatherWarp0 + kF1GatherWarps) {
-    // ===================================================== gather + normalise -> A operand (6 warps, thread = patch pixel)
-    // Thread t < 180 owns pixel (row t/10, col t%10) of the haloed patch and loops over the planes: a warp-level byte load
-    // then touches ~4 cache lines (3 patch rows of one plane), not 32 as with one (plane, row) per lane.  The bytes of the
-    // NEXT tile are loaded before the current tile is converted (two register sets).
+  if (warp == kLoaderWarp) {
+    // ===================================================== loader: global -> raw strips, one bulk copy per (plane, row)
+    const int4* table4 = reinterpret_cast<const int4*>(p.table);
+    const uint32_t strips_u32 = smem_u32(strips);
+    constexpr int kChunks = kCopy / 16;                          // 5 / 12
+    int segk = 0, cur_tn = -1;
+    int4 ent = make_int4(0, 0, 0, 0);
+    for (int seg = seg_begin; seg < seg_end; ++seg, ++segk) {
+      const int buf = segk & 1;
+      const uint32_t sphase = (uint32_t)(segk >> 1) & 1u;
+      mbar_wait(&sempty_bar[buf], sphase ^ 1u, 500 + buf);       // the converters are done with this buffer's previous segment
+      const int tn = seg / kF1SegPerSnip, rem = seg - tn * kF1SegPerSnip;
+      const int th = rem >> 2, sq = rem & 3;
+      const int y_first = th * kF1TileH - 1, x_first = sq * kF1SegTiles * kF1TileW - 1;
+      if (tn != cur_tn) {                                          // lane pl keeps the table row of plane pl of this snippet
+        cur_tn = tn;
+        ent = lane < p.planes ? __ldg(table4 + (size_t)tn * p.planes + lane) : make_int4(0, 0, 0, 0);
+      }
+      {
+        const uint32_t mask = __ballot_sync(0xffffffffu, lane < p.planes && ent.w != 0);
+        if (lane == 0) flipmask[buf] = mask;
+      }
+      // 16-byte asynchronous copies (LDGSTS, L1 bypass), lane = one (plane, row): the row's address is computed once and
+      // its 5 / 12 chunks are issued back to back.  (One cp.async.bulk per row -- 360 TMA requests per flow segment -- and,
+      // after that, lane = chunk with the address arithmetic repeated per chunk both kept the loader behind the MMAs:
+      // 1340 / 920 clk of strip wait per tile.)
+      for (int unit0 = 0; unit0 < units; unit0 += 32) {
+        const int unit = min(unit0 + lane, units - 1);
+        const int pl = (unit * 3641) >> 16;                      // unit / 18 (exact below 4000)
+        const int r = unit - pl * kF1Rows;
+        const int y = y_first + r;
+        int4 e;                                                  // image id, crop top, crop left, flip
+        e.x = __shfl_sync(0xffffffffu, ent.x, pl); e.y = __shfl_sync(0xffffffffu, ent.y, pl);
+        e.z = __shfl_sync(0xffffffffu, ent.z, pl); e.w = __shfl_sync(0xffffffffu, ent.w, pl);
+        if (unit0 + lane < units && (unsigned)y < (unsigned)kF1Crop) {   // rows above / below the crop: zero padding
+          // lowest source column of the segment: crop column x_first, or 223 - (x_first + 57) when the plane is flipped
+          const int col_lo = e.z + (e.w ? (kF1Crop - 1) - (x_first + kF1SegPix - 1) : x_first);
+          const long long img_lo = (long long)e.x * (long long)p.image_bytes;
+          const long long off = img_lo + ((long long)(e.y + y) * p.img_w + col_lo) * IMG_C;
+          long long start = off & ~15ll;
+          if (start < img_lo) start = img_lo;                    // (only pixels outside the crop lie before / after the image)
+          const long long img_hi = img_lo + (long long)p.image_bytes;
+          if (start + kCopy > img_hi) start = img_hi - kCopy;
+          // byte of segment pixel 0 inside the copied row; a flipped plane walks backwards from its last pixel
+          rowoff[buf * units + unit] = (int)(off - start) + (e.w ? (kF1SegPix - 1) * IMG_C : 0);
+          const uint32_t dst = strips_u32 + (uint32_t)buf * strip_bytes + (uint32_t)unit * kPitch;
+          const uint8_t* src_g = p.images + start;
+#pragma unroll
+          for (int j = 0; j < kChunks; ++j)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * j), "l"(src_g + 16 * j) : "memory");
+        }
+      }
+      // every lane's copies report to the strip's barrier when they land; lane 0 adds a normal (releasing) arrival after
+      // the warp's row-offset / flip-mask stores
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&sfull_bar[buf])) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull_bar[buf]);
+    }
+  } else if (warp >= kGatherWarp0 && warp < kGatherWarp0 + kF1GatherWarps) {
+    // ===================================================== strip bytes -> normalise -> A operand (6 warps, thread = patch pixel)
     const int gt = threadIdx.x - kGatherWarp0 * 32;
     const bool has_px = gt < kF1Pix;
     const int prow = has_px ? gt / kF1Pitch : 0, pcol = has_px ? gt % kF1Pitch : 0;
-    const int4* table4 = reinterpret_cast<const int4*>(p.table);
-    const int nch = p.planes * IMG_C;
-    uint32_t ua[MAXCH], ub[MAXCH];
-    bool va_ok = false, vb_ok = false;
-    const uint32_t lut_u32 = smem_u32(lut_s), plb_u32 = smem_u32(pl_base), plf_u32 = smem_u32(pl_flip);
-
-    auto load_tile = [&](int tile, uint32_t (&u)[MAXCH], bool& ok) {
-      uint32_t mt, tw, th, tn;
-      p.div_w.divmod((uint32_t)tile, mt, tw);
-      p.div_h.divmod(mt, tn, th);
-      if (lds_u32(plf_u32 + 4) != tn) {                // first tile of a snippet (same decision in all gather threads)
-        named_bar_sync(5, kF1GatherWarps * 32);        // nobody still reads the previous snippet's entries
-        if (gt < p.planes) {
-          const int4 e = __ldg(table4 + (size_t)tn * p.planes + gt);   // image id, crop top, crop left, flip
-          pl_base[gt] = (unsigned long long)e.x * p.image_bytes + ((unsigned long long)e.y * p.img_w + e.z) * IMG_C;
-          if (e.w) atomicOr(&pl_flip[0], 1u << gt); else atomicAnd(&pl_flip[0], ~(1u << gt));
-        }
-        if (gt == 0) pl_flip[1] = tn;
-        named_bar_sync(5, kF1GatherWarps * 32);
-      }
-      const int y = (int)th * kF1TileH - 1 + prow, x = (int)tw * kF1TileW - 1 + pcol;
-      ok = has_px && (unsigned)y < (unsigned)kF1Crop && (unsigned)x < (unsigned)kF1Crop;   // else: the conv's zero padding
-      if (!ok) return;
-      const uint32_t flips = lds_u32(plf_u32);
-      const uint32_t off_n = (uint32_t)(y * p.img_w + x) * IMG_C, off_f = (uint32_t)(y * p.img_w + (kF1Crop - 1 - x)) * IMG_C;
-#pragma unroll
-      for (int pl = 0; pl < MAXCH / IMG_C; ++pl) {
-        if (pl < p.planes) {
-          const uint8_t* src = p.images + lds_u64(plb_u32 + 8 * pl) + (((flips >> pl) & 1u) ? off_f : off_n);   // hflip == reversed columns
-#pragma unroll
-          for (int k = 0; k < IMG_C; ++k) u[pl * IMG_C + k] = __ldg(src + k);
-        }
-      }
-    };
-    auto convert_tile = [&](uint32_t a_dst, const uint32_t (&u)[MAXCH], bool ok) {
-      if (!has_px) return;
-      uint32_t pk[MAXCH / 2];                          // bf16 pairs, channel order
-#pragma unroll
-      for (int c = 0; c < MAXCH; c += 2) {
-        uint32_t lo = 0, hi = 0;
-        if (ok && c < nch) {
-          const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c];
-          lo = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c]) * REP + (REP == 32 ? lane : 0)) * 2));
-        }
-        if (ok && c + 1 < nch) {
-          const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c + 1];
-          hi = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c + 1]) * REP + (REP == 32 ? lane : 0)) * 2));
-        }
-        pk[c / 2] = lo | (hi << 16);
-      }
-      const uint32_t row_addr = a_dst + (uint32_t)gt * 32u;
-#pragma unroll
-      for (int f = 0; f < MAXCH / 16; ++f) {           // full 16-channel planes: row p = channels 16f .. 16f+15 of pixel p
-        if (f < p.n_full) {
-          const uint32_t a = row_addr + (uint32_t)f * kF1PlaneBytes;
-          sts128(swz32(a), make_uint4(pk[8 * f], pk[8 * f + 1], pk[8 * f + 2], pk[8 * f + 3]));
-          sts128(swz32(a + 16), make_uint4(pk[8 * f + 4], pk[8 * f + 5], pk[8 * f + 6], pk[8 * f + 7]));
-        }
-      }
-      if (p.has_pair) {                                // pair plane: row p = [remaining channels of pixel p | of pixel p+1]
-        uint4 g = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int f = 0; f < MAXCH / 16; ++f)
-          if (f == p.n_full) g = make_uint4(pk[8 * f], pk[8 * f + 1], pk[8 * f + 2], pk[8 * f + 3]);
-        const uint32_t a = row_addr + (uint32_t)p.n_full * kF1PlaneBytes;
-        sts128(swz32(a), g);
-        if (gt > 0) sts128(swz32(a - 32 + 16), g);
-      }
-    };
-
+    const int nch = NCH_CT ? NCH_CT : p.planes * IMG_C;
+    const uint32_t lut_u32 = smem_u32(lut_s);
+    const uint32_t strips_u32 = smem_u32(strips), rowoff_u32 = smem_u32(rowoff), flip_u32 = smem_u32(flipmask);
     const uint32_t ring_u32 = smem_u32(a_ring);
     uint32_t stage = 0, phase = 0;
-    int tile = tile_begin;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && gt == 0;
-    long long t_load = 0, t_wait = 0, t_conv = 0, t_begin = clock64(), tq = 0;
-    if (tile < tile_end) load_tile(tile, ua, va_ok);
-    // two tiles per iteration so that the register sets alternate without copies
-    while (tile < tile_end) {
-      {
-        const int next = tile + 1;
+    long long t_strip = 0, t_wait = 0, t_conv = 0, t_fence = 0, t_begin = clock64(), tq = 0;
+    int segk = 0;
+    for (int seg = seg_begin; seg < seg_end; ++seg, ++segk) {
+      const int buf = segk & 1;
+      const uint32_t sphase = (uint32_t)(segk >> 1) & 1u;
+      const int tn = seg / kF1SegPerSnip, rem = seg - tn * kF1SegPerSnip;
+      const int th = rem >> 2, sq = rem & 3;
+      if (dbg) tq = clock64();
+      mbar_wait(&sfull_bar[buf], sphase, 600 + buf);
+      if (dbg) t_strip += clock64() - tq;
+      // per-segment constants of this pixel: its source row in every plane
+      const int y = th * kF1TileH - 1 + prow;
+      const bool yok = has_px && (unsigned)y < (unsigned)kF1Crop;
+      const uint32_t flips = lds_u32(flip_u32 + 4u * buf);
+      uint32_t src[kMaxPlanes];                                  // shared address of segment pixel 0 of this row, per plane
+#pragma unroll
+      for (int pl = 0; pl < kMaxPlanes; ++pl) {
+        src[pl] = 0;
+        if (yok && pl < p.planes) {
+          const int unit = pl * kF1Rows + prow;
+          src[pl] = strips_u32 + (uint32_t)buf * strip_bytes + (uint32_t)unit * kPitch +
+                    (uint32_t)lds_s32(rowoff_u32 + 4u * (uint32_t)(buf * units + unit));
+        }
+      }
+      for (int t = 0; t < kF1SegTiles; ++t) {
+        const int rel = t * kF1TileW + pcol;                     // pixel of the segment's 58-pixel row
+        const int x = sq * kF1SegTiles * kF1TileW - 1 + rel;
+        const bool ok = yok && (unsigned)x < (unsigned)kF1Crop;   // else: the conv's zero padding
         if (dbg) tq = clock64();
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-        if (dbg) { const long long t = clock64(); t_wait += t - tq; tq = t; }
-        convert_tile(ring_u32 + stage * a_stage_bytes, ua, va_ok);
-        // generic-proxy stores -> visible to the tensor core's async-proxy reads.  ptxas implements this fence with a
-        // MEMBAR.ALL.CTA, which also waits for every global load in flight: the next tile's loads are therefore issued
-        // AFTER it (issued before, the fence exposed their whole L2 latency on every tile).
-        fence_proxy_async_smem();
-        if (dbg) { const long long t = clock64(); t_conv += t - tq; tq = t; }
+        if (dbg) { const long long tt = clock64(); t_wait += tt - tq; tq = tt; }
+        if (has_px) {
+          // two passes so that the loads of a pass are independent and issue back to back: source bytes, then table values
+          // straight-line code: pixels outside the crop read a harmless address and are zeroed by a select (a branch per
+          // channel around the volatile loads cost ~50 clk each, 850 clk per RGB tile); `ch < nch` is warp-uniform
+          uint32_t u[MAXCH];
+#pragma unroll
+          for (int ch = 0; ch < MAXCH; ++ch) {
+            u[ch] = 0;
+            if (ch < nch) {
+              const int pl = ch / IMG_C, k = ch - pl * IMG_C;
+              const int step = ((flips >> pl) & 1u) ? -rel * IMG_C : rel * IMG_C;
+              u[ch] = lds_u8(ok ? src[pl] + (uint32_t)(step + k) : lut_u32);
+            }
+          }
+          uint32_t pk[MAXCH / 2];                                // bf16 pairs, channel order
+#pragma unroll
+          for (int c = 0; c < MAXCH; c += 2) {
+            uint32_t lo = 0, hi = 0;
+            if (c < nch) {
+              const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c];
+              lo = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c]) * REP + (REP == 32 ? lane : 0)) * 2));
+            }
+            if (c + 1 < nch) {
+              const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c + 1];
+              hi = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c + 1]) * REP + (REP == 32 ? lane : 0)) * 2));
+            }
+            pk[c / 2] = ok ? (lo | (hi << 16)) : 0u;
+          }
+          const uint32_t row_addr = ring_u32 + stage * a_stage_bytes + (uint32_t)gt * 32u;
+#pragma unroll
+          for (int f = 0; f < MAXCH / 16; ++f) {         // full 16-channel planes: row p = channels 16f .. 16f+15 of pixel p
+            if (f < n_full) {
+              const uint32_t a = row_addr + (uint32_t)f * kF1PlaneBytes;
+              sts128(swz32(a), make_uint4(pk[8 * f], pk[8 * f + 1], pk[8 * f + 2], pk[8 * f + 3]));
+              sts128(swz32(a + 16), make_uint4(pk[8 * f + 4], pk[8 * f + 5], pk[8 * f + 6], pk[8 * f + 7]));
+            }
+          }
+          if (has_pair) {                                // pair plane: row p = [remaining channels of pixel p | of pixel p+1]
+            uint4 g = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int f = 0; f < MAXCH / 16; ++f)
+              if (f == n_full) g = make_uint4(pk[8 * f], pk[8 * f + 1], pk[8 * f + 2], pk[8 * f + 3]);
+            const uint32_t a = row_addr + (uint32_t)n_full * kF1PlaneBytes;
+            sts128(swz32(a), g);
+            if (gt > 0) sts128(swz32(a - 32 + 16), g);
+          }
+        }
+        if (dbg) { const long long tt = clock64(); t_conv += tt - tq; tq = tt; }
+        fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        if (dbg) t_fence += clock64() - tq;
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == kF1Stages) { stage = 0; phase ^= 1; }
-        if (next < tile_end) load_tile(next, ub, vb_ok);
-        if (dbg) { const long long t = clock64(); t_load += t - tq; tq = t; }
-        tile = next;
       }
-      if (tile >= tile_end) break;
-      {
-        const int next = tile + 1;
-        if (dbg) tq = clock64();
-        mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-        if (dbg) { const long long t = clock64(); t_wait += t - tq; tq = t; }
-        convert_tile(ring_u32 + stage * a_stage_bytes, ub, vb_ok);
-        fence_proxy_async_smem();
-        if (dbg) { const long long t = clock64(); t_conv += t - tq; tq = t; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
-        if (++stage == kF1Stages) { stage = 0; phase ^= 1; }
-        if (next < tile_end) load_tile(next, ua, va_ok);
-        if (dbg) { const long long t = clock64(); t_load += t - tq; tq = t; }
-        tile = next;
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty_bar[buf]);      // this warp no longer reads the strip
     }
-    if (dbg) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = t_load; p.dbg[2] = t_wait; p.dbg[3] = t_conv; p.dbg[11] = tile_end - tile_begin; }
+    if (dbg) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = t_strip; p.dbg[2] = t_wait; p.dbg[3] = t_conv; p.dbg[12] = t_fence; p.dbg[11] = n_tiles; }
   } else if (warp == kMmaWarp) {
     // ===================================================== MMA issuer (convergent warp, one elected lane issues)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64);
@@ -280,7 +358,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
     uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
     long long t_te = 0, t_full = 0, t_begin = clock64();
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = 0; tile < n_tiles; ++tile) {
       long long tq = dbg ? clock64() : 0;
       mbar_wait(&tempty_bar[as], as_phase ^ 1, 200 + as);
       if (dbg) { const long long t = clock64(); t_te += t - tq; tq = t; }
@@ -310,15 +388,13 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
     // two staging buffers per group: a TMA store holds its buffer until the store engine has read it
     uint8_t* stage_base = staging + eg * 2 * kF1StagingBytes;
     const uint32_t as = (uint32_t)eg;
-    int it = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && et == 0 && eg == 0;
     long long t_tf = 0, t_st = 0, t_begin = clock64();
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-      if ((it & 1) != eg) continue;
+    for (int it = eg; it < n_tiles; it += 2) {
       const uint32_t as_phase = (uint32_t)(it >> 1) & 1u;
-      uint32_t mt, tw, th, tn;
-      p.div_w.divmod((uint32_t)tile, mt, tw);
-      p.div_h.divmod(mt, tn, th);
+      const int seg = seg_begin + it / kF1SegTiles, t = it % kF1SegTiles;
+      const int tn = seg / kF1SegPerSnip, rem = seg - tn * kF1SegPerSnip;
+      const int th = rem >> 2, tw = (rem & 3) * kF1SegTiles + t;
       long long tq = dbg ? clock64() : 0;
       mbar_wait(&tfull_bar[as], as_phase, 400 + as);
       if (dbg) t_tf += clock64() - tq;
@@ -361,7 +437,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
       named_bar_sync(1 + eg, 128);
       if (et < 32) {
         if (elect_one()) {
-          tma_store_4d(&tmO, stage_out, 0, (int)tw * kF1TileW, (int)th * kF1TileH, (int)tn);
+          tma_store_4d(&tmO, stage_out, 0, tw * kF1TileW, th * kF1TileH, tn);
           tma_store_commit();
         }
         __syncwarp();
@@ -451,9 +527,9 @@ EncodeTiledFn encode_fn() {
 
 thread_local char g_err1[256];
 
-template <int IMG_C, int MAXCH, int REP>
+template <int IMG_C, int MAXCH, int REP, int NCH_CT>
 const char* launch_fused(const CUtensorMap& tO, const Conv1FusedParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = conv1_fused_kernel<IMG_C, MAXCH, REP>;
+  auto kfn = conv1_fused_kernel<IMG_C, MAXCH, REP, NCH_CT>;
   static size_t configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -511,10 +587,10 @@ const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h
   p.w_packed = static_cast<const __nv_bfloat16*>(w_fused);
   p.bias = bias;
   p.dbg = conv_get_debug_counters();
-  const int tiles_w = kF1Crop / kF1TileW, tiles_h = kF1Crop / kF1TileH;
-  p.total_tiles = n * tiles_w * tiles_h;
-  p.div_w = FastDiv::make((uint32_t)tiles_w);
-  p.div_h = FastDiv::make((uint32_t)tiles_h);
+  p.total_segments = n * kF1SegPerSnip;
+  // the loader copies 16-byte blocks clamped to the image: image bases and sizes must keep that alignment
+  if ((image_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(images) & 15) != 0 || image_bytes < (size_t)f1_copy_bytes(img_c))
+    return "conv1_fused: the image store must be 16-byte aligned with a 16-byte multiple per image";
 
   EncodeTiledFn fn = encode_fn();
   if (!fn) return "cuTensorMapEncodeTiled not available (no CUDA driver?)";
@@ -530,16 +606,23 @@ const char* conv1_fused_run(const uint8_t* images, size_t image_bytes, int img_h
   }
   const bool rep32 = img_c == 1 && p.n_luts == 1;
   const int rep = rep32 ? 32 : 1;
+  const size_t units = (size_t)planes * kF1Rows;
   const size_t smem = 1024 + 4 * kF1StagingBytes + (size_t)p.n_mma * 2048 + (size_t)kF1Stages * (p.n_full + p.has_pair) * kF1PlaneBytes +
-                      (size_t)p.n_luts * 256 * rep * 2 + 64 * 4 + 32 * 8 + 8 + (2 * kF1Stages + 4) * 8 + 16;
+                      (size_t)p.n_luts * 256 * rep * 2 + 64 * 4 + 2 * units * f1_row_pitch(img_c) + 2 * units * 4 + 8 +
+                      (2 * kF1Stages + 8) * 8 + 16;
+  if (smem > 232448) {
+    snprintf(g_err1, sizeof(g_err1), "conv1_fused: %d planes need %zu B of shared memory (strips + operand ring), 232448 available", planes, smem);
+    return g_err1;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int grid = p.total_segments < sms ? p.total_segments : sms;
   // MAXCH = channel registers per gather thread (multiple of 16)
-  if (img_c == 3) return launch_fused<3, 16, 1>(tO, p, grid, smem, st);
-  if (planes <= 16) return rep32 ? launch_fused<1, 16, 32>(tO, p, grid, smem, st) : launch_fused<1, 16, 1>(tO, p, grid, smem, st);
-  return rep32 ? launch_fused<1, 32, 32>(tO, p, grid, smem, st) : launch_fused<1, 32, 1>(tO, p, grid, smem, st);
+  if (img_c == 3) return launch_fused<3, 16, 1, 3>(tO, p, grid, smem, st);
+  if (planes == 20 && rep32) return launch_fused<1, 32, 32, 20>(tO, p, grid, smem, st);       // the path's flow stack
+  if (planes <= 16) return rep32 ? launch_fused<1, 16, 32, 0>(tO, p, grid, smem, st) : launch_fused<1, 16, 1, 0>(tO, p, grid, smem, st);
+  return rep32 ? launch_fused<1, 32, 32, 0>(tO, p, grid, smem, st) : launch_fused<1, 32, 1, 0>(tO, p, grid, smem, st);
 }
 
 }  // namespace va

@@ -95,7 +95,10 @@ class TwoStreamEvaluator:
         self.spatial, self.temporal, self.store = spatial, temporal, store
         self.combined = combined if combined is not None else CombinedModel()
         self.L = L
-        self.fused_front_end = False      # True: gather the crops inside conv1_1 (va_forward_store) instead of the K1 tensor
+        # True (default since the loader/converter version of the kernel): the crops are gathered inside conv1_1
+        # (va_forward_store), no preprocessed tensor exists in HBM; False / VA_FUSED_FRONT_END=0: K1 tensor + va_forward
+        import os as _os
+        self.fused_front_end = _os.environ.get("VA_FUSED_FRONT_END", "1") == "1"
         self._tables: Dict[int, tuple] = {}
         self.mean_s, self.std_s = list(NORM_MEANS_TF), list(NORM_STDS_TF)
         self.mean_t, self.std_t = [FLOW_NORM_MEAN] * (2 * L), [FLOW_NORM_STD] * (2 * L)
@@ -228,7 +231,8 @@ class TwoStreamEvaluator:
     def _stream(self, net: ops.StreamNet, images, shape, table, mean, std):
         """One stream over a table of snippets -> (descriptors, softmax scores).  bf16 handles gather the crops inside the
         first convolution (va_forward_store); fp32-parity handles go through the K1 tensor (va_preprocess + va_forward)."""
-        if self.fused_front_end and net.precision == "bf16":
+        if (self.fused_front_end and net.precision == "bf16" and
+                ops.StreamNet.forward_store_supported(images, shape, int(table.shape[1]))):
             desc, _, prob, _ = net.forward_store(images, shape, table, mean, std, want_logits=False, want_pred=False)
         else:
             x = ops.preprocess(images, shape, table, mean, std, c_pad=net.c_pad)

@@ -285,6 +285,16 @@ class StreamNet:
                                            ptr(desc), ptr(logits), ptr(probs), ptr(pred), stream_ptr()), "va_forward_store")
         return desc, logits, probs, pred
 
+    @staticmethod
+    def forward_store_supported(images: torch.Tensor, image_shape: Sequence[int], planes: int) -> bool:
+        """What the fused gather + conv1_1 kernel needs from the store (csrc/va_conv1_fused.cu): one RGB image or a stack
+        of 1-channel images per snippet, at least 224 x 224, 16-byte aligned with a 16-byte multiple per image (the loader
+        copies 16-byte blocks), and a plane count whose strips fit in shared memory."""
+        h, wd, c = image_shape
+        if not ((c == 3 and planes == 1) or (c == 1 and 1 <= planes <= 24)):
+            return False
+        return h >= CROP and wd >= CROP and (h * wd * c) % 16 == 0 and images.data_ptr() % 16 == 0
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().va_destroy(self._h)
