@@ -272,6 +272,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
       const int y = th * kF1TileH - 1 + prow;
       const bool yok = has_px && (unsigned)y < (unsigned)kF1Crop;
       const uint32_t flips = lds_u32(flip_u32 + 4u * buf);
+      const uint32_t all_planes = p.planes >= 32 ? 0xffffffffu : ((1u << p.planes) - 1u);
       uint32_t src[kMaxPlanes];                                  // shared address of segment pixel 0 of this row, per plane
 #pragma unroll
       for (int pl = 0; pl < kMaxPlanes; ++pl) {
@@ -290,32 +291,45 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmO, const Conv1FusedPara
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
         if (dbg) { const long long tt = clock64(); t_wait += tt - tq; tq = tt; }
         if (has_px) {
-          // two passes so that the loads of a pass are independent and issue back to back: source bytes, then table values
-          // straight-line code: pixels outside the crop read a harmless address and are zeroed by a select (a branch per
-          // channel around the volatile loads cost ~50 clk each, 850 clk per RGB tile); `ch < nch` is warp-uniform
-          uint32_t u[MAXCH];
-#pragma unroll
-          for (int ch = 0; ch < MAXCH; ++ch) {
-            u[ch] = 0;
-            if (ch < nch) {
-              const int pl = ch / IMG_C, k = ch - pl * IMG_C;
-              const int step = ((flips >> pl) & 1u) ? -rel * IMG_C : rel * IMG_C;
-              u[ch] = lds_u8(ok ? src[pl] + (uint32_t)(step + k) : lut_u32);
-            }
-          }
+          // two passes so that the loads of a pass are independent and issue back to back: source bytes, then table values.
+          // ONE branch per pixel (outside the crop -> zeros; divergent only in border tiles), and warp-uniform fast paths
+          // for the common flip patterns -- none / all planes, the 25 x 10 protocol -- so that the per-channel work is a byte
+          // load, an index and a table load (a branch per channel around the volatile loads cost ~50 clk each).
           uint32_t pk[MAXCH / 2];                                // bf16 pairs, channel order
 #pragma unroll
-          for (int c = 0; c < MAXCH; c += 2) {
-            uint32_t lo = 0, hi = 0;
-            if (c < nch) {
-              const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c];
-              lo = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c]) * REP + (REP == 32 ? lane : 0)) * 2));
+          for (int c = 0; c < MAXCH / 2; ++c) pk[c] = 0u;
+          if (ok) {
+            uint32_t u[MAXCH];
+            const int relb = rel * IMG_C;
+            if (flips == 0u) {
+#pragma unroll
+              for (int ch = 0; ch < MAXCH; ++ch)
+                if (ch < nch) u[ch] = lds_u8(src[ch / IMG_C] + (uint32_t)(relb + ch % IMG_C));
+            } else if (flips == all_planes) {
+#pragma unroll
+              for (int ch = 0; ch < MAXCH; ++ch)
+                if (ch < nch) u[ch] = lds_u8(src[ch / IMG_C] + (uint32_t)(ch % IMG_C - relb));
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < MAXCH; ++ch)
+                if (ch < nch) {
+                  const int pl = ch / IMG_C;
+                  u[ch] = lds_u8(src[pl] + (uint32_t)((((flips >> pl) & 1u) ? -relb : relb) + ch % IMG_C));
+                }
             }
-            if (c + 1 < nch) {
-              const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c + 1];
-              hi = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c + 1]) * REP + (REP == 32 ? lane : 0)) * 2));
+#pragma unroll
+            for (int c = 0; c < MAXCH; c += 2) {
+              uint32_t lo = 0, hi = 0;
+              if (c < nch) {
+                const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c];
+                lo = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c]) * REP + (REP == 32 ? lane : 0)) * 2));
+              }
+              if (c + 1 < nch) {
+                const int li = (REP == 32 || p.n_luts == 1) ? 0 : (int)p.lut_of[c + 1];
+                hi = lds_u16(lut_u32 + (uint32_t)(((li * 256 + (int)u[c + 1]) * REP + (REP == 32 ? lane : 0)) * 2));
+              }
+              pk[c / 2] = lo | (hi << 16);
             }
-            pk[c / 2] = ok ? (lo | (hi << 16)) : 0u;
           }
           const uint32_t row_addr = ring_u32 + stage * a_stage_bytes + (uint32_t)gt * 32u;
 #pragma unroll
