@@ -559,12 +559,28 @@ def main():
                         "h2d_bytes_per_step": int(sum(x[2] for x in sets_) + tab_bytes), "d2h_bytes_per_step": d2h,
                         "images_decoded_per_step": int(sum(x[0].n for x in sets_))}
 
-            e2e_jpeg = timed_jpeg_run("video")
+            # VA_JPEG_PRIORITY=1 runs the networks on a HIGH-priority stream in this leg (the block scheduler then places a
+            # layer's CTAs before pending decoder blocks).  Measured: worse -- the decoder is starved and the step waits for
+            # it (video-like content 16.6 k -> 11.5 k snippets/s, noise unchanged at 14.7 k), so it is off.
+            prio = os.environ.get("VA_JPEG_PRIORITY", "0") == "1"
+            hi_stream = torch.cuda.Stream(priority=-1) if prio else None
+
+            def with_priority(fn, *a):
+                if hi_stream is None:
+                    return fn(*a)
+                hi_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(hi_stream):
+                    r_ = fn(*a)
+                torch.cuda.current_stream().wait_stream(hi_stream)
+                return r_
+
+            e2e_jpeg = with_priority(timed_jpeg_run, "video")
+            e2e_jpeg["network_stream_priority"] = "high" if prio else "default"
             e2e_jpeg["content"] = ("video-like frames and flow images (low-frequency structure + noise sigma 3, ~25 KB per file: the "
                                    "bit rate of real UCF101 frames); network inputs are whatever the files decode to")
             e2e_jpeg["input"] = ("JPEG files (cv2.imwrite format) in pinned host memory -> H2D -> CUDA decode (side stream, two steps "
                                  "ahead) -> K1 -> networks -> fusion -> D2H")
-            worst = timed_jpeg_run("noise")
+            worst = with_priority(timed_jpeg_run, "noise")
             worst["content"] = ("the synthetic store's hash-noise pixels (~67 KB per file, no EOB, every coefficient non-zero): the "
                                 "entropy decoder's worst case")
             e2e_jpeg["worst_case_noise"] = worst
