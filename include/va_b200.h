@@ -263,12 +263,13 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
  * the kernel is bit-identical to it).  One 16-CTA thread-block cluster solves one pair entirely on chip.
  *   images:     u8 store as for va_preprocess, image `id` at images + id*image_bytes, [img_h][img_w][img_c], img_c 1 or 3 (RGB)
  *   pair_table: DEVICE int32 [n][4] = {id of frame t-1, id of frame t, OUTPUT id of the x image, OUTPUT id of the y image};
- *               output image `k` is written as u8 [img_h][img_w] at out_images + k*out_image_bytes
+ *               output image `k` is written as u8 [H][W] at out_images + k*out_image_bytes, (H, W) = (img_h, img_w) or the
+ *               resize target of `params` (the tool's frame resize, pinned to cv2.resize in the oracle's tests)
  *   params:     HOST struct, NULL = the defaults below
  *   flow_f32:   optional fp32 [n][2][img_h][img_w] (x then y displacement); iterations: optional int32
  *               [n][nscales_used*warps] inner iterations run per (level, warp) in processing order (coarsest level first)
  *   workspace:  DEVICE scratch of va_tvl1_workspace_bytes(img_h, img_w, params) bytes
- * Limits: img_w <= 704 and ceil(img_h/16) * img_w <= 5504 (the on-chip band capacity: 340x256 and 320x240 fit);
+ * Limits (of the size the flow is computed at): W <= 704 and ceil(H/16) * W <= 5504 (the on-chip band capacity: 340x256 and 320x240 fit);
  * anything larger returns VA_ERR_UNSUPPORTED.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct va_tvl1_params {
@@ -281,6 +282,8 @@ typedef struct va_tvl1_params {
   int nscales;         /* 5 */
   int warps;           /* 5 */
   int iterations;      /* 300 */
+  int resize_w;        /* 0 = flow at the frames' own size; else cv::resize(frame, Size(resize_w, resize_h), INTER_LINEAR) first, */
+  int resize_h;        /*     as dense_flow does with TSN's new_size 340 x 256; outputs are then [resize_h][resize_w]            */
   int reserved;
 } va_tvl1_params;
 size_t va_tvl1_workspace_bytes(int img_h, int img_w, const va_tvl1_params* params);

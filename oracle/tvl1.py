@@ -16,7 +16,8 @@ sqrt(x*x + y*y)).  The CUDA kernel (csrc/va_tvl1.cu) uses the same operations th
 and oracle agree BIT FOR BIT on the u8 images and on the fp32 flow; what is unpinned is only how close this restatement
 is to the third-party tool's own rounding (its nvcc build contracts multiply-adds).
 
-What IS pinned: the grey conversion (`cv2.cvtColor(BGR2GRAY)`, run in this container; tests/golden/tvl1_*.npz) and the
+What IS pinned: the frame resize and the grey conversion (`cv2.resize` INTER_LINEAR, `cv2.cvtColor(BGR2GRAY)`, run in this
+container; tests/test_tvl1_oracle.py, tests/golden/tvl1_*.npz) and the
 8-bit conversion rule (dense_flow's CAST macro: round-half-even of 255*(v+bound)/(2*bound), saturated).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
@@ -52,6 +53,43 @@ def gray_from_rgb(rgb: np.ndarray) -> np.ndarray:
     g = rgb[..., 1].astype(np.int32)
     b = rgb[..., 2].astype(np.int32)
     return ((r * 9798 + g * 19235 + b * 3735 + 16384) >> 15).astype(np.uint8)
+
+
+def resize_linear_u8(src: np.ndarray, dh: int, dw: int) -> np.ndarray:
+    """cv::resize(src, Size(dw, dh), INTER_LINEAR) on u8 images, the resize TSN's dense_flow applies to every frame before the
+    flow (`new_size` 340 x 256).  OpenCV's fixed-point path: source position (d + 0.5) * scale - 0.5 evaluated in double and
+    cast to float, 11-bit coefficients round-half-even((1 - f) * 2048) / (f * 2048); horizontally the fraction is zeroed where the
+    position leaves the image, vertically only the row indices are clamped (so the first / last rows blend a row with itself
+    using both coefficients); horizontal pass in int32, vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+    PINNED: equal to cv2.resize of this container's OpenCV 4.13 on up- and down-scaling cases (tests/test_tvl1_oracle.py)."""
+    sh, sw = src.shape[:2]
+
+    def coeffs(dn, sn, clamp_fraction):
+        scale = sn / dn
+        d = np.arange(dn, dtype=np.float64)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        fr = (f - s.astype(np.float32)).astype(np.float32)
+        if clamp_fraction:
+            lo = s < 0
+            fr[lo] = 0
+            s[lo] = 0
+            hi = s >= sn - 1
+            fr[hi] = 0
+            s[hi] = sn - 1
+        c0 = np.rint((np.float32(1.0) - fr) * np.float32(2048)).astype(np.int64)
+        c1 = np.rint(fr * np.float32(2048)).astype(np.int64)
+        return np.clip(s, 0, sn - 1), np.clip(s + 1, 0, sn - 1), c0, c1
+
+    xs, xs1, a0, a1 = coeffs(dw, sw, True)
+    ys, ys1, b0, b1 = coeffs(dh, sh, False)
+    S = src.astype(np.int64)
+    if S.ndim == 2:
+        S = S[..., None]
+    hp = S[:, xs, :] * a0[None, :, None] + S[:, xs1, :] * a1[None, :, None]
+    r0, r1 = hp[ys], hp[ys1]
+    out = ((((b0[:, None, None] * (r0 >> 4)) >> 16) + ((b1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2).clip(0, 255).astype(np.uint8)
+    return out if src.ndim == 3 else out[..., 0]
 
 
 def pyramid_sizes(h: int, w: int, p: TVL1Params):
@@ -259,9 +297,14 @@ def flow_to_u8(u: np.ndarray, bound: float) -> np.ndarray:
     return q.astype(np.uint8)
 
 
-def flow_images(frame0_rgb: np.ndarray, frame1_rgb: np.ndarray, params: TVL1Params | None = None):
+def flow_images(frame0_rgb: np.ndarray, frame1_rgb: np.ndarray, params: TVL1Params | None = None, new_size=None):
     """The whole producer for one frame pair: RGB u8 frames -> (flow_x u8, flow_y u8), the images temporalModel.py:80-81
-    opens."""
+    opens.  new_size = (width, height): dense_flow's resize of every frame before the grey conversion (TSN: 340 x 256)."""
     p = params or TVL1Params()
-    u1, u2 = tvl1_flow(gray_from_rgb(frame0_rgb), gray_from_rgb(frame1_rgb), p)
+    if new_size is not None:
+        frame0_rgb = resize_linear_u8(frame0_rgb, new_size[1], new_size[0])
+        frame1_rgb = resize_linear_u8(frame1_rgb, new_size[1], new_size[0])
+    g0 = gray_from_rgb(frame0_rgb) if frame0_rgb.ndim == 3 else frame0_rgb
+    g1 = gray_from_rgb(frame1_rgb) if frame1_rgb.ndim == 3 else frame1_rgb
+    u1, u2 = tvl1_flow(g0, g1, p)
     return flow_to_u8(u1, p.bound), flow_to_u8(u2, p.bound)

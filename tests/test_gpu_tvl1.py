@@ -75,6 +75,59 @@ def test_full_size_tsn_images_and_many_pairs():
         assert np.array_equal(fl[k], fl[k % 2])
 
 
+def test_frame_resize_to_the_tsn_flow_size():
+    """UCF101 frames (240 x 320) resized to 340 x 256 first, as dense_flow does (cv::resize pinned to cv2 in the oracle's
+    tests): u8 flow images and fp32 flow bit-equal to the oracle, written into the DEFAULT store layout's 256 x 340 images."""
+    from video_analytics_b200.store import DeviceStore, make_layout
+    p = flow.TVL1Params(new_size=(340, 256))
+    clip = flow.synthetic_clip(3, 240, 320, seed=51)
+    fr = torch.from_numpy(clip).cuda()
+    fx, fy, fl = flow.flow_images(fr, params=p, return_flow=True)
+    assert tuple(fx.shape) == (2, 256, 340)
+    for k in range(2):
+        ox, oy = otv.flow_images(clip[k], clip[k + 1], otv.TVL1Params(), new_size=(340, 256))
+        assert np.array_equal(fx[k].cpu().numpy(), ox) and np.array_equal(fy[k].cpu().numpy(), oy)
+    g0 = otv.gray_from_rgb(otv.resize_linear_u8(clip[0], 256, 340))
+    g1 = otv.gray_from_rgb(otv.resize_linear_u8(clip[1], 256, 340))
+    u1, u2 = otv.tvl1_flow(g0, g1)
+    assert np.array_equal(fl[0, 0].cpu().numpy(), u1) and np.array_equal(fl[0, 1].cpu().numpy(), u2)
+    lay = make_layout(1, min_frames=3, frame_span=1, flows_per_frame=1)            # default shapes: 240x320x3 frames, 256x340 flow
+    store = DeviceStore(lay)
+    m = lay.videos[0]
+    cnt = flow.fill_flow_store(store, 0, fr, params=p)
+    imgs = store.flow.view(-1, 256, 340)
+    assert cnt == 2 and torch.equal(imgs[m.flowx_first:m.flowx_first + 2], fx) and torch.equal(imgs[m.flowy_first:m.flowy_first + 2], fy)
+
+
+def test_video_to_flow_tree(tmp_path):
+    """convertVideosToFlow: list line -> <root>/<Category>/<video>.avi -> flow_x_%04d.jpg / flow_y_%04d.jpg, the directory
+    TemporalDataset walks (temporalModel.py:76-81); the pixels are the oracle's on the frames cv2.VideoCapture decodes."""
+    cv2 = pytest.importorskip("cv2")
+    import os
+    clip = flow.synthetic_clip(5, 240, 320, seed=61)
+    root, save = tmp_path / "videos", tmp_path / "flow"
+    (root / "Archery").mkdir(parents=True)
+    path = str(root / "Archery" / "v_Archery_g01_c01.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (320, 240))
+    if not vw.isOpened():
+        pytest.skip("no video writer in this OpenCV build")
+    for f in clip:
+        vw.write(np.ascontiguousarray(f[..., ::-1]))
+    vw.release()
+    lst = tmp_path / "list.txt"
+    lst.write_text("Archery/v_Archery_g01_c01.avi 1\n")
+    assert flow.convertVideosToFlow(str(root), str(save), str(lst), mode="train") == 1
+    out = save / "Archery" / "v_Archery_g01_c01"
+    names = sorted(os.listdir(out))
+    assert names == ["flow_x_%04d.jpg" % k for k in range(1, 5)] + ["flow_y_%04d.jpg" % k for k in range(1, 5)]
+    frames = flow.read_video_frames(path)
+    assert frames.shape == (5, 240, 320, 3)
+    ox, oy = otv.flow_images(frames[0], frames[1], otv.TVL1Params(), new_size=(340, 256))
+    want = cv2.imdecode(cv2.imencode(".jpg", ox, [cv2.IMWRITE_JPEG_QUALITY, 95])[1], cv2.IMREAD_GRAYSCALE)
+    got = cv2.imread(str(out / "flow_x_0001.jpg"), cv2.IMREAD_GRAYSCALE)
+    assert got.shape == (256, 340) and np.array_equal(got, want)
+
+
 def test_parameters_and_saturation():
     """Non-default parameters (fewer levels/warps, no early stop, small bound so that the 8-bit mapping saturates)."""
     p = flow.TVL1Params(tau=0.2, lambda_=0.1, theta=0.25, nscales=3, warps=2, epsilon=0.0, iterations=40, scale_step=0.7, bound=1.0)

@@ -15,6 +15,15 @@ def test_gray_equals_cv2_on_every_colour():
     assert np.array_equal(tvl1.gray_from_rgb(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
 
 
+@pytest.mark.parametrize("shape,dsize", [((240, 320, 3), (340, 256)), ((240, 320), (340, 256)), ((77, 101, 3), (64, 48)),
+                                         ((256, 340, 3), (320, 240)), ((31, 17), (200, 300)), ((480, 640, 3), (340, 256))])
+def test_frame_resize_equals_cv2(shape, dsize):
+    """dense_flow resizes every frame to TSN's new_size before the flow: the restated fixed-point bilinear equals cv2."""
+    cv2 = pytest.importorskip("cv2")
+    img = np.random.default_rng(sum(shape)).integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(tvl1.resize_linear_u8(img, dsize[1], dsize[0]), cv2.resize(img, dsize, interpolation=cv2.INTER_LINEAR))
+
+
 def test_golden_reproduces(golden):
     g = golden("tvl1_small.npz")
     assert np.array_equal(tvl1.gray_from_rgb(g["clip_a"][0]), g["gray_a_cv2"][0])

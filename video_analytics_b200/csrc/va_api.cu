@@ -663,14 +663,15 @@ va_status va_tvl1_debug_cycles(long long* dev_cycles) {
 static va_tvl1_params tvl1_defaults() {
   va_tvl1_params d;
   d.tau = 0.25; d.lambda = 0.15; d.theta = 0.3; d.epsilon = 0.01; d.scale_step = 0.8; d.bound = 20.0;
-  d.nscales = 5; d.warps = 5; d.iterations = 300; d.reserved = 0;
+  d.nscales = 5; d.warps = 5; d.iterations = 300; d.resize_w = 0; d.resize_h = 0; d.reserved = 0;
   return d;
 }
 
 size_t va_tvl1_workspace_bytes(int img_h, int img_w, const va_tvl1_params* params) {
   const va_tvl1_params d = params ? *params : tvl1_defaults();
   if (img_h < 1 || img_w < 1 || d.nscales < 1 || !(d.scale_step > 0.0 && d.scale_step < 1.0)) return 0;
-  return va::tvl1_workspace_bytes(img_h, img_w, d.nscales, d.scale_step);
+  const bool rs = d.resize_w > 0 && d.resize_h > 0;
+  return va::tvl1_workspace_bytes(rs ? d.resize_h : img_h, rs ? d.resize_w : img_w, d.nscales, d.scale_step);
 }
 
 va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,
@@ -679,19 +680,22 @@ va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int
                        size_t workspace_bytes, va_stream_t stream) {
   if (n == 0) return VA_OK;
   if (!images || !pair_table || !out_images || !workspace) return fail(VA_ERR_INVALID, "va_tvl1_flow: NULL argument");
-  if (n < 0 || img_h < 16 || img_w < 16 || (img_c != 1 && img_c != 3))
-    return fail(VA_ERR_INVALID, "va_tvl1_flow: bad sizes n=%d %dx%dx%d (frames >= 16 pixels, 1 or 3 channels)", n, img_h, img_w, img_c);
-  if (image_bytes < (size_t)img_h * img_w * img_c || out_image_bytes < (size_t)img_h * img_w)
-    return fail(VA_ERR_INVALID, "va_tvl1_flow: image_bytes / out_image_bytes smaller than an image");
   const va_tvl1_params d = params ? *params : tvl1_defaults();
+  if ((d.resize_w > 0) != (d.resize_h > 0) || d.resize_w < 0 || d.resize_h < 0)
+    return fail(VA_ERR_INVALID, "va_tvl1_flow: resize_w / resize_h must both be set (or both 0)");
+  const int fh = d.resize_h > 0 ? d.resize_h : img_h, fw = d.resize_w > 0 ? d.resize_w : img_w;     // size the flow is computed at
+  if (n < 0 || fh < 16 || fw < 16 || img_h < 1 || img_w < 1 || (img_c != 1 && img_c != 3))
+    return fail(VA_ERR_INVALID, "va_tvl1_flow: bad sizes n=%d %dx%dx%d -> %dx%d (flow images >= 16 pixels, 1 or 3 channels)", n, img_h,
+                img_w, img_c, fh, fw);
+  if (image_bytes < (size_t)img_h * img_w * img_c || out_image_bytes < (size_t)fh * fw)
+    return fail(VA_ERR_INVALID, "va_tvl1_flow: image_bytes / out_image_bytes smaller than an image");
   if (!(d.tau > 0.0) || !(d.lambda > 0.0) || !(d.theta > 0.0) || !(d.epsilon >= 0.0) || !(d.bound > 0.0) ||
       !(d.scale_step > 0.0 && d.scale_step < 1.0) || d.nscales < 1 || d.nscales > 8 || d.warps < 1 || d.iterations < 1)
     return fail(VA_ERR_INVALID, "va_tvl1_flow: bad parameters");
-  if (img_w > 704 || (size_t)((img_h + 15) / 16) * img_w > 5504)
-    return fail(VA_ERR_UNSUPPORTED, "va_tvl1_flow: %dx%d exceeds the on-chip band capacity (width <= 704, ceil(h/16)*w <= 5504)",
-                img_h, img_w);
+  if (fw > 704 || (size_t)((fh + 15) / 16) * fw > 5504)
+    return fail(VA_ERR_UNSUPPORTED, "va_tvl1_flow: %dx%d exceeds the on-chip band capacity (width <= 704, ceil(h/16)*w <= 5504)", fh, fw);
   if (va_status s = require_sm100()) return s;
-  const char* e = va::tvl1_run(images, image_bytes, img_h, img_w, img_c, pair_table, n, d.tau, d.lambda, d.theta, d.nscales,
+  const char* e = va::tvl1_run(images, image_bytes, img_h, img_w, img_c, fh, fw, pair_table, n, d.tau, d.lambda, d.theta, d.nscales,
                                d.warps, d.epsilon, d.iterations, d.scale_step, d.bound, out_images, out_image_bytes, flow_f32,
                                iterations, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   if (e) return fail(VA_ERR_INVALID, "va_tvl1_flow: %s", e);

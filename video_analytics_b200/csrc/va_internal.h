@@ -71,7 +71,8 @@ const char* svm_fit_run(const double* X, const int32_t* class_index, int V, int 
 // ---- TV-L1 optical flow (va_tvl1.cu)
 size_t tvl1_workspace_bytes(int h, int w, int nscales, double scale_step);
 void tvl1_set_debug_cycles(long long* dev);
-const char* tvl1_run(const uint8_t* images, size_t image_bytes, int h, int w, int c, const int32_t* pairs, int n,
+// src_h x src_w: the stored frames; h x w: the size the flow is computed (and written) at -- different = cv::resize first
+const char* tvl1_run(const uint8_t* images, size_t image_bytes, int src_h, int src_w, int c, int h, int w, const int32_t* pairs, int n,
                      double tau, double lambda, double theta, int nscales, int warps, double epsilon, int iterations,
                      double scale_step, double bound, uint8_t* out, size_t out_bytes, float* flow, int32_t* stats,
                      void* workspace, size_t workspace_bytes, cudaStream_t st);

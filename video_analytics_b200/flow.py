@@ -28,7 +28,7 @@ from ._lib import VAError, check, ptr, stream_ptr
 class _CParams(C.Structure):
     _fields_ = [("tau", C.c_double), ("lambda_", C.c_double), ("theta", C.c_double), ("epsilon", C.c_double),
                 ("scale_step", C.c_double), ("bound", C.c_double), ("nscales", C.c_int), ("warps", C.c_int),
-                ("iterations", C.c_int), ("reserved", C.c_int)]
+                ("iterations", C.c_int), ("resize_w", C.c_int), ("resize_h", C.c_int), ("reserved", C.c_int)]
 
 
 @dataclass
@@ -43,10 +43,15 @@ class TVL1Params:
     iterations: int = 300
     scale_step: float = 0.8
     bound: float = 20.0
+    new_size: Optional[Tuple[int, int]] = None       # (width, height): dense_flow's frame resize before the flow (TSN: (340, 256))
 
     def _c(self) -> _CParams:
+        rw, rh = self.new_size if self.new_size is not None else (0, 0)
         return _CParams(self.tau, self.lambda_, self.theta, self.epsilon, self.scale_step, self.bound, self.nscales,
-                        self.warps, self.iterations, 0)
+                        self.warps, self.iterations, int(rw), int(rh), 0)
+
+    def out_shape(self, h: int, w: int) -> Tuple[int, int]:
+        return (int(self.new_size[1]), int(self.new_size[0])) if self.new_size is not None else (h, w)
 
     def levels(self, h: int, w: int) -> int:
         n = 1
@@ -87,11 +92,12 @@ def tvl1(images: torch.Tensor, image_shape: Tuple[int, int, int], pair_table: to
     p = params or TVL1Params()
     cp = p._c()
     n = int(pair_table.shape[0])
+    oh, ow = p.out_shape(h, w)
     ib = image_bytes if image_bytes is not None else h * w * c
-    ob = out_image_bytes if out_image_bytes is not None else h * w
+    ob = out_image_bytes if out_image_bytes is not None else oh * ow
     res = {}
-    flow = torch.empty((n, 2, h, w), dtype=torch.float32, device=images.device) if return_flow else None
-    its = torch.zeros((n, p.levels(h, w) * p.warps), dtype=torch.int32, device=images.device) if return_iterations else None
+    flow = torch.empty((n, 2, oh, ow), dtype=torch.float32, device=images.device) if return_flow else None
+    its = torch.zeros((n, p.levels(oh, ow) * p.warps), dtype=torch.int32, device=images.device) if return_iterations else None
     wsb = _workspace(h, w, cp, images.device)
     check(_lib.load().va_tvl1_flow(ptr(images), ib, h, w, c, ptr(pair_table), n, C.byref(cp), ptr(out_images), ob, ptr(flow),
                                    ptr(its), ptr(wsb), wsb.numel(), stream_ptr()), "va_tvl1_flow")
@@ -116,7 +122,8 @@ def flow_images(frames: torch.Tensor, *, params: Optional[TVL1Params] = None, st
     dev = frames.device
     k = torch.arange(m, dtype=torch.int32, device=dev)
     table = torch.stack([k, k + step, k, k + m], dim=1).contiguous()
-    out = torch.empty((2 * m, h, w), dtype=torch.uint8, device=dev)
+    oh, ow = (params or TVL1Params()).out_shape(h, w)
+    out = torch.empty((2 * m, oh, ow), dtype=torch.uint8, device=dev)
     res = tvl1(frames, (h, w, c), table, out, params=params, return_flow=return_flow)
     if return_flow:
         return out[:m], out[m:], res["flow"]
@@ -132,8 +139,10 @@ def fill_flow_store(store, video_index: int, frames: torch.Tensor, *, params: Op
     if frames.dim() == 3:
         frames = frames.unsqueeze(-1)
     n, h, w, c = frames.shape
-    if tuple(lay.flow_shape) != (h, w, 1):
-        raise ValueError(f"fill_flow_store: frames are {h}x{w} but the store's flow images are {lay.flow_shape}")
+    oh, ow = (params or TVL1Params()).out_shape(h, w)
+    if tuple(lay.flow_shape) != (oh, ow, 1):
+        raise ValueError(f"fill_flow_store: the flow images come out {oh}x{ow} (frames {h}x{w}, new_size "
+                         f"{(params or TVL1Params()).new_size}) but the store's flow images are {lay.flow_shape}")
     cnt = min(m.n_flows, n - 1)
     k = torch.arange(cnt, dtype=torch.int32, device=frames.device)
     table = torch.stack([k, k + 1, k + m.flowx_first, k + m.flowy_first], dim=1).contiguous()
@@ -188,3 +197,65 @@ def synthetic_clip(n_frames: int, h: int, w: int, *, seed: int = 0, channels: in
             v = 128.0 + 40.0 * v + rng.integers(-noise, noise + 1, size=(h, w))
             out[t, :, :, c] = np.clip(np.rint(v), 0, 255).astype(np.uint8)
     return out
+
+
+def read_video_frames(video_path: str):
+    """All frames of a video as RGB u8 [N, H, W, 3] (host decode with cv2.VideoCapture, like the reference's own frame
+    extractor utils.py:51-69; UCF101's .avi files are MPEG-4 ASP, which no NVDEC generation decodes)."""
+    import cv2
+    import numpy as np
+
+    cap = cv2.VideoCapture(video_path)
+    if not cap.isOpened():
+        raise ValueError("Error opening video file %s" % video_path)        # utils.py:56
+    frames = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        frames.append(fr[..., ::-1])
+    cap.release()
+    if not frames:
+        raise ValueError("no frames in %s" % video_path)
+    return np.ascontiguousarray(np.stack(frames))
+
+
+def extract_video_flow(video_path: str, out_dir: Optional[str] = None, *, params: Optional[TVL1Params] = None,
+                       step: int = 1, chunk: int = 64, quality: int = 95):
+    """TSN `dense_flow` (`extract_gpu -f video -x flow_x -y flow_y -b 20 -s 1`, new_size 340 x 256) for one video: every
+    frame pair (t - step, t) -> `flow_x_%04d.jpg` / `flow_y_%04d.jpg` numbered from 1 -- the files TemporalDataset lists
+    (temporalModel.py:76-81).  Frames are decoded on the host, resized + converted + solved on the GPU in chunks.
+    Returns (flow_x, flow_y) u8 device tensors [N - step, H, W]; writes the JPEGs when out_dir is given."""
+    p = params if params is not None else TVL1Params(new_size=(340, 256))
+    frames = read_video_frames(video_path)
+    n = frames.shape[0]
+    if n <= step:
+        raise ValueError("%s has %d frames, need more than %d" % (video_path, n, step))
+    xs, ys = [], []
+    for a in range(0, n - step, chunk):
+        b = min(n, a + chunk + step)
+        fx, fy = flow_images(torch.from_numpy(frames[a:b]).cuda(), params=p, step=step)
+        xs.append(fx)
+        ys.append(fy)
+    fx, fy = torch.cat(xs), torch.cat(ys)
+    if out_dir is not None:
+        write_flow_tree(out_dir, fx, fy, quality=quality)
+    return fx, fy
+
+
+def convertVideosToFlow(rootDir: str, saveDir: str, videoListLoc: str, mode: str = "train", *,
+                        params: Optional[TVL1Params] = None) -> int:
+    """The flow counterpart of the reference's convertVideosToFrames (utils.py:95-121): for every line of the video list,
+    `<rootDir>/<Category>/<video>.avi` -> `<saveDir>/<Category>/<video>/flow_{x,y}_%04d.jpg` -- the tree FLOW_DATA_DIR
+    points at (parameters.py:27).  Returns the number of videos converted."""
+    from .utils import videoInfo
+
+    done = 0
+    with open(videoListLoc) as f:
+        for line in f:
+            if not line.strip():
+                continue
+            loc, name, _, category, _, _ = videoInfo(line, mode)
+            extract_video_flow(os.path.join(rootDir, loc), os.path.join(saveDir, category, name), params=params)
+            done += 1
+    return done
