@@ -128,6 +128,38 @@ def test_video_to_flow_tree(tmp_path):
     assert got.shape == (256, 340) and np.array_equal(got, want)
 
 
+def test_store_straight_from_videos(tmp_path):
+    """DeviceStore.from_videos: video files -> (every 10th frame, all TV-L1 flow pairs) in HBM, the counts and pixels the
+    reference's two offline steps would have left on disk; the temporal protocol tables address it like any other store."""
+    cv2 = pytest.importorskip("cv2")
+    from video_analytics_b200.evaluate import temporal_table
+    from video_analytics_b200.store import DeviceStore
+    root = tmp_path / "videos"
+    lines = []
+    for v, (cat, nfr) in enumerate((("Archery", 23), ("Bowling", 31))):
+        (root / cat).mkdir(parents=True)
+        name = f"v_{cat}_g01_c0{v + 1}"
+        vw = cv2.VideoWriter(str(root / cat / (name + ".avi")), cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (320, 240))
+        if not vw.isOpened():
+            pytest.skip("no video writer in this OpenCV build")
+        for f in flow.synthetic_clip(nfr, 240, 320, seed=70 + v):
+            vw.write(np.ascontiguousarray(f[..., ::-1]))
+        vw.release()
+        lines.append(f"{cat}/{name}.avi {v + 1}\n")
+    store = DeviceStore.from_videos(lines, "train", str(root))
+    lay = store.layout
+    assert [(m.n_frames, m.n_flows, m.label) for m in lay.videos] == [(3, 22, 1), (4, 30, 2)]
+    assert lay.rgb_shape == (240, 320, 3) and lay.flow_shape == (256, 340, 1)
+    frames = flow.read_video_frames(str(root / "Bowling" / "v_Bowling_g01_c02.avi"))
+    m = lay.videos[1]
+    assert np.array_equal(store.rgb.view(-1, 240, 320, 3)[m.rgb_first + 2].cpu().numpy(), frames[20])       # frame "2.jpg" = video frame 20
+    ox, oy = otv.flow_images(frames[7], frames[8], otv.TVL1Params(), new_size=(340, 256))
+    fl = store.flow.view(-1, 256, 340)
+    assert np.array_equal(fl[m.flowx_first + 7].cpu().numpy(), ox) and np.array_equal(fl[m.flowy_first + 7].cpu().numpy(), oy)
+    tab = temporal_table(m, lay.flow_shape)                  # 250 snippets x 20 planes over this video's 30 flow pairs
+    assert tab.shape == (250, 20, 4) and tab[:, :, 0].min() >= m.flowx_first and tab[:, :, 0].max() < m.flowy_first + m.n_flows
+
+
 def test_parameters_and_saturation():
     """Non-default parameters (fewer levels/warps, no early stop, small bound so that the 8-bit mapping saturates)."""
     p = flow.TVL1Params(tau=0.2, lambda_=0.1, theta=0.25, nscales=3, warps=2, epsilon=0.0, iterations=40, scale_step=0.7, bound=1.0)

@@ -199,6 +199,66 @@ class DeviceStore:
         return self
 
     @classmethod
+    def from_videos(cls, video_lines, mode: str, videos_root: str, label_of=None, device=None, flow_params=None,
+                    sample_rate: int = VIDEO_FRAME_SAMPLE_RATE):
+        """Build BOTH stores straight from the video files, with no image files in between: what the reference prepares
+        offline in two steps -- convertVideosToFrames (every `sample_rate`-th frame -> `<i>.jpg`, utils.py:95-121) and the
+        third-party TV-L1 tool that writes `flow_x_/flow_y_` (parameters.py:27) -- done here as host decode
+        (cv2.VideoCapture, like utils.py:51-69) + va_tvl1_flow on the GPU (flow.py; frames resized to 340 x 256 first, as the
+        tool does).  Video v then has ceil(N / sample_rate) stored frames and N - 1 flow pairs, exactly the counts the
+        datasets would find in the reference's trees.  All videos must share one frame size."""
+        import os
+
+        import torch
+
+        from . import flow as _flow
+        from .utils import videoInfo
+
+        self = cls.__new__(cls)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        fp = flow_params if flow_params is not None else _flow.TVL1Params(new_size=(FLOW_SHAPE[1], FLOW_SHAPE[0]))
+        lay = StoreLayout(videos=[], seed=0)
+        clips, seen = [], set()
+        rgb = flw = 0
+        for line in video_lines:
+            if not line.strip():
+                continue
+            loc, name, label, category, _, _ = videoInfo(line, mode)
+            if name in seen:
+                continue
+            seen.add(name)
+            if label is None:
+                label = label_of(category) if label_of is not None else 0
+            frames = _flow.read_video_frames(os.path.join(videos_root, loc))
+            if clips and frames.shape[1:] != clips[0].shape[1:]:
+                raise ValueError("%s is %r, the first video is %r (one frame size per store)" % (loc, frames.shape[1:], clips[0].shape[1:]))
+            n = frames.shape[0]
+            n_frames = (n + sample_rate - 1) // sample_rate                       # frames 0, N, 2N, ... (utils.py:65)
+            n_flows = max(0, n - 1)
+            lay.videos.append(VideoMeta(name, category, int(label), n_frames, rgb, n_flows, flw, flw + n_flows))
+            rgb += n_frames
+            flw += 2 * n_flows
+            clips.append(frames)
+        if not clips:
+            raise ValueError("from_videos: no videos in the list")
+        h, w, c = clips[0].shape[1:]
+        oh, ow = fp.out_shape(h, w)
+        lay.n_rgb_images, lay.n_flow_images = rgb, flw
+        lay.rgb_shape, lay.flow_shape = (h, w, c), (oh, ow, 1)
+        self.layout = lay
+        self.rgb = torch.empty(max(1, rgb) * h * w * c, dtype=torch.uint8, device=dev)
+        self.flow = torch.empty(max(1, flw) * oh * ow, dtype=torch.uint8, device=dev)
+        rgb_v = self.rgb.view(-1, h, w, c)
+        for k, frames in enumerate(clips):
+            m = lay.videos[k]
+            fr = torch.from_numpy(frames).to(dev)
+            rgb_v[m.rgb_first:m.rgb_first + m.n_frames].copy_(fr[::sample_rate])
+            if m.n_flows:
+                _flow.fill_flow_store(self, k, fr, params=fp)
+        torch.cuda.current_stream().synchronize()
+        return self
+
+    @classmethod
     def from_host(cls, layout: StoreLayout, rgb_u8, flow_u8, device=None):
         """Upload host-decoded frames (numpy u8) instead of generating them."""
         import torch
