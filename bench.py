@@ -675,7 +675,7 @@ def main():
         peaks = read_peaks()
         achieved = (t_f.value / 1e12) / (t_ms.value * 1e-3) if t_ms.value > 0 else 0.0
         traffic = None      # DRAM bytes per layer-kernel launch from the committed ncu --set full capture (profiles/)
-        tpath = os.path.join(ROOT, "profiles", "r02_ncu_conv_tc_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_conv_tc_traffic_final.json")
         if os.path.exists(tpath):
             # the capture ran one 250-snippet chunk; a launch of this run processes `chunk` snippets: activation bytes scale
             # with the chunk, the weights (0.27 GB of 9.2 GB per 250-snippet chunk) do not -- scaled linearly, 3 % high
@@ -697,13 +697,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_tc2h_kernel (tcgen05 implicit-GEMM conv/FC)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                         "traffic_source": "profiles/r02_ncu_conv_tc_traffic.json (ncu --set full of the layer launches of one 250-snippet "
+                         "traffic_source": "profiles/r02_ncu_conv_tc_traffic_final.json (ncu --set full of the layer launches of one 250-snippet "
                                            "spatial chunk: dram__bytes_read + dram__bytes_write, averaged per launch), scaled to this run's "
                                            "snippets per launch",
-                         "tensor_pipe_pct": 79.6,
-                         "tensor_pipe_source": "profiles/r02_ncu_layer_table.md: sm__pipe_tensor_cycles_active (pct of peak, elapsed), "
+                         "tensor_pipe_pct": 79.5,
+                         "tensor_pipe_source": "profiles/r02_ncu_layer_table_final.md: sm__pipe_tensor_cycles_active (pct of peak, elapsed), "
                                                "duration-weighted over the layer launches of one 250-snippet chunk under ncu; "
-                                               "88.8-94.1 % on conv2_1..conv4_3",
+                                               "89.4-94.7 % on conv2_1..conv4_3",
                          "peak_source": peaks["src"], "launches": int(t_l.value), "avg_launch_ms": t_ms.value / max(1, t_l.value),
                          "flops_per_launch": t_f.value / max(1, t_l.value),
                          "share_of_step": t_ms.value / total_ms if total_ms > 0 else None},
