@@ -345,7 +345,10 @@ def main(args, embedded=False):
                                       f"{tr_s.grad_allreduce_dtype} payload ({tr_s.flat_grad.numel() * (2 if tr_s.grad_allreduce_dtype == 'bf16' else 4) / 1e6:.0f}"
                                       f" + {tr_t.flat_grad.numel() * (2 if tr_t.grad_allreduce_dtype == 'bf16' else 4) / 1e6:.0f} MB), "
                                       + ("classifier slice launched as soon as its gradients exist" if tr_s.overlap_allreduce else
-                                         "one collective after the backward pass (the persistent layer kernels hold every SM)"),
+                                         (f"one collective per stream, run under the OTHER stream's forward pass (deferred update; "
+                                          f"{tr_s.reserve_sms} SMs reserved for NCCL during {tr_s.reserve_launches} layer launches)"
+                                          if tr_s.defer_update else
+                                          "one collective after the backward pass (the persistent layer kernels hold every SM)")),
                        "l2_policy": "inputs larger than L2: activations of one step are several GB",
                        "weights": "random init (seed 0) of the reference architecture, fp32 master copies",
                        "loss_first_step": loss_first, "loss_last_step": loss_last},
