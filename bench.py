@@ -300,6 +300,9 @@ def main():
         raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback for the product path)")
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version banner there)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("VA_DEFER_UPDATE", "1") == "1":
+        from video_analytics_b200.distributed import reserve_nccl_ctas
+        reserve_nccl_ctas()          # the training step overlaps each stream's all-reduce with the other stream's forward
     rank, world, local = init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

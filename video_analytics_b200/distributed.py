@@ -34,16 +34,22 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
-            # The collectives of this path run BESIDE persistent one-CTA-per-SM layer kernels (training: a stream's gradient
-            # all-reduce under the other stream's forward, with va_reserve_sms leaving 8 SMs free for 5 layer launches): cap NCCL's
-            # CTAs to the SMs that are reserved for it (measured at N = 2, ms per step: 8 SMs x 5 launches 49.41, 16 x 3 49.84,
-            # 32 x 3 49.67, 24 x 5 50.11, collective after the backward pass 50.47; profiles/r02_train_defer_n2.json).
-            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("VA_ALLREDUCE_SMS", "8"))
+            # Two-stream training with deferred updates (training.py) runs a stream's gradient all-reduce BESIDE the other
+            # stream's persistent one-CTA-per-SM layer kernels, on SMs left free by va_reserve_sms: the caller that enables it
+            # caps NCCL's CTAs to that reservation BEFORE this call (reserve_nccl_ctas below); nothing is capped otherwise.
             torch.cuda.set_device(local)
             dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local
+
+
+def reserve_nccl_ctas(n: int = None) -> None:
+    """Cap NCCL's CTAs to the SMs the deferred-update training schedule reserves for it (VA_ALLREDUCE_SMS, default 8).  Must
+    run before the process group is created.  Measured (ms per step, batch 256 per GPU and stream): N = 2: 8 SMs x 5 layer
+    launches 49.41, 16 x 3 49.84, 32 x 3 49.67, 24 x 5 50.11, collective after the backward pass 50.47
+    (profiles/r02_train_defer_n2.json); N = 8: 51.31 / 51.39 (16 x 6) / 52.20 (32 x 8) / 53.74 (r02_train_defer_n8.json)."""
+    os.environ.setdefault("NCCL_MAX_CTAS", str(n) if n is not None else os.environ.get("VA_ALLREDUCE_SMS", "8"))
 
 
 def gather_video_rows(buffers: Dict[str, torch.Tensor], rank: int, world: int, per: int) -> Dict[str, torch.Tensor]:
