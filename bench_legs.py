@@ -60,7 +60,7 @@ def small_batch_legs(spatial, temporal, ev, store, layout):
              "ms_per_batch_with_preprocess": ms64_e2e})
 
 
-def flow_leg(cpu_baseline=True, pairs=56, frames=9, h=256, w=340):
+def flow_leg(cpu_baseline=True, pairs=126, frames=9, h=256, w=340):
     """va_tvl1_flow on a synthetic moving-texture clip (TSN's 340 x 256 flow-image size): device-timed pairs/s, the
     data-dependent iteration counts, and how far the on-chip iteration is from the SMs' fp32 issue rate.  The CPU figure
     beside it is oracle/tvl1.py (numpy, one core) on ONE pair of the same clip."""
@@ -88,13 +88,13 @@ def flow_leg(cpu_baseline=True, pairs=56, frames=9, h=256, w=340):
     instr_min = 105.0           # fp32 + load/store instructions one primal + dual update of a pixel needs at least
     peak = sm * 128 * clk_hz / instr_min
     leg = {"workload": f"TV-L1 optical flow (OpenCV CUDA defaults: 5 levels x 5 warps x <= 300 iterations, epsilon 0.01), {pairs} frame pairs of "
-                       f"{w}x{h} RGB, one 16-CTA cluster per pair, u8 flow_x/flow_y out (bound 20)",
+                       f"{w}x{h} RGB, one thread-block cluster per pair and pyramid level (4 / 8 / 16 CTAs), u8 flow_x/flow_y out (bound 20)",
            "pairs_per_s": pairs / ms * 1e3, "ms": ms, "inner_iterations_per_pair": float(its.sum(1).mean()),
            "pixel_iterations_per_s": pix_iters / ms * 1e3,
            "roofline": {"bound": "fp32 issue (solver state resident in shared memory, no HBM traffic in the iteration)",
                         "achieved": pix_iters / ms * 1e3, "peak": peak, "unit": "pixel-iterations/s", "frac": pix_iters / ms * 1e3 / peak,
                         "peak_definition": f"{sm} SMs x 128 lanes x SM clock / {instr_min:.0f} instructions per pixel-iteration",
-                        "limiters": "7 clusters of 16 CTAs fit (112 of 148 SMs); neighbour synchronisation latency dominates the coarse levels"},
+                        "limiters": "the two finest levels need 16-CTA clusters, of which 7 fit (112 of 148 SMs); ~2500 clk of neighbour handshakes + barriers per iteration; ~200 issued instructions per pixel-iteration"},
            "parity": "bit-identical to oracle/tvl1.py (tests/test_gpu_tvl1.py); oracle unpinned: third-party tool absent"}
     if cpu_baseline:
         from oracle import tvl1 as otv
