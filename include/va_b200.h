@@ -260,7 +260,7 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
  * consumes them, the TSN `dense_flow` tool that wrote `..._flow_img_tvl1_gpu` is third-party): per frame pair, grey
  * conversion (cv::cvtColor BGR2GRAY), Zach/Pock/Bischof TV-L1 with OpenCV's CUDA structure and defaults, then the 8-bit
  * mapping of [-bound, bound] to [0, 255].  The arithmetic contract is oracle/tvl1.py (separately rounded fp32 operations;
- * the kernel is bit-identical to it).  One 16-CTA thread-block cluster solves one pair entirely on chip.
+ * the kernel is bit-identical to it).  A thread-block cluster (4 / 8 / 16 CTAs per pyramid level) iterates a pair on chip.
  *   images:     u8 store as for va_preprocess, image `id` at images + id*image_bytes, [img_h][img_w][img_c], img_c 1 or 3 (RGB)
  *   pair_table: DEVICE int32 [n][4] = {id of frame t-1, id of frame t, OUTPUT id of the x image, OUTPUT id of the y image};
  *               output image `k` is written as u8 [H][W] at out_images + k*out_image_bytes, (H, W) = (img_h, img_w) or the
