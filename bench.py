@@ -508,12 +508,25 @@ def main():
             consumed = [torch.cuda.Event() for _ in range(DEPTH)]
             jpeg_bytes = [0]
 
+            # VA_JPEG_MODE=overlap (default): the whole decode (H2D + kernels) of step i+2 runs on a side stream under steps i,
+            # i+1.  VA_JPEG_MODE=serial: only the H2D copy runs ahead; the decode kernels of a step run on the compute stream
+            # right before its networks.  Measured (snippets/s, video-like / noise content): overlap 15.3-16.6 k / 14.6-15.0 k,
+            # serial 11.0-12.1 k / 13.5-15.4 k -- a decoder block lives ~1.5 ms (one image's serial entropy stream) and cannot
+            # co-reside with the 220-227 KB kernels (fused conv1_1, FC layers), so overlapped decode costs a step 5-6 ms for
+            # 3.3 ms of decode work, but serialising it costs more.
+            jpeg_mode = os.environ.get("VA_JPEG_MODE", "overlap")
+            staged_up = {}
+
             def issue_decode(i):
                 slot2 = i % DEPTH
-                nb = 0
+                fs_, offs_, nb = step_fileset(step_keys(i))
+                if jpeg_mode == "serial":
+                    with torch.cuda.stream(side):
+                        side.wait_event(consumed[slot2])
+                    staged_up[i] = fs_.upload(dev, side)
+                    return nb
                 with torch.cuda.stream(side):
                     side.wait_event(consumed[slot2])
-                    fs_, offs_, nb = step_fileset(step_keys(i))
                     fs_.decode_into(stages2[slot2].all, offs_)
                     decoded[slot2].record(side)
                 return nb
@@ -526,7 +539,11 @@ def main():
                 for slot, v in enumerate(vids):
                     hs, ht = staged_tables(v % len(layout.videos), slot)
                     tabs_s.append(hs.to(dev, non_blocking=True)); tabs_t.append(ht.to(dev, non_blocking=True))
-                cur.wait_event(decoded[slot2])
+                if jpeg_mode == "serial":
+                    fs_, offs_, _ = step_fileset(step_keys(i))
+                    fs_.decode_into(stages2[slot2].all, offs_, staged=staged_up.pop(i))
+                else:
+                    cur.wait_event(decoded[slot2])
                 if i + DEPTH - 1 < end:
                     jpeg_bytes[0] = issue_decode(i + DEPTH - 1)    # runs under this and the next step's networks
                 r = ev.run_tables(torch.cat(tabs_s), torch.cat(tabs_t), len(vids), store=stages2[slot2])
@@ -581,8 +598,10 @@ def main():
             e2e_jpeg["network_stream_priority"] = "high" if prio else "default"
             e2e_jpeg["content"] = ("video-like frames and flow images (low-frequency structure + noise sigma 3, ~25 KB per file: the "
                                    "bit rate of real UCF101 frames); network inputs are whatever the files decode to")
-            e2e_jpeg["input"] = ("JPEG files (cv2.imwrite format) in pinned host memory -> H2D -> CUDA decode (side stream, two steps "
-                                 "ahead) -> K1 -> networks -> fusion -> D2H")
+            e2e_jpeg["input"] = ("JPEG files (cv2.imwrite format) in pinned host memory -> H2D (copy stream, two steps ahead) -> CUDA "
+                                 "decode -> gather + networks -> fusion -> D2H; decode kernels "
+                                 + ("on the compute stream before the step's networks" if jpeg_mode == "serial" else
+                                    "on a side stream under the previous steps' networks"))
             worst = with_priority(timed_jpeg_run, "noise")
             worst["content"] = ("the synthetic store's hash-noise pixels (~67 KB per file, no EOB, every coefficient non-zero): the "
                                 "entropy decoder's worst case")

@@ -238,9 +238,23 @@ class JpegFileSet:
             self.group_bytes.append((g0, pos))
         hv[pos:] = 0
 
-    def decode_into(self, out: torch.Tensor, out_offsets: Sequence[int]) -> None:
+    def upload(self, device, stream=None):
+        """H2D copy of the compressed files only (pinned host memory -> device), on `stream` (default: current).  Returns the
+        per-group device buffers + the event to wait for; pass them to decode_into(staged=...).  Lets a loader run the
+        copies of the NEXT step on a copy stream while the decode kernels stay on the compute stream."""
+        st = stream if stream is not None else torch.cuda.current_stream()
+        bufs = []
+        with torch.cuda.stream(st):
+            for (g0, g1) in self.group_bytes:
+                bufs.append(self.host[g0:g1 + 16].to(device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return bufs, ev
+
+    def decode_into(self, out: torch.Tensor, out_offsets: Sequence[int], staged=None) -> None:
         """Image k goes to byte offset out_offsets[k] of the flat uint8 device tensor `out` as [H][W] (one component) or
-        [H][W][3] RGB.  Asynchronous on the current CUDA stream."""
+        [H][W][3] RGB.  Asynchronous on the current CUDA stream.  staged = upload()'s result: the files are already on the
+        device (the current stream waits for that copy)."""
         if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
             raise VAError("jpeg decode: `out` must be a contiguous uint8 CUDA tensor (no CPU decode fallback)")
         if len(out_offsets) != self.n:
@@ -250,8 +264,10 @@ class JpegFileSet:
                 raise VAError("jpeg decode: image of %dx%dx%d at offset %d does not fit in `out`" % (h, w, c, off))
         lib = _lib.load()
         cur = torch.cuda.current_stream()
-        for (a, b_, batch), (g0, g1) in zip(self.groups, self.group_bytes):
-            dev = self.host[g0:g1 + 16].to(out.device, non_blocking=True)
+        if staged is not None:
+            cur.wait_event(staged[1])
+        for gi, ((a, b_, batch), (g0, g1)) in enumerate(zip(self.groups, self.group_bytes)):
+            dev = staged[0][gi] if staged is not None else self.host[g0:g1 + 16].to(out.device, non_blocking=True)
             batch.images["out_offset"] = np.asarray(out_offsets[a:b_], dtype=np.uint64)
             images, q, h = batch.images, batch.qtables, batch.htables
             check(lib.va_jpeg_decode(ptr(dev), images.ctypes.data_as(C.c_void_p), batch.n, q.ctypes.data_as(C.c_void_p),
