@@ -513,7 +513,9 @@ def main():
             # right before its networks.  Measured (snippets/s, video-like / noise content): overlap 15.3-16.6 k / 14.6-15.0 k,
             # serial 11.0-12.1 k / 13.5-15.4 k -- a decoder block lives ~1.5 ms (one image's serial entropy stream) and cannot
             # co-reside with the 220-227 KB kernels (fused conv1_1, FC layers), so overlapped decode costs a step 5-6 ms for
-            # 3.3 ms of decode work, but serialising it costs more.
+            # 3.3 ms of decode work, but serialising it costs more.  Capping the layer kernels' shared memory at 212 KB so that a
+            # decoder block would fit beside them changed nothing (14.2 k vs 14.5 k): their 320-512 threads x 128 registers fill
+            # the register file, which is the real co-residency limit.
             jpeg_mode = os.environ.get("VA_JPEG_MODE", "overlap")
             staged_up = {}
 
