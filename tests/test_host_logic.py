@@ -273,3 +273,33 @@ def test_flow_starts_reject_videos_shorter_than_a_stack():
     for n in (10, 5, 0):
         with pytest.raises(ValueError):
             flow_starts(n, 10)
+
+
+def test_frame_extraction_equals_the_reference(golden, tmp_path):
+    """SURVEY 8f row 2 (second half): convertVideosToFrames / extractEveryNthFrame write what the REFERENCE's own functions
+    wrote for the committed video (oracle/make_golden_frames.py ran Sheet03/utils.py:51-69,95-121 itself): same file names,
+    same JPEG bytes, same kept frames."""
+    import hashlib
+    import os
+    import shutil
+    from conftest import GOLDEN
+    cv2 = pytest.importorskip("cv2")
+    man = golden("frames_manifest.json")
+    video = os.path.join(GOLDEN, man["video"])
+    assert hashlib.sha256(open(video, "rb").read()).hexdigest() == man["video_sha256"]
+    if cv2.__version__ != man["cv2_version"]:
+        pytest.skip("JPEG bytes are pinned for OpenCV %s" % man["cv2_version"])
+    root, save = tmp_path / "videos", tmp_path / "frames"
+    (root / "Archery").mkdir(parents=True)
+    shutil.copy(video, root / "Archery" / "v_Archery_g01_c01.avi")
+    lst = tmp_path / "list.txt"
+    lst.write_text("Archery/v_Archery_g01_c01.avi 1\n")
+    U.convertVideosToFrames(str(root), str(save), str(lst), man["sample_rate"], "train")
+    out = save / "Archery" / "v_Archery_g01_c01"
+    got = {n: hashlib.sha256(open(out / n, "rb").read()).hexdigest() for n in sorted(os.listdir(out))}
+    assert got == man["reference_files"]
+    kept = U.extractEveryNthFrame(str(root / "Archery" / "v_Archery_g01_c01.avi"), 7)
+    assert len(kept) == man["every_7th"]["count"]
+    assert [hashlib.sha256(np.ascontiguousarray(k).tobytes()).hexdigest() for k in kept] == man["every_7th"]["sha256"]
+    with pytest.raises(ValueError):
+        U.extractEveryNthFrame(str(root / "missing.avi"), 10)

@@ -46,8 +46,10 @@ def getOneHot(label, nClasses):
 
 
 def extractEveryNthFrame(videoLoc, N):
-    """reference utils.py:51-69 -- decode a video with OpenCV and keep frames 0, N, 2N, ...  (host-side, input
-    preparation; GPU decode is row f.2 of SURVEY.md section 8 and not built)."""
+    """reference utils.py:51-69 -- decode a video with OpenCV and keep frames 0, N, 2N, ...  Host-side input preparation,
+    as in the reference (UCF101's .avi files are MPEG-4 ASP, which NVDEC does not decode); pinned against the reference's
+    own function on a committed video (tests/test_host_logic.py, oracle/make_golden_frames.py).  store.DeviceStore.from_videos
+    uses the same decode and keeps the frames (and the TV-L1 flow of all pairs) in HBM without writing JPEGs."""
     import cv2
     if not (os.path.exists(videoLoc) and os.path.isfile(videoLoc)):
         raise ValueError("Video does not exist: %s" % (videoLoc))
