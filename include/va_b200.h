@@ -88,7 +88,8 @@ va_status va_forward(va_handle* h, const void* in_nhwc, int n, float* descriptor
 /* Fused front end: the same forward, but fed from the image store.  The snippet transform (va_preprocess: utils.py:137-151,
  * spatialModel.py:64-81, temporalModel.py:67-92) is gathered straight into the first convolution's shared-memory operand
  * (csrc/va_conv1_fused.cu), so no preprocessed tensor exists in HBM.  Arguments as va_preprocess (crop is 224) and
- * va_forward; planes * img_c must equal the handle's in_channels; (planes, img_c) = (1, 3) or (any, 1).  Results are
+ * va_forward; planes * img_c must equal the handle's in_channels; (planes, img_c) = (1, 3) or (1..23, 1); `images` must be
+ * 16-byte aligned with image_bytes a multiple of 16 (the loader copies 16-byte blocks; true for 240x320x3 and 256x340).  Results are
  * those of va_preprocess + va_forward up to the summation order inside the first layer's fp32 accumulation.
  * Returns VA_ERR_UNSUPPORTED for precision-1 handles (use va_preprocess + va_forward). */
 va_status va_forward_store(va_handle* h, const uint8_t* images, size_t image_bytes, int img_h, int img_w, int img_c,

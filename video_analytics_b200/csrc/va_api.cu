@@ -332,7 +332,7 @@ va_status va_forward_store(va_handle* h, const uint8_t* images, size_t image_byt
   if (planes < 1 || img_c < 1 || planes * img_c != h->cin)
     return fail(VA_ERR_INVALID, "va_forward_store: planes %d x img_c %d != in_channels %d", planes, img_c, h->cin);
   if (!va::conv1_fused_supported(planes, img_c, kCrop))
-    return fail(VA_ERR_UNSUPPORTED, "va_forward_store: (planes, img_c) = (%d, %d); supported (1, 3) and (any, 1)", planes, img_c);
+    return fail(VA_ERR_UNSUPPORTED, "va_forward_store: (planes, img_c) = (%d, %d); supported (1, 3) and (1..23, 1)", planes, img_c);
   if (img_h < kCrop || img_w < kCrop || image_bytes < (size_t)img_h * img_w * img_c)
     return fail(VA_ERR_INVALID, "va_forward_store: image %dx%dx%d (%zu bytes) cannot hold a %d crop", img_h, img_w, img_c, image_bytes, kCrop);
   const StoreInput src{images, image_bytes, img_h, img_w, img_c, index_table, planes, mean, std};
@@ -345,7 +345,7 @@ va_status va_conv1_fused(const uint8_t* images, size_t image_bytes, int img_h, i
   if (!images || !index_table || !mean || !std || !w || !bias || !y) return fail(VA_ERR_INVALID, "va_conv1_fused: NULL argument");
   if (n < 0 || planes < 1 || img_c < 1 || planes * img_c > 32) return fail(VA_ERR_INVALID, "va_conv1_fused: bad shape");
   if (!va::conv1_fused_supported(planes, img_c, kCrop))
-    return fail(VA_ERR_UNSUPPORTED, "va_conv1_fused: (planes, img_c) = (%d, %d); supported (1, 3) and (any, 1)", planes, img_c);
+    return fail(VA_ERR_UNSUPPORTED, "va_conv1_fused: (planes, img_c) = (%d, %d); supported (1, 3) and (1..23, 1)", planes, img_c);
   if (img_h < kCrop || img_w < kCrop) return fail(VA_ERR_INVALID, "va_conv1_fused: image smaller than the crop");
   if (va_status s = require_sm100()) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

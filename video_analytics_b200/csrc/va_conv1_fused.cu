@@ -562,7 +562,8 @@ const char* launch_fused(const CUtensorMap& tO, const Conv1FusedParams& p, int g
 int conv1_fused_packed_bytes(int cin) { return make_schedule(cin).plan.n_mma * 2048; }
 
 bool conv1_fused_supported(int planes, int img_c, int crop) {
-  return crop == kF1Crop && ((planes == 1 && img_c == 3) || (img_c == 1 && planes >= 1 && planes <= 32));
+  // 1-channel stacks: two raw strip buffers of planes x 18 rows x 80 B must fit beside the operand ring (23 planes: 229.7 KB)
+  return crop == kF1Crop && ((planes == 1 && img_c == 3) || (img_c == 1 && planes >= 1 && planes <= 23));
 }
 
 cudaError_t launch_pack_conv1_fused_w(const float* w, void* out, int cin, cudaStream_t st) {

@@ -291,7 +291,7 @@ class StreamNet:
         of 1-channel images per snippet, at least 224 x 224, 16-byte aligned with a 16-byte multiple per image (the loader
         copies 16-byte blocks), and a plane count whose strips fit in shared memory."""
         h, wd, c = image_shape
-        if not ((c == 3 and planes == 1) or (c == 1 and 1 <= planes <= 24)):
+        if not ((c == 3 and planes == 1) or (c == 1 and 1 <= planes <= 23)):
             return False
         return h >= CROP and wd >= CROP and (h * wd * c) % 16 == 0 and images.data_ptr() % 16 == 0
 
