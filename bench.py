@@ -404,13 +404,12 @@ def main():
     def e2e_run(first, last):
         nonlocal h2d, d2h
         groups = [my[i * vps:(i + 1) * vps] for i in range(first, last)]
-        for r in ev.host_pipeline(host, groups):
-            nd = 0
+        # every step's scores / predictions are read back to pinned host memory by the pipeline itself (event-synchronised
+        # per step; the next step's kernels are already queued when a step's results are handed out)
+        for r in ev.host_pipeline(host, groups, to_host=tuple(res_host)):
             for kname, hbuf in res_host.items():
-                hbuf[:r[kname].shape[0]].copy_(r[kname], non_blocking=True)
-                nd += r[kname].numel() * r[kname].element_size()
-            torch.cuda.current_stream().synchronize()      # the step's result is on the host
-            h2d, d2h = ev.last_h2d_bytes, nd
+                hbuf[:r[kname].shape[0]].copy_(r[kname])        # host -> host: the caller's own result buffers
+            h2d, d2h = ev.last_h2d_bytes, ev.last_d2h_bytes
 
     e2e_run(0, W)
     barrier()

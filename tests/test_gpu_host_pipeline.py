@@ -31,6 +31,17 @@ def test_host_pipeline_equals_resident_store():
         want = ev.run_videos(g)
         for k in ("video_scores", "video_desc", "score_pred"):
             assert torch.equal(r[k], want[k]), (g, k)
+    # the same groups with the results read back by the pipeline (pinned host buffers, next group's kernels queued before a
+    # group's results are handed out): identical rows, in order, D2H bytes counted
+    got_h = []
+    for res in ev.host_pipeline(host, groups, to_host=("video_scores", "score_pred")):
+        assert not res["video_scores"].is_cuda and res["video_scores"].is_pinned()
+        got_h.append({k: v.clone() for k, v in res.items()})
+    assert len(got_h) == len(groups)
+    for g, r, h in zip(groups, got, got_h):
+        assert h["video_scores"].shape[0] == len(g)
+        assert torch.equal(h["video_scores"], r["video_scores"].cpu()) and torch.equal(h["score_pred"], r["score_pred"].cpu())
+    assert ev.last_d2h_bytes == len(groups[-1]) * (101 * 4 + 4)
     # bytes per group: 25 frames + 500 flow images per video + the two index tables
     per_video = 25 * 240 * 320 * 3 + 500 * 256 * 340 + 250 * 4 * 4 + 250 * 20 * 4 * 4
     assert ev.last_h2d_bytes == 2 * per_video

@@ -140,11 +140,15 @@ class TwoStreamEvaluator:
     MAX_RGB_PER_VIDEO = N_TEST_SNIPPETS
     MAX_FLOW_PER_VIDEO = 2 * N_TEST_SNIPPETS * VIDEO_INPUT_FLOW_COUNT
 
-    def host_pipeline(self, host: HostStore, groups: Sequence[Sequence[int]], depth: int = 2):
+    def host_pipeline(self, host: HostStore, groups: Sequence[Sequence[int]], depth: int = 2, to_host: Optional[Sequence[str]] = None):
         """Generator: evaluates each group of video ids from PINNED HOST images and yields its fusion result dict.
         The images a group touches (25 frames + 2 x 250 flow images per video) and its index tables are copied into one
         of `depth` device stage stores on a copy stream while the previous group's networks run; `self.last_h2d_bytes` is
-        the byte count of the most recent group's copies.  Results are stream-ordered on the CURRENT stream."""
+        the byte count of the most recent group's copies.  Results are stream-ordered on the CURRENT stream.
+        to_host = names of result tensors (e.g. ("video_scores", "score_pred")): the pipeline also copies those rows back
+        into pinned host buffers and yields HOST tensors, synchronised by an event -- and it queues the NEXT group's
+        kernels before it waits for that event, so the GPU never idles while the host handles a group's results (a plain
+        stream synchronise per group left it idle for the host's launch time; `self.last_d2h_bytes` = bytes read back)."""
         lay = host.layout
         dev = self.store.rgb.device
         vmax = max((len(g) for g in groups), default=0)
@@ -213,6 +217,11 @@ class TwoStreamEvaluator:
 
         for gi in range(min(depth - 1, len(groups))):
             issue(gi)
+        if to_host is not None and getattr(self, "_host_out_key", None) != (tuple(to_host), vmax):
+            self._host_out = [dict() for _ in range(2)]
+            self._host_done = [torch.cuda.Event() for _ in range(2)]
+            self._host_out_key = (tuple(to_host), vmax)
+        prev = None
         for gi in range(len(groups)):
             slot = gi % depth
             ts, tt, nb = pending.pop(gi)
@@ -221,12 +230,34 @@ class TwoStreamEvaluator:
             tt.record_stream(cur)
             res = self.run_tables(ts, tt, len(groups[gi]), store=self._stages[slot])
             self._consumed[slot].record(cur)
+            hres = None
+            if to_host is not None:
+                hb, nd = self._host_out[gi & 1], 0
+                hres = {}
+                for name in to_host:
+                    t = res[name]
+                    if name not in hb or hb[name].shape[1:] != t.shape[1:] or hb[name].dtype != t.dtype:
+                        hb[name] = torch.empty((vmax,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                    hres[name] = hb[name][:t.shape[0]]
+                    hres[name].copy_(t, non_blocking=True)
+                    nd += t.numel() * t.element_size()
+                self._host_done[gi & 1].record(cur)
+                self.last_d2h_bytes = nd
             # the next group's ~150 copy calls are issued AFTER this group's kernels are queued: the host spends ~0.5 ms on
             # them, which would otherwise be GPU idle time right after the caller's per-step synchronisation
             if gi + depth - 1 < len(groups):
                 issue(gi + depth - 1)                 # its copies run under this group's networks
             self.last_h2d_bytes = nb
-            yield res
+            if to_host is None:
+                yield res
+            else:
+                if prev is not None:                  # group gi is queued: now hand out group gi-1
+                    prev[1].synchronize()
+                    yield prev[0]
+                prev = (hres, self._host_done[gi & 1])
+        if prev is not None:
+            prev[1].synchronize()
+            yield prev[0]
 
     def _stream(self, net: ops.StreamNet, images, shape, table, mean, std):
         """One stream over a table of snippets -> (descriptors, softmax scores).  bf16 handles gather the crops inside the
