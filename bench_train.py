@@ -115,10 +115,13 @@ def main(args, embedded=False):
     # data parallel: each stream's gradient all-reduce runs under the OTHER stream's forward pass (deferred update + SM
     # reservation, training.py); VA_DEFER_UPDATE=0 gives the collective-after-backward schedule for A/B runs
     defer = world > 1 and os.environ.get("VA_DEFER_UPDATE", "1") == "1"
+    # the gradient all-reduce is the library's own two-shot kernel over the NVSwitch multicast address of a symmetric
+    # arena (csrc/va_allreduce.cu); VA_ALLREDUCE_IMPL=nccl gives torch.distributed's (measured equal at N = 2 and N = 8)
+    impl = os.environ.get("VA_ALLREDUCE_IMPL", "va")
     tr_s = StreamTrainer(build_spatial_torch_model(C, D, seed=0), None, lr=args.lr, momentum=0.9, c_pad=16, process_group=group,
-                         defer_update=defer)
+                         defer_update=defer, allreduce_impl=impl)
     tr_t = StreamTrainer(build_temporal_torch_model(C, L, D, seed=0), None, lr=args.lr, momentum=0.9, c_pad=32, process_group=group,
-                         defer_update=defer)
+                         defer_update=defer, allreduce_impl=impl)
     layout = make_layout(args.pool)
     store = DeviceStore(layout, dev)
     mean_s, std_s = list(NORM_MEANS_TF), list(NORM_STDS_TF)
@@ -350,6 +353,8 @@ def main(args, embedded=False):
                                       + ("classifier slice launched as soon as its gradients exist" if tr_s.overlap_allreduce else
                                          (f"one collective per stream, run under the OTHER stream's forward pass (deferred update; "
                                           f"{tr_s.reserve_sms} SMs reserved for NCCL during {tr_s.reserve_launches} layer launches)"
+                                          + (", own two-shot all-reduce kernel over " + ("NVSwitch multicast" if tr_s._symm_use_mc else "NVLink peer pointers")
+                                             if tr_s._symm is not None else ", NCCL")
                                           if tr_s.defer_update else
                                           "one collective after the backward pass (the persistent layer kernels hold every SM)")),
                        "l2_policy": "inputs larger than L2: activations of one step are several GB",

@@ -293,6 +293,18 @@ va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int
                        size_t out_image_bytes, float* flow_f32, int32_t* iterations, void* workspace,
                        size_t workspace_bytes, va_stream_t stream);
 
+/* Gradient all-reduce (sum) of the data-parallel training step as the library's own kernel over NVLink peer memory
+ * (serves loss.backward()/optimizer.step() of spatialModel.py:178-181 on several GPUs; the reference itself is single-GPU).
+ * In place over a SYMMETRIC bf16 buffer of n_elems elements (multiple of 8) that every rank of `world` holds:
+ *   peer_ptrs:     HOST array of `world` DEVICE pointers, entry p = rank p's buffer as addressable from this GPU (P2P);
+ *   multicast_ptr: the buffer's NVSwitch multicast address, or NULL -- when given, the kernel uses in-switch reduction
+ *                  (multimem.ld_reduce, fp32 accumulation) and replicated stores (multimem.st) instead of W loads / stores.
+ * Two-shot: rank r reduces slice r and writes it to all ranks, so replicas receive bit-identical sums.  The CALLER brackets
+ * the launch with a cross-rank barrier with system-scope release/acquire (torch symmetric memory: handle.barrier()).
+ * n_ctas: CTAs of 1024 threads to use (8 by default: it runs beside the layer kernels on the SMs va_reserve_sms frees). */
+va_status va_allreduce_bf16(const void* const* peer_ptrs, void* multicast_ptr, int world, int rank, long long n_elems,
+                            int n_ctas, va_stream_t stream);
+
 /* SM reservation for a collective that runs beside the layer kernels (data-parallel training: the gradient all-reduce of
  * one stream under the other stream's forward pass).  The layer kernels are persistent, one CTA per SM with 210-227 KB of
  * shared memory, so a collective's CTAs cannot co-reside with them: launched beside a full grid they hold some SMs and the

@@ -83,6 +83,40 @@ def main():
     if rank == 0:
         print(f"deferred vs immediate update: rel diff of the 2-step parameter change {rel_defer:.3e} (pending before flush: {pending})")
         ok = ok and pending and rel_defer < 1e-4
+    # the library's own all-reduce kernel (va_allreduce_bf16) over the symmetric gradient arena: NVSwitch multicast form and
+    # peer-pointer form, against the fp32 sum of the ranks' bf16-rounded gradients rounded once to bf16 (what both compute)
+    import os
+    del trA, trB
+    torch.cuda.empty_cache()
+    own_ok = True
+    for mc in ("1", "0"):
+        os.environ["VA_ALLREDUCE_MULTICAST"] = mc
+        trV = StreamTrainer(build_spatial_torch_model(101, 256, seed=7), None, lr=0.01, momentum=0.9, c_pad=16,
+                            process_group=dist.group.WORLD, allreduce_impl="va", defer_update=False)
+        trV.forward_backward(*args)
+        ref = trV.flat_grad.bfloat16().float()
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        ref = ref.bfloat16()
+        trV._allreduce_async(0, trV.flat_grad.numel()).wait()
+        torch.cuda.synchronize()
+        if trV._symm_use_mc:       # in-switch reduction: its accumulation order / denormal handling is the fabric's -- one bf16 ulp
+            d = (trV.flat_grad_bf16.float() - ref.float()).abs()
+            same_v = bool((d <= 2.0 ** -7 * ref.float().abs() + 1e-37).all())
+            n_diff = int((trV.flat_grad_bf16 != ref).sum())
+        else:                      # fp32 sum in rank order, rounded once: exactly the reference
+            same_v = torch.equal(trV.flat_grad_bf16, ref)
+            n_diff = 0
+        nz = int((trV.flat_grad_bf16 != 0).sum())
+        fl = torch.tensor([1 if same_v and nz > 0 else 0], device="cuda")
+        dist.all_reduce(fl, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"va_allreduce_bf16 ({'multicast' if trV._symm_use_mc else 'peer pointers'}; multicast available: "
+                  f"{int(trV._symm.multicast_ptr or 0) != 0}): matches the reference sum on all ranks = {bool(int(fl))} "
+                  f"({n_diff} of {nz} non-zero elements differ, within one bf16 ulp)")
+        own_ok = own_ok and bool(int(fl))
+        del trV, ref
+        torch.cuda.empty_cache()
+    ok = ok and own_ok if rank == 0 else ok
     if rank == 0:
         good = ok and int(flag) == 1 and int(synced) == 1 and rel16 < 1e-2
         print(("DDP_OK" if good else "DDP_FAIL"), f"world={world} params_identical={bool(int(flag))} replicas_synced={bool(int(synced))} "

@@ -58,6 +58,7 @@ SIGNATURES = {
     "va_tvl1_flow": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "va_tvl1_debug_cycles": (_i, [_vp]),
     "va_reserve_sms": (_i, [_i, _i]),
+    "va_allreduce_bf16": (_i, [_vp, _vp, _i, _i, C.c_longlong, _i, _vp]),
     "va_synth_fill": (_i, [_vp, _sz, _i, _i, _i, _i, _u32, _u32, _vp]),
     "va_debug_conv_counters": (_i, [_vp]),
     "va_profile_enable": (_i, [_i]),

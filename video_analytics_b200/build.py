@@ -16,7 +16,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libva_b200.so"
 BUILD_DIR = PKG_DIR / "build"
 
-SOURCES = ["va_api.cu", "va_conv_tc.cu", "va_conv1_fused.cu", "va_small_kernels.cu", "va_train_kernels.cu", "va_wgrad_tc.cu", "va_jpeg.cu", "va_svm_fit.cu", "va_tvl1.cu"]
+SOURCES = ["va_api.cu", "va_conv_tc.cu", "va_conv1_fused.cu", "va_small_kernels.cu", "va_train_kernels.cu", "va_wgrad_tc.cu", "va_jpeg.cu", "va_svm_fit.cu", "va_tvl1.cu", "va_allreduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

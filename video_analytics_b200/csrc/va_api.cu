@@ -649,6 +649,15 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
   return VA_OK;
 }
 
+va_status va_allreduce_bf16(const void* const* peer_ptrs, void* multicast_ptr, int world, int rank, long long n_elems, int n_ctas,
+                            va_stream_t stream) {
+  if (!peer_ptrs && !multicast_ptr) return fail(VA_ERR_INVALID, "va_allreduce_bf16: neither peer pointers nor a multicast pointer");
+  if (va_status s = require_sm100()) return s;
+  const char* e = va::allreduce_bf16_run(peer_ptrs, multicast_ptr, world, rank, n_elems, n_ctas, static_cast<cudaStream_t>(stream));
+  if (e) return fail(VA_ERR_INVALID, "va_allreduce_bf16: %s", e);
+  return VA_OK;
+}
+
 va_status va_reserve_sms(int sms, int launches) {
   if (sms < 0 || launches < 0) return fail(VA_ERR_INVALID, "va_reserve_sms: negative argument");
   va::conv_reserve_sms(sms, launches);

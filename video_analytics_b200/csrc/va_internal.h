@@ -68,6 +68,10 @@ const char* svm_fit_run(const double* X, const int32_t* class_index, int V, int 
                         double tol, int max_iter, double* coef, double* intercept, int32_t* epochs, double* work,
                         cudaStream_t st);
 
+// ---- gradient all-reduce over NVLink peer memory / NVSwitch multicast (va_allreduce.cu)
+const char* allreduce_bf16_run(const void* const* peer_ptrs, void* multicast_ptr, int world, int rank, long long n_elems, int n_ctas,
+                               cudaStream_t st);
+
 // ---- TV-L1 optical flow (va_tvl1.cu)
 size_t tvl1_workspace_bytes(int h, int w, int nscales, double scale_step);
 void tvl1_set_debug_cycles(long long* dev);

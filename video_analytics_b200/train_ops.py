@@ -203,3 +203,12 @@ def reserve_sms(sms: int, launches: int) -> None:
     """va_reserve_sms: the next `launches` layer-kernel launches of this process leave `sms` SMs free for a collective
     that was just launched on another stream (0, 0 switches it off)."""
     check(_lib.load().va_reserve_sms(int(sms), int(launches)), "va_reserve_sms")
+
+
+def allreduce_bf16_(peer_ptrs, multicast_ptr: int, world: int, rank: int, n_elems: int, n_ctas: int = 8) -> None:
+    """va_allreduce_bf16: in-place sum over the ranks' symmetric bf16 buffers (the caller brackets it with the symmetric
+    memory barrier).  peer_ptrs: sequence of `world` device addresses (int); multicast_ptr: NVSwitch multicast address or 0."""
+    import ctypes as C
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    check(_lib.load().va_allreduce_bf16(arr, C.c_void_p(int(multicast_ptr) or None), int(world), int(rank), C.c_longlong(int(n_elems)),
+                                        int(n_ctas), stream_ptr()), "va_allreduce_bf16")

@@ -43,7 +43,8 @@ class StreamTrainer:
     def __init__(self, module: torch.nn.Module, optimizer: Optional[torch.optim.SGD] = None, *, lr: float = 0.1,
                  momentum: float = 0.9, c_pad: int = 16, process_group=None, grad_allreduce_dtype: str = "bf16",
                  overlap_allreduce: Optional[bool] = None, defer_update: Optional[bool] = None,
-                 reserve_sms: Optional[int] = None, reserve_launches: Optional[int] = None):
+                 reserve_sms: Optional[int] = None, reserve_launches: Optional[int] = None,
+                 allreduce_impl: Optional[str] = None):
         """module: the (unwrapped) torchvision-layout VGG16 with the swapped classifier (parameter container only).
         optimizer: the torch.optim.SGD over module.parameters(); its lr / momentum are read at every step (so a
         MultiStepLR scheduler keeps working) and its momentum buffers are re-pointed at the arena."""
@@ -82,6 +83,15 @@ class StreamTrainer:
         self.reserve_sms = int(_os.environ.get("VA_ALLREDUCE_SMS", "8")) if reserve_sms is None else int(reserve_sms)
         self.reserve_launches = int(_os.environ.get("VA_ALLREDUCE_LAUNCHES", "5")) if reserve_launches is None else int(reserve_launches)
         self._deferred = None
+        # allreduce_impl: "nccl" (torch.distributed) or "va" -- the library's own two-shot kernel over NVLink peer memory /
+        # NVSwitch multicast (csrc/va_allreduce.cu) on a symmetric allocation (torch symmetric memory supplies the peer and
+        # multicast addresses and the cross-rank barrier).  bf16 payload only.  None -> VA_ALLREDUCE_IMPL env, else "nccl".
+        if allreduce_impl is None:
+            allreduce_impl = _os.environ.get("VA_ALLREDUCE_IMPL", "nccl")
+        if allreduce_impl not in ("nccl", "va"):
+            raise VAError("allreduce_impl must be 'nccl' or 'va'")
+        self.allreduce_impl = allreduce_impl if (process_group is not None and grad_allreduce_dtype == "bf16") else "nccl"
+        self._symm = None
         sd = dict(self.module.named_parameters())
         missing = [k for k in STATE_DICT_KEYS if k not in sd]
         if missing:
@@ -96,8 +106,32 @@ class StreamTrainer:
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_buf = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_grad_bf16 = (torch.zeros(total, dtype=torch.bfloat16, device=dev)
-                               if (process_group is not None and grad_allreduce_dtype == "bf16") else None)
+        self.flat_grad_bf16 = None
+        if process_group is not None and grad_allreduce_dtype == "bf16":
+            if self.allreduce_impl == "va":
+                import sys
+                import torch.distributed as dist
+                ok_flag = torch.ones(1, dtype=torch.int32, device=dev)
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+                    self.flat_grad_bf16 = symm_mem.empty(total, dtype=torch.bfloat16, device=dev)
+                    self.flat_grad_bf16.zero_()
+                    self._symm = symm_mem.rendezvous(self.flat_grad_bf16, process_group)
+                    self._symm_world, self._symm_rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+                    self._symm_use_mc = (_os.environ.get("VA_ALLREDUCE_MULTICAST", "1") == "1" and
+                                         int(self._symm.multicast_ptr or 0) != 0)
+                    if self._symm_world not in (1, 2, 4, 8) and not self._symm_use_mc:
+                        raise VAError("peer-pointer form needs 1, 2, 4 or 8 ranks")
+                    self._comm_stream = torch.cuda.Stream(device=dev)
+                except Exception as e:          # no symmetric memory on this box: every rank falls back together, loudly
+                    ok_flag.zero_()
+                    sys.stderr.write(f"[video_analytics_b200] allreduce_impl='va' unavailable ({e!r}); using NCCL\n")
+                dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN, group=process_group)
+                if int(ok_flag.item()) == 0:
+                    self._symm, self.allreduce_impl = None, "nccl"
+                    self.flat_grad_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+            else:
+                self.flat_grad_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self.grads: List[torch.Tensor] = []
         self.bufs: List[torch.Tensor] = []
         for p, off in zip(self.params, self.offsets):
@@ -255,8 +289,33 @@ class StreamTrainer:
         import torch.distributed as dist
         if self.flat_grad_bf16 is not None:
             T.f32_to_bf16_(self.flat_grad[lo:hi], self.flat_grad_bf16[lo:hi])      # one HBM pass; the update reads the bf16 sum
+            if self._symm is not None:
+                if lo != 0 or hi != self.flat_grad.numel():
+                    raise VAError("allreduce_impl='va' reduces the whole arena in one launch (overlap_allreduce is an NCCL option)")
+                return self._allreduce_own()
             return dist.all_reduce(self.flat_grad_bf16[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _allreduce_own(self):
+        """The whole bf16 arena through va_allreduce_bf16 on the communication stream: barrier (every rank's arena is
+        written) -> two-shot kernel over peer / multicast addresses -> barrier (every slice is stored everywhere).  Returns an
+        object whose wait() makes the current stream wait for it, like a torch.distributed Work."""
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ready)
+            self._symm.barrier(channel=0)
+            T.allreduce_bf16_(self._symm.buffer_ptrs, self._symm.multicast_ptr if self._symm_use_mc else 0, self._symm_world,
+                              self._symm_rank, self.flat_grad_bf16.numel(), n_ctas=max(1, self.reserve_sms))
+            self._symm.barrier(channel=0)
+            done.record(self._comm_stream)
+
+        class _Done:
+            def wait(self_inner):
+                torch.cuda.current_stream().wait_event(done)
+        return _Done()
 
     def apply_update(self, pending=()):
         """Gradient all-reduce (when a process group is given) + the fused SGD-momentum update over the arena.
