@@ -77,6 +77,8 @@ def test_training_primitives_reject_bad_arguments_without_touching_the_gpu(built
     assert b"ks" in lib.va_last_error()
     assert lib.va_conv2d_dgrad(p, 1, 4, 4, 48, p, 64, p, None) != 0             # channels must be multiples of 64
     assert lib.va_maxpool2x2_nhwc(p, 1, 5, 4, 64, p, None, None) != 0           # odd height
+    # va_allreduce_bf16: neither peer pointers nor a multicast pointer
+    assert lib.va_allreduce_bf16(None, None, 2, 0, ctypes.c_longlong(64), 8, None) != 0
     # va_svm_fit (combinedModel.py:34-35): NULL arguments, one class only, too many features, bad regularisation
     d = ctypes.c_double
     assert lib.va_svm_fit(None, None, 4, 8, 2, d(1.0), d(1.0), d(1e-4), 10, None, None, None, None, None) != 0

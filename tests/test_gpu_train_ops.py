@@ -225,3 +225,38 @@ def test_sgd_momentum_matches_torch():
         opt.step()
         T.sgd_momentum_(p, grad, buf, lr=0.1, momentum=0.9, first_step=(step == 0))
         assert torch.allclose(p, ref_p.detach(), rtol=1e-6, atol=1e-7), step
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_own_allreduce_peer_form_on_one_gpu(world):
+    """va_allreduce_bf16, peer-pointer form: the `world` symmetric buffers are emulated by `world` buffers on this GPU (peer
+    pointers are plain device pointers); each rank's launch reduces its slice in fp32 in rank order and writes it to every
+    buffer.  After all ranks ran, every buffer holds round_bf16(sum of the original bf16 buffers) -- bit for bit."""
+    import torch
+    from video_analytics_b200 import train_ops as T
+    g = torch.Generator().manual_seed(world)
+    n = 8 * 1024 * 37 + 8 * 5                      # not a multiple of world * threads: ragged last slice
+    bufs = [(torch.randn(n, generator=g) * (1 + r)).bfloat16().cuda() for r in range(world)]
+    want = torch.zeros(n, dtype=torch.float32, device="cuda")
+    for b in bufs:
+        want += b.float()
+    want = want.bfloat16()
+    ptrs = [b.data_ptr() for b in bufs]
+    for r in range(world):
+        T.allreduce_bf16_(ptrs, 0, world, r, n, n_ctas=3)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b, want)
+
+
+def test_own_allreduce_rejects_bad_arguments():
+    import torch
+    from video_analytics_b200 import train_ops as T
+    from video_analytics_b200._lib import VAError
+    x = torch.zeros(64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(VAError):
+        T.allreduce_bf16_([x.data_ptr()], 0, 1, 0, 60)            # not a multiple of 8 elements
+    with pytest.raises(VAError):
+        T.allreduce_bf16_([x.data_ptr()] * 3, 0, 3, 0, 64)        # peer form: 1, 2, 4 or 8 ranks
+    with pytest.raises(VAError):
+        T.allreduce_bf16_([x.data_ptr(), 0], 0, 2, 0, 64)         # NULL peer
