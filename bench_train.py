@@ -352,7 +352,7 @@ def main(args, embedded=False):
                                       f" + {tr_t.flat_grad.numel() * (2 if tr_t.grad_allreduce_dtype == 'bf16' else 4) / 1e6:.0f} MB), "
                                       + ("classifier slice launched as soon as its gradients exist" if tr_s.overlap_allreduce else
                                          (f"one collective per stream, run under the OTHER stream's forward pass (deferred update; "
-                                          f"{tr_s.reserve_sms} SMs reserved for NCCL during {tr_s.reserve_launches} layer launches)"
+                                          f"{tr_s.reserve_sms} SMs reserved for the collective during {tr_s.reserve_launches} layer launches)"
                                           + (", own two-shot all-reduce kernel over " + ("NVSwitch multicast" if tr_s._symm_use_mc else "NVLink peer pointers")
                                              if tr_s._symm is not None else ", NCCL")
                                           if tr_s.defer_update else
