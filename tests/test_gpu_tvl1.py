@@ -160,6 +160,21 @@ def test_store_straight_from_videos(tmp_path):
     assert tab.shape == (250, 20, 4) and tab[:, :, 0].min() >= m.flowx_first and tab[:, :, 0].max() < m.flowy_first + m.n_flows
 
 
+def test_more_pairs_than_scratch_slots():
+    """One call with more pairs than a launch batch holds (63 scratch slots): the batches are processed in sequence and a
+    pair's result does not depend on its batch or slot."""
+    p = flow.TVL1Params()
+    clip = flow.synthetic_clip(3, 40, 56, seed=81, channels=1)
+    pairs = [(0, 1), (1, 2), (0, 2)] * 45                     # 135 pairs: three batches
+    out, fl, its = _run(clip, p, pairs)
+    m = len(pairs)
+    u1, u2, st, qx, qy = _oracle_pair(clip[0], clip[2], p)
+    assert np.array_equal(out[2], qx) and np.array_equal(out[m + 2], qy) and list(its[2][:len(st)]) == st
+    for k in range(3, m):
+        assert np.array_equal(out[k], out[k % 3]) and np.array_equal(out[m + k], out[m + k % 3]), k
+        assert np.array_equal(fl[k], fl[k % 3]) and np.array_equal(its[k], its[k % 3]), k
+
+
 def test_parameters_and_saturation():
     """Non-default parameters (fewer levels/warps, no early stop, small bound so that the 8-bit mapping saturates)."""
     p = flow.TVL1Params(tau=0.2, lambda_=0.1, theta=0.25, nscales=3, warps=2, epsilon=0.0, iterations=40, scale_step=0.7, bound=1.0)
