@@ -270,8 +270,8 @@ va_status va_svm_fit(const double* X, const int32_t* class_index, int V, int F, 
  *   flow_f32:   optional fp32 [n][2][img_h][img_w] (x then y displacement); iterations: optional int32
  *               [n][nscales_used*warps] inner iterations run per (level, warp) in processing order (coarsest level first)
  *   workspace:  DEVICE scratch of va_tvl1_workspace_bytes(img_h, img_w, params) bytes
- * Limits (of the size the flow is computed at): W <= 704 and ceil(H/16) * W <= 5504 (the on-chip band capacity: 340x256 and 320x240 fit);
- * anything larger returns VA_ERR_UNSUPPORTED.
+ * Pyramid levels with W <= 704 and ceil(H/16) * W <= 5504 (340x256 and 320x240 frames: all levels) are solved in shared memory;
+ * larger levels run the same formulas on L2-resident fields (slower per iteration, same results); H, W <= 4096.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct va_tvl1_params {
   double tau;          /* 0.25 */

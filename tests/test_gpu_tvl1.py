@@ -209,10 +209,23 @@ def test_flow_store_feeds_the_temporal_stream():
     assert np.array_equal(fx[0].cpu().numpy(), qx) and np.array_equal(fy[0].cpu().numpy(), qy)
 
 
-def test_rejects_what_does_not_fit_on_chip():
+def test_frames_beyond_the_on_chip_capacity():
+    """288 x 400 frames: the finest pyramid level does not fit in the shared memory of a 16-CTA cluster and runs the
+    global-memory fallback kernel, the four coarser ones the on-chip kernel -- same formulas, results bit-equal to the oracle."""
+    p = flow.TVL1Params(iterations=60)                       # bounded oracle time at this size
+    clip = flow.synthetic_clip(2, 288, 400, seed=91, channels=1)
+    out, fl, its = _run(clip, p, [(0, 1), (1, 0), (0, 1)])
+    u1, u2, st, qx, qy = _oracle_pair(clip[0], clip[1], p)
+    assert list(its[0]) == st
+    assert np.array_equal(fl[0, 0], u1) and np.array_equal(fl[0, 1], u2)
+    assert np.array_equal(out[0], qx) and np.array_equal(out[3], qy)
+    assert np.array_equal(out[2], out[0]) and np.array_equal(fl[2], fl[0])
+
+
+def test_rejects_bad_arguments():
     dev = torch.device("cuda")
-    frames = torch.zeros((2, 480, 640, 1), dtype=torch.uint8, device=dev)
+    frames = torch.zeros((2, 4200, 64, 1), dtype=torch.uint8, device=dev)
     with pytest.raises(VAError):
-        flow.flow_images(frames)
+        flow.flow_images(frames)                             # beyond 4096 pixels
     with pytest.raises(VAError):
         flow.tvl1(torch.zeros(10, dtype=torch.uint8), (1, 1, 1), torch.zeros((1, 4), dtype=torch.int32), torch.zeros(10, dtype=torch.uint8))

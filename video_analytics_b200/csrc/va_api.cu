@@ -701,8 +701,7 @@ va_status va_tvl1_flow(const uint8_t* images, size_t image_bytes, int img_h, int
   if (!(d.tau > 0.0) || !(d.lambda > 0.0) || !(d.theta > 0.0) || !(d.epsilon >= 0.0) || !(d.bound > 0.0) ||
       !(d.scale_step > 0.0 && d.scale_step < 1.0) || d.nscales < 1 || d.nscales > 8 || d.warps < 1 || d.iterations < 1)
     return fail(VA_ERR_INVALID, "va_tvl1_flow: bad parameters");
-  if (fw > 704 || (size_t)((fh + 15) / 16) * fw > 5504)
-    return fail(VA_ERR_UNSUPPORTED, "va_tvl1_flow: %dx%d exceeds the on-chip band capacity (width <= 704, ceil(h/16)*w <= 5504)", fh, fw);
+  if (fw > 4096 || fh > 4096) return fail(VA_ERR_UNSUPPORTED, "va_tvl1_flow: %dx%d: flow images larger than 4096 pixels", fh, fw);
   if (va_status s = require_sm100()) return s;
   const char* e = va::tvl1_run(images, image_bytes, img_h, img_w, img_c, fh, fw, pair_table, n, d.tau, d.lambda, d.theta, d.nscales,
                                d.warps, d.epsilon, d.iterations, d.scale_step, d.bound, out_images, out_image_bytes, flow_f32,
