@@ -303,3 +303,66 @@ def test_frame_extraction_equals_the_reference(golden, tmp_path):
     assert [hashlib.sha256(np.ascontiguousarray(k).tobytes()).hexdigest() for k in kept] == man["every_7th"]["sha256"]
     with pytest.raises(ValueError):
         U.extractEveryNthFrame(str(root / "missing.avi"), 10)
+
+
+def test_index_rows_are_validated_before_upload(tmp_path):
+    """va_preprocess addresses images + id * image_bytes unchecked: rows are checked on the host against the store."""
+    lay = make_layout(3)
+    sd, td, _, _ = _datasets(tmp_path, lay)
+    import random
+    random.seed(1)
+    torch.manual_seed(1)
+    rows, _, _ = sd.sample_indices(0)
+    sd.check_rows(rows)
+    trows, _, _ = td.sample_indices(1)
+    td.check_rows(trows)
+    bad = rows.copy(); bad[0, 0] = lay.n_rgb_images
+    with pytest.raises(IndexError):
+        sd.check_rows(bad)
+    bad = rows.copy(); bad[0, 0] = -1
+    with pytest.raises(IndexError):
+        sd.check_rows(bad)
+    bad = trows.copy(); bad[3, 1] = lay.flow_shape[0] - 223          # a 224-row window starting there leaves the image
+    with pytest.raises(ValueError):
+        td.check_rows(bad)
+    bad = trows.copy(); bad[0, 2] = -1
+    with pytest.raises(ValueError):
+        td.check_rows(bad)
+    bad = rows.copy(); bad[0, 3] = 2
+    with pytest.raises(ValueError):
+        sd.check_rows(bad)
+    U.check_index_rows(np.zeros((0, 1, 4), np.int32), 0, lay.rgb_shape)        # empty tables pass
+
+
+def test_combined_model_exports_a_scikit_learn_estimator(monkeypatch):
+    """combinedModel.main dumps what the reference dumps (combinedModel.py:36): a LinearSVC that predicts like the model."""
+    from sklearn import svm
+    from video_analytics_b200.combinedModel import CombinedModel
+    monkeypatch.setattr(torch, "from_numpy", lambda a, _f=torch.from_numpy: _Host(_f(a)))
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((40, 6))
+    for n_cls, labels in ((3, np.array([4, 9, 17])), (2, np.array([5, 8]))):
+        y = labels[rng.integers(0, n_cls, 40)]
+        ref = svm.LinearSVC().fit(X, y)
+        m = CombinedModel().set_svm(ref.coef_, ref.intercept_, ref.classes_)
+        est = m.as_sklearn()
+        assert isinstance(est, svm.LinearSVC)
+        assert np.array_equal(est.coef_, ref.coef_) and np.array_equal(est.intercept_, ref.intercept_)
+        assert np.array_equal(est.classes_, ref.classes_)
+        assert np.array_equal(est.predict(X), ref.predict(X))
+        import io
+        import joblib
+        buf = io.BytesIO()
+        joblib.dump(est, buf)
+        buf.seek(0)
+        assert np.array_equal(joblib.load(buf).predict(X), ref.predict(X))
+
+
+class _Host:
+    """torch tensor stand-in whose .cuda() stays on the host (set_svm uploads its weights; no GPU in the CPU suite)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def cuda(self):
+        return self.t

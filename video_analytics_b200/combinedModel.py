@@ -80,6 +80,22 @@ class CombinedModel:
         self._b_dev = torch.from_numpy(intercept).cuda()
         return self
 
+    def as_sklearn(self):
+        """The fitted model as a scikit-learn `LinearSVC` (coef_, intercept_, classes_ set as `fit` would leave them; the
+        two-class case collapsed back to scikit-learn's single hyperplane), so that a file written by `main()` loads in a
+        consumer of the reference's `joblib.dump(linearClassifier, SVM_FILE)` (combinedModel.py:36) and `.predict`s there."""
+        if self.coef_ is None:
+            raise ops.VAError("CombinedModel: no SVM set (call fit() or set_svm() first)")
+        from sklearn import svm
+        est = svm.LinearSVC()
+        two = len(self.classes_) == 2
+        est.coef_ = np.ascontiguousarray(self.coef_[1:2] if two else self.coef_)
+        est.intercept_ = np.ascontiguousarray(self.intercept_[1:2] if two else self.intercept_)
+        est.classes_ = np.asarray(self.classes_)
+        est.n_features_in_ = int(self.coef_.shape[1])
+        est.n_iter_ = int(np.max(getattr(self, "n_iter_", 0)))
+        return est
+
     def decision_function(self, descriptors) -> torch.Tensor:
         """[V, C_svm] fp64 scores on the device for already-fused descriptors [V, 2D] (numpy or tensor), scored in fp64 on
         the fp64 values -- what `linearClassifier.predict(svmTestData)` (reference :38) sees after pandas parsed the CSVs."""
@@ -109,7 +125,7 @@ def main():
     trainX, trainY = combineDescriptors(SPATIAL_TRAIN_CSV_LOC, TEMPORAL_TRAIN_CSV_LOC)
     testX, testY = combineDescriptors(SPATIAL_TEST_CSV_LOC, TEMPORAL_TEST_CSV_LOC)
     model = CombinedModel().fit(trainX, trainY)
-    joblib.dump({"coef": model.coef_, "intercept": model.intercept_, "classes": model.classes_}, SVM_FILE)
+    joblib.dump(model.as_sklearn(), SVM_FILE)                 # reference :36: a LinearSVC object, loadable by its consumers
     preds = model.predict(testX)
     acc = sum(int(p == a) for p, a in zip(preds, testY))
     print("accuracy = %f percent" % ((acc * 100.0) / len(testY)))

@@ -23,8 +23,8 @@ import torch.nn as nn
 from . import ops
 from ._lib import VAError
 from .parameters import *  # noqa: F401,F403
-from .utils import (AverageMeter, DeviceVideoDict, SnippetBatch, checkAndMakeDirectories, makeCheckpoint,
-                    saveVideoDescriptors, savePerformance, videoInfo)
+from .utils import (AverageMeter, DeviceVideoDict, SnippetBatch, checkAndMakeDirectories, check_index_rows,
+                    makeCheckpoint, saveVideoDescriptors, savePerformance, videoInfo)
 
 
 def _read_action_labels(actionLabelLoc):
@@ -87,6 +87,10 @@ class SpatialDataset(torch.utils.data.Dataset):
         rows = np.array([[meta.rgb_first + frameName, i, j, flip]], dtype=np.int32)
         return rows, int(actionLabel), videoName
 
+    def check_rows(self, rows):
+        """Host check of table rows against this dataset's store before upload (utils.check_index_rows)."""
+        check_index_rows(rows, self.store.layout.n_rgb_images, self.store.layout.rgb_shape)
+
     # -- device side
     def preprocess_table(self, table: torch.Tensor, reference_layout: bool = False, c_pad: int = 16):
         mean, std = self.imageTransforms.norm_constants(3, 3)
@@ -95,6 +99,7 @@ class SpatialDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, index):
         rows, label, name = self.sample_indices(index)
+        self.check_rows(rows)
         table = torch.from_numpy(rows[None]).cuda()
         return self.preprocess_table(table, reference_layout=True)[0], label, name
 

@@ -15,7 +15,7 @@ from . import ops
 from ._lib import VAError
 from .parameters import *  # noqa: F401,F403
 from .spatialModel import _StreamNetwork, _read_action_labels, swap_classifier
-from .utils import videoInfo
+from .utils import check_index_rows, videoInfo
 
 
 class TemporalDataset(torch.utils.data.Dataset):
@@ -79,6 +79,10 @@ class TemporalDataset(torch.utils.data.Dataset):
         self.last_indices = dict(start=iFlowFrame, crops=crops)
         return np.array(rows, dtype=np.int32), actionLabel, videoName
 
+    def check_rows(self, rows):
+        """Host check of table rows against this dataset's store before upload (utils.check_index_rows)."""
+        check_index_rows(rows, self.store.layout.n_flow_images, self.store.layout.flow_shape)
+
     def preprocess_table(self, table: torch.Tensor, reference_layout: bool = False, c_pad: int = 32):
         mean, std = self.imageTransforms.norm_constants(self.planes, 1)
         return ops.preprocess(self.store.flow, self.store.layout.flow_shape, table, mean, std, c_pad=c_pad,
@@ -86,6 +90,7 @@ class TemporalDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, index):
         rows, label, name = self.sample_indices(index)
+        self.check_rows(rows)
         table = torch.from_numpy(rows[None]).cuda()
         return self.preprocess_table(table, reference_layout=True)[0], label, name
 

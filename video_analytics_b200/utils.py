@@ -174,6 +174,24 @@ def test_flow_starts(nFlows: int, L: int = VIDEO_INPUT_FLOW_COUNT, n: int = _P.N
 
 
 # ------------------------------------------------------------------------------------------------ loader
+def check_index_rows(rows, n_images: int, image_shape, crop: int = 224) -> None:
+    """Host-side validation of index-table rows (image id, crop top, crop left, flip) before they are uploaded: the
+    preprocess kernels address `images + id * image_bytes` unchecked (va_preprocess is not told the store's size), so an
+    id outside [0, n_images) or a crop window outside the image would read foreign memory.  The reference fails in the
+    same situations with an IOError from Image.open / a ValueError from RandomCrop."""
+    r = np.asarray(rows).reshape(-1, 4)
+    if r.size == 0:
+        return
+    h, w = int(image_shape[0]), int(image_shape[1])
+    if r[:, 0].min() < 0 or r[:, 0].max() >= n_images:
+        raise IndexError("index table: image id range [%d, %d] outside the store's %d images"
+                         % (r[:, 0].min(), r[:, 0].max(), n_images))
+    if r[:, 1].min() < 0 or r[:, 1].max() + crop > h or r[:, 2].min() < 0 or r[:, 2].max() + crop > w:
+        raise ValueError("index table: a %dx%d crop window leaves the %dx%d image" % (crop, crop, h, w))
+    if ((r[:, 3] != 0) & (r[:, 3] != 1)).any():
+        raise ValueError("index table: flip must be 0 or 1")
+
+
 class SnippetBatch:
     """A preprocessed batch resident in HBM: bf16 NHWC [B,224,224,c_pad] plus the index table that produced it."""
 
@@ -204,6 +222,7 @@ def getDataLoader(dataset, batchSize=TEMPORAL_BATCH_SIZE, nWorkers=NWORKERS_LOAD
 
     def _collate(items):
         rows = np.stack([it[0] for it in items]).astype(np.int32)
+        dataset.check_rows(rows)
         labels = torch.tensor([it[1] for it in items], dtype=torch.int64)
         names = tuple(it[2] for it in items)
         table = torch.from_numpy(rows).pin_memory().cuda(non_blocking=True)
