@@ -89,7 +89,10 @@ class SpatialDataset(torch.utils.data.Dataset):
 
     def check_rows(self, rows):
         """Host check of table rows against this dataset's store before upload (utils.check_index_rows)."""
-        check_index_rows(rows, self.store.layout.n_rgb_images, self.store.layout.rgb_shape)
+        shape = self.store.layout.rgb_shape
+        buf = getattr(self.store, "rgb", None)           # the bound that matters is the buffer the kernel will read
+        n = self.store.layout.n_rgb_images if buf is None else int(buf.numel()) // (shape[0] * shape[1] * shape[2])
+        check_index_rows(rows, n, shape)
 
     # -- device side
     def preprocess_table(self, table: torch.Tensor, reference_layout: bool = False, c_pad: int = 16):

@@ -81,7 +81,10 @@ class TemporalDataset(torch.utils.data.Dataset):
 
     def check_rows(self, rows):
         """Host check of table rows against this dataset's store before upload (utils.check_index_rows)."""
-        check_index_rows(rows, self.store.layout.n_flow_images, self.store.layout.flow_shape)
+        shape = self.store.layout.flow_shape
+        buf = getattr(self.store, "flow", None)           # the bound that matters is the buffer the kernel will read
+        n = self.store.layout.n_flow_images if buf is None else int(buf.numel()) // (shape[0] * shape[1] * shape[2])
+        check_index_rows(rows, n, shape)
 
     def preprocess_table(self, table: torch.Tensor, reference_layout: bool = False, c_pad: int = 32):
         mean, std = self.imageTransforms.norm_constants(self.planes, 1)
