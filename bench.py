@@ -610,6 +610,14 @@ def main():
         except Exception as e:      # keep the contract line alive: report why this optional leg is missing
             e2e_jpeg = {"unavailable": repr(e)}
 
+    _sd = {}
+
+    def stream_state_dict(kind):
+        """fp32 state_dict of the seed-0 torch module the handles were loaded from (built once, shared by the legs below)."""
+        if kind not in _sd:
+            _sd[kind] = (build_spatial_torch_model(C, D, seed=0) if kind == "s" else build_temporal_torch_model(C, 10, D, seed=0)).state_dict()
+        return _sd[kind]
+
     # ---- HBM-bound kernels of the path, timed alone (CUDA events, inputs >> L2): algorithmic bytes of SURVEY.md 8d
     aux = []
     if rank == 0:
@@ -653,7 +661,45 @@ def main():
                         "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": nbytes,
                         "moved_bytes_per_launch": moved, "moved_gbs": moved / (ms_k * 1e-3) / 1e9,
                         "moved_frac": moved / (ms_k * 1e-3) / 1e9 / hbm})
+        for a_ in aux[:2]:
+            a_["on_path"] = ("training loader and reference-layout __getitem__ only: the evaluation step of this line runs "
+                             "conv1_fused_kernel (next two entries), which never materialises the padded tensor")
         del fd, fs, fout, fout2
+        # the default front end of the evaluation path (va_forward_store): index-table gather + normalise + conv1_1 in one
+        # kernel.  Algorithmic bytes per snippet = the cropped u8 it reads (150 528 / 1 003 520 B) + the bf16
+        # [224,224,64] layer output it writes (6 422 528 B) -- the write dominates, so the bound is HBM, not the tensor pipe
+        try:
+            t1s, t1t = tabs[0]
+            wsd = {"s": stream_state_dict("s"), "t": stream_state_dict("t")}
+            for name, key, images, shape, tab, mean, std, rd in (
+                    ("conv1_fused_kernel (RGB: gather + normalise + conv1_1 + ReLU, u8 store -> bf16 NHWC 64ch)", "s", store.rgb,
+                     layout.rgb_shape, t1s, ev.mean_s, ev.std_s, 150_528),
+                    ("conv1_fused_kernel (flow stack: 20 planes gathered per snippet, same epilogue)", "t", store.flow,
+                     layout.flow_shape, t1t, ev.mean_t, ev.std_t, 1_003_520)):
+                w1 = wsd[key]["features.0.weight"].float().to(dev).contiguous()
+                b1 = wsd[key]["features.0.bias"].float().to(dev).contiguous()
+                ms_c = timed(lambda: ops.conv1_fused(images, shape, tab, mean, std, w1, b1))
+                nb = (rd + px * 64 * 2) * tab.shape[0]
+                gbs = nb / (ms_c * 1e-3) / 1e9
+                aux.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                            "ms_per_launch": ms_c, "snippets_per_launch": int(tab.shape[0]), "algorithmic_bytes_per_launch": nb,
+                            "moved_bytes_per_launch": nb, "moved_gbs": gbs, "moved_frac": gbs / hbm,
+                            "write_share_of_bytes": px * 64 * 2 / (rd + px * 64 * 2),
+                            "on_path": "evaluation (TwoStreamEvaluator default front end)"})
+            # `peak` above is the read+write COPY figure; a stream of stores alone gets far less of it on this part
+            # (tools/bench_write_bw.py, profiles/r02_hbm_write_only_bw.json: memset and a fill kernel both 3.86 TB/s beside a
+            # 6.50 TB/s copy).  Measured live on a buffer the size of one launch's output, so the store-dominated entries
+            # can be read against the ceiling that applies to them.
+            wbuf = torch.empty(250 * px * 64, dtype=torch.bfloat16, device=dev)
+            ms_w = timed(lambda: wbuf.zero_())
+            w_gbs = wbuf.numel() * 2 / (ms_w * 1e-3) / 1e9
+            del wbuf
+            for a_ in aux[-2:]:
+                a_["write_only_peak"] = w_gbs
+                a_["frac_of_write_only_peak"] = a_["achieved"] / w_gbs
+            del w1, b1
+        except Exception as e:      # an evidence entry, not the contract: say why it is missing
+            aux.append({"kernel": "conv1_fused_kernel", "unavailable": repr(e)})
         jpeg_line = jpeg_decode_measurement(store, layout, dev)
 
     # ---- the reference's CPU path beside it (rank 0, N = 1): the oracle port on the box's host cores, bounded sample
@@ -675,7 +721,7 @@ def main():
     legs = {}
     if args.legs:
         import bench_legs
-        sd_s, sd_t = build_spatial_torch_model(C, D, seed=0).state_dict(), build_temporal_torch_model(C, 10, D, seed=0).state_dict()
+        sd_s, sd_t = stream_state_dict("s"), stream_state_dict("t")
         for key, fn in (
                 ("small", (lambda: bench_legs.small_batch_legs(spatial, temporal, ev, store, layout)) if world == 1 else None),
                 ("parity", (lambda: bench_legs.parity_leg(spatial, temporal, ev, store, layout, sd_s, sd_t,
